@@ -1,0 +1,204 @@
+/* kmldpc_b200 — C ABI of the B200-native (sm_100a) Monte-Carlo link path of trganda/kmldpc.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types.  Every entry point cites the
+ * reference interface it replaces (paths relative to the reference's kmldpc/ directory).  All functions return 0 on
+ * success or a negative kml_status; kml_last_error() gives the message.  No exceptions, no exit() (the reference
+ * exit(-1)s on file errors, lib/lab/src/binaryldpccodec.cc:77-80).  There is NO CPU fallback: kml_create() fails
+ * with KML_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Layout conventions: batch-major, frame-contiguous; complex numbers interleaved (re, im) float32; bits as int32
+ * (0/1) in the stage entry points — exactly the reference's `int *uu / *cc` — and bit-packed uint32 words
+ * (bit t of a frame = word t/32, bit t%32) where a name says `_packed`.  Pointers are HOST pointers unless the
+ * function name ends in `_dev`; `_dev` variants take device pointers plus a cudaStream_t passed as void*.
+ * A context is owned by one host thread.
+ */
+#ifndef KMLDPC_B200_H
+#define KMLDPC_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  KML_OK = 0,
+  KML_ERR_ARG = -1,     /* bad argument / unsupported configuration */
+  KML_ERR_IO = -2,      /* file could not be opened or parsed */
+  KML_ERR_CUDA = -3,    /* CUDA runtime error or no usable device */
+  KML_ERR_STATE = -4,   /* call order / capacity problem */
+} kml_status;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-side code / constellation descriptions (immutable once built; borrowed by kml_create, copied to the device)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* LDPC code after the reference's Gaussian elimination + column permutation.
+ * Replaces: BinaryLDPCCodec::BinaryLDPCCodec(toml) + SystemMatrixH (lib/lab/src/binaryldpccodec.cc:62-129,346-493)
+ *           Binary5GLDPCCodec ctor + SystemMatrixH (lib/lab/src/binary5gldpccodec.cc:12-80,240-391). */
+typedef struct kml_code {
+  int32_t n_rows;        /* M: checks */
+  int32_t n_graph;       /* columns of H (variables in the Tanner graph) */
+  int32_t n_tx;          /* transmitted bits per frame (= n_graph - puncture) */
+  int32_t k;             /* information bits: code_dim() */
+  int32_t n_chk;         /* rank found by the elimination: code_chk_ */
+  int32_t puncture;      /* 2Z leading graph columns that are never transmitted (5G), else 0 */
+  int32_t info_offset;   /* uu_hat = cc_hat[info_offset .. info_offset+k): code_chk_ (PEG) or 0 (5G) */
+  int32_t n_edges;       /* E */
+  int32_t is_5g;
+  int32_t encoder_active;/* [ldpc] active */
+  int32_t enc_words;     /* uint32 words per row of enc_rows = ceil(k/32) */
+  int32_t reserved;
+  const int32_t *row_ptr;   /* [M+1]  CSR of the PERMUTED H, columns ascending within a row */
+  const int32_t *col_idx;   /* [E] */
+  const int32_t *perm;      /* [n_graph] new column j = original column perm[j] (tempP) */
+  const uint32_t *enc_rows; /* [n_chk][enc_words] parity part of the reduced matrix: bit j of row t multiplies
+                               info bit j; parity bit t = XOR_j u_j & enc[t][j].  NULL when !encoder_active */
+} kml_code;
+
+/* Parses an H file ("num_of_row--num_of_col--rank_of_H" format) and runs the bit-packed elimination.
+ * The result is identical (permutation, reduced matrix, graph) to the reference's byte-matrix SystemMatrixH. */
+int kml_code_load(const char *h_file, int is_5g, int encoder_active, kml_code **out);
+void kml_code_free(kml_code *code);
+
+/* Constellation. Replaces Modem::init (lib/lab/src/modem.cc:87-129): points scaled to unit mean energy;
+ * the label of point i is i, MSB first. */
+typedef struct kml_modem {
+  int32_t bits_per_symbol; /* m */
+  int32_t n_points;        /* Q = 2^m */
+  const double *points;    /* [Q][2] (re, im) after normalisation */
+} kml_modem;
+int kml_modem_load(const char *modem_file, kml_modem **out);
+void kml_modem_free(kml_modem *modem);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct kml_opts {
+  int32_t max_iter;      /* [ldpc] max_iter (binaryldpccodec.cc:70) */
+  int32_t known_h;       /* [decoder] true_h_arg (simulator.cc:14-15) */
+  int32_t metric_type;   /* [xcodec] metric_type: 0 hard syndrome weight, 1 soft syndrome (kmcodec.cc:146-155) */
+  int32_t metric_iter;   /* [xcodec] metric_iter (kmcodec.cc:25) */
+  int32_t kmeans_iter;   /* 20 (simulator.cc:140) */
+  int32_t early_exit;    /* 1 = reference semantics (stop at the first zero syndrome, binaryldpccodec.cc:231);
+                            0 = fixed-iteration timing mode: all max_iter iterations are executed but the decision
+                            and return value are latched at the first zero syndrome, so RESULTS ARE IDENTICAL */
+  int32_t max_batch;     /* frames per launch the workspaces are sized for (0 = default 16384) */
+  int32_t reserved;
+} kml_opts;
+
+typedef struct kml_ctx kml_ctx;
+
+int kml_create(kml_ctx **out, int device, const kml_code *code, const kml_modem *modem, const kml_opts *opts);
+void kml_destroy(kml_ctx *ctx);
+const char *kml_last_error(const kml_ctx *ctx);  /* ctx may be NULL: message of the last failed create/load */
+int kml_set_early_exit(kml_ctx *ctx, int early_exit);
+/* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
+int kml_info(const kml_ctx *ctx, int32_t info[8]);
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t kml_launch_count(const kml_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage entry points (host buffers; parity tests and the standalone roofline runs call these)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* A2  BinaryLDPCCodec::Encoder (binaryldpccodec.cc:144-162) / Binary5GLDPCCodec::Encoder (binary5gldpccodec.cc:86-109)
+ *     u[B][k] -> c[B][n_tx] (int32 0/1).  With encoder_active = 0 the reference zeroes BOTH u and c; here c = 0. */
+int kml_encode(kml_ctx *ctx, int B, const int32_t *u, int32_t *c);
+
+/* A1+A3+A5  SourceSink::GetBitStr (sourcesink.cc:5-9), the h draw (simulator.cc:120-128) and
+ *     ModemLinearSystem::PartitionModemLSystem (modemlinearsystem.cc:30-48) with the LCG replaced by Philox4x32-10
+ *     keyed by `seed`, counter = (stream, frame index, sample).  Frame indices are frame0 .. frame0+B-1, so results
+ *     do not depend on batch size or GPU count.  Outputs (any may be NULL): u[B][k], c[B][n_tx] int32,
+ *     h[B][2], y[B][n_sym][2] float32.  sigma^2 = 10^(-snr_db/10) (simulator.cc:74-77). */
+int kml_generate(kml_ctx *ctx, int B, double snr_db, uint64_t seed, uint64_t frame0, int32_t *u, int32_t *c,
+                 float *h, float *y);
+
+/* A4+A5 with caller-supplied bits, fading and noise (deterministic: used to replay reference frames):
+ *     y = h*x(c) + (sigma/sqrt2)*noise, noise[B][n_sym][2] standard normals or NULL for no noise. */
+int kml_modulate(kml_ctx *ctx, int B, const int32_t *c, const float *h, const float *noise, double sigma, float *y);
+
+/* A6  kmldpc::KMeans::Run + clusters()[0]/constellations[0] (src/kmeans.cc:15-84, simulator.cc:134-145),
+ *     compiled semantics (cumulative sums, cluster 0 anchor).  y[B][n_sym][2] -> hhat[B][2]; passes[B] (may be NULL)
+ *     = number of assignment passes executed. */
+int kml_kmeans(kml_ctx *ctx, int B, const float *y, float *hhat, int32_t *passes);
+
+/* A7+A8  ModemLinearSystem::DeMapping (modemlinearsystem.cc:51-98, modem.cc:23-79) with all bit priors 0.5
+ *     (kmcodec.cc:92-103).  One channel estimate per frame: h[B][2].  Output llr[B][n_tx] = ln(P(bit=0)/P(bit=1))
+ *     with the reference's clipping order, i.e. |llr| <= ln((1-1e-12)/1e-12). */
+int kml_demap(kml_ctx *ctx, int B, const float *y, const float *h, double var, float *llr);
+
+/* A9  KmCodec::GetMetrics / Metric / GetParityCheck + first argmin (kmcodec.cc:54-66,105-163): the four candidates
+ *     hhat*exp(j*(kPi/2)*k).  Outputs metric[B][4] (float: syndrome weights, or |sum ln syndrom_soft|) and kstar[B]. */
+int kml_resolve(kml_ctx *ctx, int B, const float *y, const float *hhat, double var, float *metric, int32_t *kstar);
+
+/* A10 BinaryLDPCCodec::Decoder / Binary5GLDPCCodec::Decoder (binaryldpccodec.cc:165-278, binary5gldpccodec.cc:112-232).
+ *     llr[B][n_tx] -> cc_hat[B][n_graph], uu_hat[B][k] (int32, either may be NULL), ret[B] = iter + (iter < max_iter)
+ *     exactly like the reference's return value.  iter_count as in Decoder(M2V, uu_hat, iter_count). */
+int kml_decode(kml_ctx *ctx, int B, const float *llr, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret);
+
+/* KmCodec::Decoder (kmcodec.cc:54-72) preceded by the k-means block of Simulator::run_blocks (simulator.cc:131-148):
+ *     the whole receiver for B frames.  y[B][n_sym][2]; true_h[B][2] is read only when opts.known_h.
+ *     Outputs (any may be NULL): uu_hat_packed[B][ceil(k/32)], hhat[B][2], kstar[B], ret[B]. */
+int kml_receive(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                float *hhat, int32_t *kstar, int32_t *ret);
+
+/* A11 SourceSink::CntErr (sourcesink.cc:29-47) for B frames: counters[4] += {tot_blk, err_blk, tot_bit, err_bit}
+ *     (64-bit; the reference's 32-bit counters wrap at 3.7 M frames).  u_packed / uu_hat_packed [B][ceil(k/32)]. */
+int kml_count_errors(kml_ctx *ctx, int B, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
+                     uint64_t counters[4]);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused path: the body of Simulator::run / run_blocks (simulator.cc:70-168) for one SNR point
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Runs frames [frame_begin, frame_begin+frame_count) of SNR point `snr_db` entirely on the device (Philox bits ->
+ * encode -> map -> channel -> k-means -> resolve -> demap -> decode -> count) in batches of max_batch and ADDS to
+ * counters[4] = {tot_blk, err_blk, tot_bit, err_bit}.  Stops early after the batch in which err_blk (including the
+ * caller's incoming counters[1]) reaches max_err_blk (0 = never), mirroring simulator.cc:117 with batch granularity.
+ * iters_sum (may be NULL) accumulates the decoder iterations executed. */
+int kml_simulate(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
+                 uint64_t max_err_blk, uint64_t counters[4], uint64_t *iters_sum);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Device-pointer variants (inputs already resident in HBM; asynchronous on `stream`)
+ * ---------------------------------------------------------------------------------------------------------- */
+int kml_generate_dev(kml_ctx *ctx, int B, double snr_db, uint64_t seed, uint64_t frame0, uint32_t *u_packed,
+                     float *h, float *y, void *stream);
+int kml_kmeans_dev(kml_ctx *ctx, int B, const float *y, float *hhat, int32_t *passes, void *stream);
+int kml_receive_dev(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                    int32_t *ret, void *stream);
+/* llr/lr in HBM -> packed decisions in HBM.  in_is_lr = 1 when the input already holds likelihood ratios P0/P1. */
+int kml_decode_dev(kml_ctx *ctx, int B, const float *llr, int in_is_lr, int iter_count, uint32_t *cc_hat_packed,
+                   int32_t *ret, void *stream);
+/* counters_dev: 4 x uint64 in device memory, accumulated with atomics. */
+int kml_count_errors_dev(kml_ctx *ctx, int B, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
+                         uint64_t *counters_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Sweep driver: Simulator::Simulator + Simulator::Simulate (src/simulator.cc:3-67) on top of kml_simulate
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct kml_sweep_cfg {
+  double min_snr, max_snr, step_snr;                 /* [range] */
+  uint64_t max_err_blk, max_num_blk;                 /* [range] maximum_error_number / maximum_block_number */
+  int32_t known_h, is_5g, metric_type, metric_iter;  /* [decoder] / [xcodec] */
+  int32_t max_iter, encoder_active;                  /* [ldpc] */
+  int32_t histogram_enable, reserved;                /* [histogram] (unsupported: must be 0) */
+  char matrix_file[512];                             /* [ldpc] matrix_file */
+  char modem_file[512];                              /* [modem] modem_file */
+  /* optional [gpu] table (ignored by the reference binary) */
+  uint64_t seed;
+  int32_t n_gpus, max_batch, early_exit, reserved2;
+} kml_sweep_cfg;
+
+/* Minimal TOML reader for exactly the keys above (the reference parses the same file with toml11, kmldpc.cpp:29-31). */
+int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg);
+/* Runs the sweep on n_gpus devices (one host thread per GPU, SNR points x frame ranges sharded, counters summed on the
+ * host) and fills ber[n_points], fer[n_points], counters[n_points][4].  data_dir is prepended to relative file names.
+ * log_cb (may be NULL) receives the reference-format lines ("SNR = … Total blk = …", "BER Result", …). */
+int kml_sweep_points(const kml_sweep_cfg *cfg);
+int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
+                  void (*log_cb)(const char *line, void *user), void *user);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMLDPC_B200_H */

@@ -1,0 +1,339 @@
+// Flooding sum-product LDPC decoder for sm_100a — the hot kernel of the link path.
+//
+// Replaces BinaryLDPCCodec::Decoder (lib/lab/src/binaryldpccodec.cc:165-278) and Binary5GLDPCCodec::Decoder
+// (lib/lab/src/binary5gldpccodec.cc:112-232): same schedule (variable phase → hard decision → syndrome test →
+// check phase), same clipping of check messages to [1e-12, 1-1e-12], same return value.
+//
+// Number representation (fp32, chosen so that no quantity the reference keeps in fp64 is lost):
+//   * check→variable message: likelihood ratio  x = P0/P1  in [1e-12, 1e12]  (the clipped pair (c2v0, 1-c2v0));
+//     variable nodes multiply ratios: extrinsic_e = L_ch * prod_{e' != e} x_e'  (reference: alpha/beta products with
+//     per-step renormalisation, which cancels in the ratio).
+//   * variable→check message: (hard bit h, small probability s <= 0.5): P(bit = h) = 1 - s.  s is computed directly
+//     as min(x,1)/(1+x), so probabilities as small as 1e-36 keep full relative precision — the fp32 analogue of the
+//     reference carrying both members of the pair in fp64.  A word packs s (bit 30 of any float < 2 is 0), the
+//     extrinsic hard bit (bit 31) and the POSTERIOR hard decision of the variable (bit 30), so the check phase can
+//     evaluate the syndrome of the current decisions without a second gather.
+//   * check node: the reference's 2-state trellis is, in this representation, s_ab = s_a + s_b - 2 s_a s_b on the small
+//     probabilities (all terms positive → no cancellation) and XOR on the hard bits; forward/backward partial
+//     combinations give every extrinsic output in 3(d-2) combines.
+//
+// One CTA decodes one frame at a time (persistent CTAs, dynamic frame queue).  Per iteration and edge the kernel makes
+// 4 shared-memory word accesses (16 B), 2 MUFU.RCP and ~27 issue slots; nothing but the channel ratios (4 B/variable,
+// coalesced) and the packed decisions (1 bit/variable) touches HBM.
+#include <cstdio>
+
+#include "kml_internal.h"
+#include "kml_kernels.cuh"
+
+namespace kml {
+namespace {
+
+constexpr float kClampLo = 1.0e-36f, kClampHi = 1.0e36f;
+constexpr float kLlrClip = 27.631021f;  // ln((1-1e-12)/1e-12)
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// s_ab = s_a + s_b - 2 s_a s_b
+__device__ __forceinline__ float sp_combine(float a, float b) { return fmaf(-2.0f * a, b, a + b); }
+// same with t_b = 1 - 2 s_b precomputed
+__device__ __forceinline__ float sp_chain(float acc, float s, float t) { return fmaf(acc, t, s); }
+
+__device__ __forceinline__ uint32_t v2c_word(float ext, uint32_t post_bit) {
+  // ext = P0/P1 of the extrinsic.  hard = 1 when P1 > P0 ; s = min(P0, P1) = min(ext, 1) / (1 + ext)
+  const float s = fminf(ext, 1.0f) * rcp_approx(1.0f + ext);
+  return __float_as_uint(s) | (ext < 1.0f ? 0x80000000u : 0u) | (post_bit << 30);
+}
+
+__device__ __forceinline__ float c2v_ratio(float s, uint32_t hard) {
+  // clip of c2v0 to [1e-12, 1-1e-12] (binaryldpccodec.cc:259-263) acts on the small side only
+  s = fmaxf(s, kSmallProbF);
+  const float big = 1.0f - s;
+  const float num = hard ? s : big, den = hard ? big : s;
+  return num * rcp_approx(den);
+}
+
+__device__ __forceinline__ float load_channel_ratio(const float *in, int idx, int in_is_lr) {
+  float v = __ldg(in + idx);
+  if (!in_is_lr) v = __expf(fminf(fmaxf(v, -kLlrClip), kLlrClip));
+  return fminf(fmaxf(v, kLrMin), kLrMax);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (3,6)-regular codes (PEG2304, PEG8064): N = VPT * T variables, M = CPT * T checks, everything unrolled,
+// edge addresses and channel ratios resident in registers.
+// ---------------------------------------------------------------------------------------------------------------
+template <int VPT, int CPT>
+__global__ void __launch_bounds__(VPT == 6 ? 384 : 672, VPT == 6 ? 3 : 1) bp_regular_kernel(const DecParams p) {
+  extern __shared__ uint32_t msg[];
+  __shared__ int s_frame;
+  const int T = blockDim.x, tid = threadIdx.x;
+  const int mpad = p.t.m_pad;
+
+  uint32_t va[VPT][3];
+#pragma unroll
+  for (int j = 0; j < VPT; j++) {
+    const int v = j * T + tid;
+#pragma unroll
+    for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[v * 3 + k];
+  }
+
+  while (true) {
+    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const int f = s_frame;
+    if (f >= p.B) break;
+    const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
+    float ch[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; j++) ch[j] = load_channel_ratio(in, j * T + tid, p.in_is_lr);
+    for (int i = tid; i < 6 * mpad; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
+    __syncthreads();
+
+    uint32_t bits = 0, latched_bits = 0;
+    int ret = p.iters + (p.iters < p.max_iter);
+    bool latched = false;
+    float soft = 0.0f, soft_out = 0.0f;
+    for (int t = 0; t < p.iters; t++) {
+      // ---- variable nodes (binaryldpccodec.cc:177-212)
+      bits = 0;
+#pragma unroll
+      for (int j = 0; j < VPT; j++) {
+        const float x0 = __uint_as_float(msg[va[j][0]]);
+        const float x1 = __uint_as_float(msg[va[j][1]]);
+        const float x2 = __uint_as_float(msg[va[j][2]]);
+        const float a = ch[j] * x0, b = ch[j] * x1;
+        const float e2 = a * x1, e1 = a * x2, e0 = b * x2;
+        const float post = e2 * x2;
+        const uint32_t bit = (post > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
+        bits |= bit << j;
+        msg[va[j][0]] = v2c_word(e0, bit);
+        msg[va[j][1]] = v2c_word(e1, bit);
+        msg[va[j][2]] = v2c_word(e2, bit);
+      }
+      __syncthreads();
+      // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
+      int fail = 0;
+      const float soft_before = soft;  // syndrom_soft_ as the reference holds it when it leaves at this iteration
+      soft = 0.0f;
+#pragma unroll
+      for (int j = 0; j < CPT; j++) {
+        const int slot = j * T + tid;
+        uint32_t w[6];
+        float s[6], tt[6];
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          w[k] = msg[k * mpad + slot];
+          x ^= w[k];
+          s[k] = __uint_as_float(w[k] & 0x3fffffffu);
+          tt[k] = fmaf(-2.0f, s[k], 1.0f);
+        }
+        fail |= (int)((x >> 30) & 1u);
+        float pre[6], suf[6];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}, suf[k] = s_k ⊕ … ⊕ s_5
+        pre[1] = s[0];
+#pragma unroll
+        for (int k = 2; k < 6; k++) pre[k] = sp_chain(pre[k - 1], s[k - 1], tt[k - 1]);
+        suf[5] = s[5];
+#pragma unroll
+        for (int k = 4; k >= 1; k--) suf[k] = sp_chain(suf[k + 1], s[k], tt[k]);
+        float so[6];
+        so[0] = suf[1];
+        so[5] = pre[5];
+#pragma unroll
+        for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
+#pragma unroll
+        for (int k = 0; k < 6; k++)
+          msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], ((x ^ w[k]) >> 31) & 1u));
+        if (p.out_soft) {  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
+          const float sall = sp_chain(pre[5], s[5], tt[5]);
+          soft += __logf((x >> 31) ? sall : 1.0f - sall);
+        }
+      }
+      const int any_fail = __syncthreads_or(fail);
+      if (!any_fail && !latched) {
+        latched = true;
+        latched_bits = bits;
+        soft_out = soft_before;
+        ret = t + (t < p.max_iter);
+        if (p.early_exit) break;  // the reference leaves BEFORE the check phase; its c2v are never read again
+      }
+    }
+    if (!latched) {
+      latched_bits = bits;
+      soft_out = soft;
+    }
+    const int lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < VPT; j++) {
+      const uint32_t word = __ballot_sync(0xffffffffu, (latched_bits >> j) & 1u);
+      if (lane == 0) p.out_bits[(size_t)f * p.words_n + ((j * T + tid) >> 5)] = word;
+    }
+    if (tid == 0) p.out_ret[f] = ret;
+    if (p.out_soft) {
+      // NOTE: when the reference leaves at t = 0 its syndrom_soft_ is stale (left over from the previous call);
+      // here that case reports 0.
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
+      if (lane == 0) atomicAdd(p.out_soft + f, soft_out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Any Tanner graph with column degree <= DV and row degree <= DC (5G BG2, irregular codes, odd sizes).
+// Runtime loops over the thread's variables / row slots, degree tables and address lists through the read-only
+// path, channel ratios staged in shared memory, clamped prefix/suffix products in the variable nodes.
+// ---------------------------------------------------------------------------------------------------------------
+template <int DV, int DC>
+__global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
+  extern __shared__ uint32_t smem[];
+  __shared__ int s_frame;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+  const int mpad = p.t.m_pad, n = p.t.n, dcm = p.t.dc_max;
+  uint32_t *msg = smem;                                  // [dc_max * m_pad]
+  float *chan = reinterpret_cast<float *>(smem + dcm * mpad);  // [n]
+  uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);      // [2][words_n] decisions, double buffered
+  const int n_round = (n + 31) & ~31;
+
+  while (true) {
+    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const int f = s_frame;
+    if (f >= p.B) break;
+    const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
+    for (int v = tid; v < n; v += T)  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
+      chan[v] = v < p.t.punct ? 1.0f : load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
+    for (int i = tid; i < dcm * mpad; i += T) msg[i] = 0x3f800000u;
+    __syncthreads();
+
+    int ret = p.iters + (p.iters < p.max_iter);
+    bool latched = false;
+    int last_t = 0;
+    float soft = 0.0f, soft_out = 0.0f;
+    for (int t = 0; t < p.iters; t++) {
+      last_t = t;
+      uint32_t *dcur = dec + (t & 1) * p.words_n;
+      for (int v = tid; v < n_round; v += T) {
+        uint32_t bit = 0;
+        if (v < n) {
+          const int d = __ldg(p.t.vn_deg + v);
+          const uint16_t *ad = p.t.vn_addr + (size_t)v * p.t.dv_max;
+          uint32_t a[DV];
+          float x[DV];
+#pragma unroll
+          for (int k = 0; k < DV; k++) {
+            a[k] = k < d ? __ldg(ad + k) : 0u;
+            x[k] = k < d ? __uint_as_float(msg[a[k]]) : 1.0f;
+          }
+          float pre[DV + 1], suf[DV + 1];
+          pre[0] = chan[v];
+#pragma unroll
+          for (int k = 0; k < DV; k++) pre[k + 1] = fminf(fmaxf(pre[k] * x[k], kClampLo), kClampHi);
+          suf[DV] = 1.0f;
+#pragma unroll
+          for (int k = DV - 1; k >= 0; k--) suf[k] = fminf(fmaxf(suf[k + 1] * x[k], kClampLo), kClampHi);
+          bit = (pre[DV] > 1.0f) ? 0u : 1u;
+#pragma unroll
+          for (int k = 0; k < DV; k++)
+            if (k < d) msg[a[k]] = v2c_word(fminf(fmaxf(pre[k] * suf[k + 1], kClampLo), kClampHi), bit);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == 0) dcur[v >> 5] = word;
+      }
+      __syncthreads();
+      int fail = 0;
+      const float soft_before = soft;
+      soft = 0.0f;
+      for (int slot = tid; slot < mpad; slot += T) {
+        const int d = __ldg(p.t.cn_deg + slot);
+        if (d == 0) continue;
+        uint32_t w[DC];
+        float s[DC], tt[DC];
+        uint32_t x = 0;
+#pragma unroll
+        for (int k = 0; k < DC; k++) {
+          w[k] = k < d ? msg[k * mpad + slot] : 0u;
+          x ^= w[k];
+          s[k] = __uint_as_float(w[k] & 0x3fffffffu);  // s = 0 is the neutral element
+          tt[k] = fmaf(-2.0f, s[k], 1.0f);
+        }
+        fail |= (int)((x >> 30) & 1u);
+        float pre[DC + 1], suf[DC + 1];
+        pre[0] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DC; k++) pre[k + 1] = sp_chain(pre[k], s[k], tt[k]);
+        suf[DC] = 0.0f;
+#pragma unroll
+        for (int k = DC - 1; k >= 0; k--) suf[k] = sp_chain(suf[k + 1], s[k], tt[k]);
+#pragma unroll
+        for (int k = 0; k < DC; k++)
+          if (k < d)
+            msg[k * mpad + slot] = __float_as_uint(c2v_ratio(sp_combine(pre[k], suf[k + 1]), ((x ^ w[k]) >> 31) & 1u));
+        if (p.out_soft) soft += __logf((x >> 31) ? pre[DC] : 1.0f - pre[DC]);
+      }
+      const int any_fail = __syncthreads_or(fail);
+      if (!any_fail && !latched) {
+        latched = true;
+        soft_out = soft_before;
+        ret = t + (t < p.max_iter);
+        for (int w = tid; w < p.words_n; w += T) p.out_bits[(size_t)f * p.words_n + w] = dcur[w];
+        if (p.early_exit) break;
+      }
+    }
+    if (!latched) {
+      soft_out = soft;
+      const uint32_t *dl = dec + (last_t & 1) * p.words_n;
+      for (int w = tid; w < p.words_n; w += T) p.out_bits[(size_t)f * p.words_n + w] = dl[w];
+    }
+    if (tid == 0) p.out_ret[f] = ret;
+    if (p.out_soft) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
+      if (lane == 0) atomicAdd(p.out_soft + f, soft_out);
+    }
+  }
+}
+
+typedef void (*dec_kernel_t)(const DecParams);
+
+dec_kernel_t kernel_of(DecKernelKind k) {
+  switch (k) {
+    case DEC_REG_6_3: return bp_regular_kernel<6, 3>;
+    case DEC_REG_12_6: return bp_regular_kernel<12, 6>;
+    case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
+    case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
+    case DEC_GEN_16_32: return bp_generic_kernel<16, 32>;
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+cudaError_t dec_prepare(DecLaunch &l) {
+  dec_kernel_t k = kernel_of(l.kind);
+  if (!k) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
+  if (e != cudaSuccess) return e;
+  int n = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.threads, l.smem_bytes);
+  if (e != cudaSuccess) return e;
+  if (n < 1) return cudaErrorLaunchOutOfResources;
+  l.ctas_per_sm = n;
+  return cudaSuccess;
+}
+
+cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), s);
+  if (e != cudaSuccess) return e;
+  int grid = num_sms * l.ctas_per_sm;
+  if (grid > p.B) grid = p.B;
+  if (grid < 1) return cudaSuccess;
+  kernel_of(l.kind)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace kml

@@ -1,0 +1,725 @@
+// C ABI of libkmldpc_b200.so: context, stage entry points, the chained receiver and the fused simulate loop.
+// See include/kmldpc_b200.h for the contract and the reference functions each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kml_internal.h"
+#include "kml_kernels.cuh"
+
+using namespace kml;
+
+namespace {
+
+template <class T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    n = count;
+    return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+};
+
+// Work space of one in-flight batch.  Two lanes let copies of one batch overlap kernels of the other.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  DevBuf<uint32_t> u_packed, c_packed, uu_hat_packed, cc_hat_packed;
+  DevBuf<float2> h, y, hhat, noise;
+  DevBuf<float> lr, metric, soft, llr_io;
+  DevBuf<int32_t> kstar, ret, passes, bits_io;
+  DevBuf<unsigned int> work_counter;
+};
+
+}  // namespace
+
+struct kml_ctx {
+  int device = 0, num_sms = 148;
+  // code / modem
+  int M = 0, N = 0, n_tx = 0, K = 0, n_chk = 0, punct = 0, info_offset = 0, E = 0, is_5g = 0, active = 0;
+  int k_words = 0, tx_words = 0, words_n = 0, bits = 0, Q = 0, n_sym = 0;
+  kml_opts opts{};
+  int max_batch = 0;
+  float2 rot[4];
+  // device tables
+  DevBuf<uint32_t> enc_t;
+  DevBuf<float2> points;
+  DevBuf<int32_t> row_ptr, col_idx;
+  DevBuf<uint16_t> vn_addr;
+  DevBuf<uint8_t> vn_deg, cn_deg;
+  DecTables dt{};
+  DecLaunch dl{};
+  Lane lane[2];
+  DevBuf<unsigned long long> counters;  // 5 x u64
+  unsigned long long *h_counters = nullptr;  // pinned
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+#define KML_CUDA(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                          \
+      return KML_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+#define KML_LAUNCH(ctx, expr)   \
+  do {                          \
+    KML_CUDA(ctx, expr);        \
+    (ctx)->launches++;          \
+  } while (0)
+
+int fail_arg(kml_ctx *ctx, const char *msg) {
+  if (ctx) ctx->err = msg;
+  else set_global_error(msg);
+  return KML_ERR_ARG;
+}
+
+GenParams gen_params(const kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0) {
+  GenParams g{};
+  g.B = B; g.k = c->K; g.k_words = c->k_words; g.n_tx = c->n_tx; g.tx_words = c->tx_words; g.n_chk = c->n_chk;
+  g.punct = c->punct; g.is_5g = c->is_5g; g.encoder_active = c->active;
+  g.bits_per_symbol = c->bits; g.n_sym = c->n_sym; g.q = c->Q;
+  g.seed = seed; g.frame0 = frame0;
+  const double var = std::pow(10.0, -0.1 * snr_db);  // simulator.cc:74-77
+  g.sigma_over_sqrt2 = (float)(std::sqrt(var) / 1.4142135623730950488016);
+  g.enc_t = c->enc_t.p;
+  g.points = c->points.p;
+  return g;
+}
+
+int alloc_lane(kml_ctx *c, Lane &l) {
+  const size_t B = (size_t)c->max_batch;
+  KML_CUDA(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  KML_CUDA(c, l.u_packed.alloc(B * c->k_words));
+  KML_CUDA(c, l.c_packed.alloc(B * c->tx_words));
+  KML_CUDA(c, l.uu_hat_packed.alloc(B * c->k_words));
+  KML_CUDA(c, l.cc_hat_packed.alloc(4 * B * c->words_n));
+  KML_CUDA(c, l.h.alloc(B));
+  KML_CUDA(c, l.y.alloc(B * c->n_sym));
+  KML_CUDA(c, l.hhat.alloc(B));
+  KML_CUDA(c, l.lr.alloc(4 * B * c->n_tx));
+  KML_CUDA(c, l.metric.alloc(4 * B));
+  KML_CUDA(c, l.soft.alloc(4 * B));
+  KML_CUDA(c, l.kstar.alloc(B));
+  KML_CUDA(c, l.ret.alloc(4 * B));
+  KML_CUDA(c, l.passes.alloc(B));
+  KML_CUDA(c, l.work_counter.alloc(1));
+  return KML_OK;
+}
+
+void free_lane(Lane &l) {
+  l.u_packed.release(); l.c_packed.release(); l.uu_hat_packed.release(); l.cc_hat_packed.release();
+  l.h.release(); l.y.release(); l.hhat.release(); l.noise.release(); l.lr.release(); l.metric.release();
+  l.soft.release(); l.llr_io.release(); l.kstar.release(); l.ret.release(); l.passes.release(); l.bits_io.release();
+  l.work_counter.release();
+  if (l.stream) cudaStreamDestroy(l.stream);
+  l.stream = nullptr;
+}
+
+// Builds the shared-memory layout of the decoder: row r sits in slot r, its k-th edge at word k * m_pad + r.
+int build_decoder_tables(kml_ctx *c, const kml_code *code) {
+  const int M = c->M, N = c->N;
+  const int mpad = (M + 31) & ~31;
+  std::vector<int> rdeg(M), cdeg(N, 0);
+  int dcm = 0, dvm = 0;
+  for (int r = 0; r < M; r++) {
+    rdeg[r] = code->row_ptr[r + 1] - code->row_ptr[r];
+    dcm = std::max(dcm, rdeg[r]);
+    for (int e = code->row_ptr[r]; e < code->row_ptr[r + 1]; e++) cdeg[code->col_idx[e]]++;
+  }
+  for (int v = 0; v < N; v++) dvm = std::max(dvm, cdeg[v]);
+  if ((size_t)dcm * mpad >= 0xFFFFu) return fail_arg(c, "code too large for 16-bit shared-memory edge addresses");
+  const bool regular = std::all_of(rdeg.begin(), rdeg.end(), [](int d) { return d == 6; }) &&
+                       std::all_of(cdeg.begin(), cdeg.end(), [](int d) { return d == 3; }) && c->punct == 0 &&
+                       mpad == M && N == 2 * M;
+  DecLaunch dl{};
+  int dv_tab;
+  if (regular && N % 6 == 0 && (N / 6) % 32 == 0 && N / 6 <= 384) {
+    dl.kind = DEC_REG_6_3; dl.threads = N / 6; dv_tab = 3;
+    dl.smem_bytes = 6 * mpad * 4;
+  } else if (regular && N % 12 == 0 && (N / 12) % 32 == 0 && N / 12 <= 672) {
+    dl.kind = DEC_REG_12_6; dl.threads = N / 12; dv_tab = 3;
+    dl.smem_bytes = 6 * mpad * 4;
+  } else {
+    if (dvm <= 4 && dcm <= 8) { dl.kind = DEC_GEN_4_8; }
+    else if (dvm <= 9 && dcm <= 10) { dl.kind = DEC_GEN_9_10; }
+    else if (dvm <= 16 && dcm <= 32) { dl.kind = DEC_GEN_16_32; }
+    else return fail_arg(c, "row/column degree beyond the compiled decoder kernels (max 32/16)");
+    dv_tab = dvm;
+    int t = ((N + 5) / 6 + 31) & ~31;
+    dl.threads = std::min(1024, std::max(128, t));
+    dl.smem_bytes = (dcm * mpad + N + 2 * c->words_n) * 4;
+  }
+  if (dl.smem_bytes > 227 * 1024) return fail_arg(c, "code too large for one frame per SM in shared memory");
+  std::vector<uint16_t> vaddr((size_t)N * dv_tab, 0xFFFFu);
+  std::vector<uint8_t> vdeg(N, 0), cndeg(mpad, 0);
+  for (int r = 0; r < M; r++) {
+    cndeg[r] = (uint8_t)rdeg[r];
+    for (int e = code->row_ptr[r], k = 0; e < code->row_ptr[r + 1]; e++, k++) {
+      const int v = code->col_idx[e];
+      vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(k * mpad + r);
+    }
+  }
+  KML_CUDA(c, c->vn_addr.alloc(vaddr.size()));
+  KML_CUDA(c, cudaMemcpy(c->vn_addr.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  KML_CUDA(c, c->vn_deg.alloc(N));
+  KML_CUDA(c, cudaMemcpy(c->vn_deg.p, vdeg.data(), N, cudaMemcpyHostToDevice));
+  KML_CUDA(c, c->cn_deg.alloc(mpad));
+  KML_CUDA(c, cudaMemcpy(c->cn_deg.p, cndeg.data(), mpad, cudaMemcpyHostToDevice));
+  c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
+  c->dt.n = N; c->dt.m_pad = mpad; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct; c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
+  KML_CUDA(c, dec_prepare(dl));
+  c->dl = dl;
+  return KML_OK;
+}
+
+DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t *sel, int n_cand, int in_is_lr, int iters,
+                     uint32_t *out_bits, int32_t *out_ret, float *out_soft) {
+  DecParams p{};
+  p.t = c->dt;
+  p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
+  p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
+  p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
+  p.work_counter = l.work_counter.p; p.words_n = c->words_n;
+  return p;
+}
+
+// k-means → 4 candidates → metric → argmin → demap → decode (simulator.cc:131-148 + kmcodec.cc:54-72), all on l.stream.
+// y and (for known_h) true_h are device pointers; decisions land in l.cc_hat_packed / l.ret / l.uu_hat_packed.
+int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *true_h, double var) {
+  cudaStream_t s = l.stream;
+  DemapParams d{};
+  d.B = B; d.n_sym = c->n_sym; d.n_tx = c->n_tx; d.bits_per_symbol = c->bits; d.q = c->Q;
+  d.m_rows = c->M; d.punct = c->punct; d.y = y; d.inv_var = (float)(1.0 / var);
+  for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
+  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p;
+  d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
+  const int32_t *sel = nullptr;
+  int n_cand = 1;
+  if (c->opts.known_h) {
+    d.h = true_h; d.n_cand = 1; d.hard_metric = 0;
+    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+  } else {
+    KML_LAUNCH(c, launch_kmeans(B, y, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, l.hhat.p, l.passes.p,
+                               c->num_sms, s));
+    const bool decode_metric = c->is_5g || c->opts.metric_type;
+    d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
+    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+    if (decode_metric) {  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
+      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
+      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * B, s));
+      DecParams p = dec_params(c, l, 4 * B, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
+      p.early_exit = 1;
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      if (soft) {
+        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * B, cudaMemcpyDeviceToDevice, s));
+        KML_LAUNCH(c, launch_abs_inplace(4 * B, l.metric.p, s));
+      } else {
+        KML_LAUNCH(c, launch_syndrome_weight(4 * B, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p,
+                                            l.metric.p, s));
+      }
+      KML_LAUNCH(c, launch_argmin4(B, l.metric.p, l.kstar.p, s));
+    }
+    sel = l.kstar.p;
+    n_cand = 4;
+  }
+  DecParams p = dec_params(c, l, B, l.lr.p, sel, n_cand, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
+  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+  KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
+  return KML_OK;
+}
+
+int check_batch(kml_ctx *c, int B) {
+  if (!c) return KML_ERR_ARG;
+  if (B < 0) return fail_arg(c, "negative batch");
+  return KML_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ context
+extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const kml_modem *modem, const kml_opts *opts) {
+  if (!out || !code || !modem || !opts) return fail_arg(nullptr, "kml_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_global_error("kml_create: no CUDA device — kmldpc_b200 has no CPU fallback");
+    return KML_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return fail_arg(nullptr, "kml_create: bad device index");
+  cudaDeviceProp prop{};
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    set_global_error("kml_create: cannot select device");
+    return KML_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_global_error("kml_create: kernels are built for sm_100a only (found sm_" + std::to_string(prop.major) +
+                     std::to_string(prop.minor) + ")");
+    return KML_ERR_CUDA;
+  }
+  if (code->n_tx % modem->bits_per_symbol != 0)  // modemlinearsystem.cc:7-13
+    return fail_arg(nullptr, "kml_create: n_tx is not a multiple of bits_per_symbol");
+  if (modem->bits_per_symbol > 6) return fail_arg(nullptr, "kml_create: constellations above 64 points are not built");
+  if (opts->max_iter < 1) return fail_arg(nullptr, "kml_create: max_iter < 1");
+  auto *c = new kml_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->M = code->n_rows; c->N = code->n_graph; c->n_tx = code->n_tx; c->K = code->k; c->n_chk = code->n_chk;
+  c->punct = code->puncture; c->info_offset = code->info_offset; c->E = code->n_edges; c->is_5g = code->is_5g;
+  c->active = code->encoder_active;
+  c->k_words = (c->K + 31) / 32; c->tx_words = (c->n_tx + 31) / 32; c->words_n = (c->N + 31) / 32;
+  c->bits = modem->bits_per_symbol; c->Q = modem->n_points; c->n_sym = c->n_tx / c->bits;
+  c->opts = *opts;
+  if (c->opts.kmeans_iter <= 0) c->opts.kmeans_iter = 20;
+  if (c->opts.metric_iter <= 0) c->opts.metric_iter = 5;
+  c->max_batch = opts->max_batch > 0 ? opts->max_batch : 16384;
+  for (int k = 0; k < 4; k++) {  // exp(j (kPi/2) k) with the reference's truncated pi (simulator.cc:146-148)
+    const double a = (kRefPi / 2) * k;
+    c->rot[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+  auto fail = [&](int rc) {
+    set_global_error(c->err);
+    kml_destroy(c);
+    return rc;
+  };
+#define KML_TRY(expr)               \
+  do {                              \
+    int rc__ = (expr);              \
+    if (rc__ != KML_OK) return fail(rc__); \
+  } while (0)
+  auto upload = [&]() -> int {
+    // encoder matrix, transposed to [word][row] so that consecutive threads read consecutive addresses
+    if (c->active) {
+      const int W = code->enc_words;
+      std::vector<uint32_t> t((size_t)W * c->n_chk);
+      for (int r = 0; r < c->n_chk; r++)
+        for (int w = 0; w < W; w++) t[(size_t)w * c->n_chk + r] = code->enc_rows[(size_t)r * W + w];
+      KML_CUDA(c, c->enc_t.alloc(t.size()));
+      KML_CUDA(c, cudaMemcpy(c->enc_t.p, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    std::vector<float2> pts(c->Q);
+    for (int i = 0; i < c->Q; i++) pts[i] = make_float2((float)modem->points[2 * i], (float)modem->points[2 * i + 1]);
+    KML_CUDA(c, c->points.alloc(c->Q));
+    KML_CUDA(c, cudaMemcpy(c->points.p, pts.data(), sizeof(float2) * c->Q, cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->row_ptr.alloc(c->M + 1));
+    KML_CUDA(c, cudaMemcpy(c->row_ptr.p, code->row_ptr, sizeof(int32_t) * (c->M + 1), cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->col_idx.alloc(c->E));
+    KML_CUDA(c, cudaMemcpy(c->col_idx.p, code->col_idx, sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->counters.alloc(5));
+    KML_CUDA(c, cudaMemset(c->counters.p, 0, 5 * sizeof(unsigned long long)));
+    KML_CUDA(c, cudaMallocHost(&c->h_counters, 5 * sizeof(unsigned long long)));
+    return KML_OK;
+  };
+  KML_TRY(upload());
+  KML_TRY(build_decoder_tables(c, code));
+  KML_TRY(alloc_lane(c, c->lane[0]));
+  KML_TRY(alloc_lane(c, c->lane[1]));
+#undef KML_TRY
+  *out = c;
+  return KML_OK;
+}
+
+extern "C" void kml_destroy(kml_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_lane(c->lane[0]);
+  free_lane(c->lane[1]);
+  c->enc_t.release(); c->points.release(); c->row_ptr.release(); c->col_idx.release();
+  c->vn_addr.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  delete c;
+}
+
+extern "C" const char *kml_last_error(const kml_ctx *c) { return c ? c->err.c_str() : global_error(); }
+
+extern "C" int kml_set_early_exit(kml_ctx *c, int early_exit) {
+  if (!c) return KML_ERR_ARG;
+  c->opts.early_exit = early_exit ? 1 : 0;
+  return KML_OK;
+}
+
+extern "C" int kml_info(const kml_ctx *c, int32_t info[8]) {
+  if (!c || !info) return KML_ERR_ARG;
+  info[0] = c->M; info[1] = c->N; info[2] = c->n_tx; info[3] = c->K;
+  info[4] = c->bits; info[5] = c->Q; info[6] = c->n_sym; info[7] = c->max_batch;
+  return KML_OK;
+}
+
+extern "C" uint64_t kml_launch_count(const kml_ctx *c) { return c ? c->launches : 0; }
+
+// ================================================================================================ stage entry points
+// Host-pointer stages run batch by batch on lane 0; temporaries for the int32 <-> packed conversions are (re)allocated
+// on demand.  They exist for parity tests and standalone measurements, not for peak throughput.
+namespace {
+template <class T>
+int ensure(kml_ctx *c, DevBuf<T> &b, size_t count) {
+  if (b.n >= count && b.p) return KML_OK;
+  b.release();
+  KML_CUDA(c, b.alloc(count));
+  return KML_OK;
+}
+#define KML_RC(expr)                  \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != KML_OK) return rc__;  \
+  } while (0)
+}  // namespace
+
+extern "C" int kml_encode(kml_ctx *c, int B, const int32_t *u, int32_t *cw) {
+  KML_RC(check_batch(c, B));
+  if (!u || !cw) return fail_arg(c, "kml_encode: null buffer");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_RC(ensure(c, l.bits_io, (size_t)nb * std::max(c->K, c->n_tx)));
+    KML_CUDA(c, cudaMemcpyAsync(l.bits_io.p, u + (size_t)b0 * c->K, sizeof(int32_t) * nb * c->K, cudaMemcpyHostToDevice, l.stream));
+    KML_LAUNCH(c, launch_pack_bits(nb, c->K, l.bits_io.p, l.u_packed.p, l.stream));
+    GenParams g = gen_params(c, nb, 0.0, 0, 0);
+    KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
+    KML_LAUNCH(c, launch_unpack_bits(nb, c->n_tx, 0, c->tx_words, l.c_packed.p, l.bits_io.p, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(cw + (size_t)b0 * c->n_tx, l.bits_io.p, sizeof(int32_t) * nb * c->n_tx, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  return KML_OK;
+}
+
+extern "C" int kml_generate(kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0, int32_t *u, int32_t *cw,
+                            float *h, float *y) {
+  KML_RC(check_batch(c, B));
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    GenParams g = gen_params(c, nb, snr_db, seed, frame0 + b0);
+    KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, l.stream));
+    KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
+    KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, l.stream));
+    KML_RC(ensure(c, l.bits_io, (size_t)nb * std::max(c->K, c->n_tx)));
+    if (u) {
+      KML_LAUNCH(c, launch_unpack_bits(nb, c->K, 0, c->k_words, l.u_packed.p, l.bits_io.p, l.stream));
+      KML_CUDA(c, cudaMemcpyAsync(u + (size_t)b0 * c->K, l.bits_io.p, sizeof(int32_t) * nb * c->K, cudaMemcpyDeviceToHost, l.stream));
+      KML_CUDA(c, cudaStreamSynchronize(l.stream));
+    }
+    if (cw) {
+      KML_LAUNCH(c, launch_unpack_bits(nb, c->n_tx, 0, c->tx_words, l.c_packed.p, l.bits_io.p, l.stream));
+      KML_CUDA(c, cudaMemcpyAsync(cw + (size_t)b0 * c->n_tx, l.bits_io.p, sizeof(int32_t) * nb * c->n_tx, cudaMemcpyDeviceToHost, l.stream));
+    }
+    if (h) KML_CUDA(c, cudaMemcpyAsync(h + (size_t)b0 * 2, l.h.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
+    if (y) KML_CUDA(c, cudaMemcpyAsync(y + (size_t)b0 * c->n_sym * 2, l.y.p, sizeof(float2) * nb * c->n_sym, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  return KML_OK;
+}
+
+extern "C" int kml_modulate(kml_ctx *c, int B, const int32_t *cw, const float *h, const float *noise, double sigma, float *y) {
+  KML_RC(check_batch(c, B));
+  if (!cw || !h || !y) return fail_arg(c, "kml_modulate: null buffer");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_RC(ensure(c, l.bits_io, (size_t)nb * std::max(c->K, c->n_tx)));
+    KML_RC(ensure(c, l.noise, (size_t)nb * c->n_sym));
+    KML_CUDA(c, cudaMemcpyAsync(l.bits_io.p, cw + (size_t)b0 * c->n_tx, sizeof(int32_t) * nb * c->n_tx, cudaMemcpyHostToDevice, l.stream));
+    KML_LAUNCH(c, launch_pack_bits(nb, c->n_tx, l.bits_io.p, l.c_packed.p, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(l.h.p, h + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, l.stream));
+    if (noise) KML_CUDA(c, cudaMemcpyAsync(l.noise.p, noise + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
+    else KML_CUDA(c, cudaMemsetAsync(l.noise.p, 0, sizeof(float2) * nb * c->n_sym, l.stream));
+    GenParams g = gen_params(c, nb, 0.0, 0, 0);
+    g.sigma_over_sqrt2 = (float)(sigma / 1.4142135623730950488016);
+    KML_LAUNCH(c, launch_channel(g, l.c_packed.p, l.h.p, l.noise.p, nullptr, l.y.p, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(y + (size_t)b0 * c->n_sym * 2, l.y.p, sizeof(float2) * nb * c->n_sym, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  return KML_OK;
+}
+
+extern "C" int kml_kmeans(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes) {
+  KML_RC(check_batch(c, B));
+  if (!y || !hhat) return fail_arg(c, "kml_kmeans: null buffer");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
+    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, l.hhat.p, l.passes.p, c->num_sms, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
+    if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  return KML_OK;
+}
+
+namespace {
+DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int hard_metric) {
+  DemapParams d{};
+  d.B = B; d.n_sym = c->n_sym; d.n_tx = c->n_tx; d.bits_per_symbol = c->bits; d.q = c->Q; d.n_cand = n_cand;
+  d.hard_metric = hard_metric; d.m_rows = c->M; d.punct = c->punct; d.y = l.y.p; d.h = l.hhat.p;
+  d.inv_var = (float)(1.0 / var);
+  for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
+  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p;
+  d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
+  return d;
+}
+}  // namespace
+
+extern "C" int kml_demap(kml_ctx *c, int B, const float *y, const float *h, double var, float *llr) {
+  KML_RC(check_batch(c, B));
+  if (!y || !h || !llr || !(var > 0)) return fail_arg(c, "kml_demap: bad argument");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(l.hhat.p, h + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, l.stream));
+    DemapParams d = demap_params(c, l, nb, var, 1, 0);
+    KML_LAUNCH(c, launch_demap(d, c->num_sms, l.stream));
+    KML_LAUNCH(c, launch_lr_to_llr((size_t)nb * c->n_tx, l.lr.p, l.lr.p, l.stream));
+    KML_CUDA(c, cudaMemcpyAsync(llr + (size_t)b0 * c->n_tx, l.lr.p, sizeof(float) * nb * c->n_tx, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  return KML_OK;
+}
+
+extern "C" int kml_resolve(kml_ctx *c, int B, const float *y, const float *hhat, double var, float *metric, int32_t *kstar) {
+  KML_RC(check_batch(c, B));
+  if (!y || !hhat || !(var > 0)) return fail_arg(c, "kml_resolve: bad argument");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
+    KML_CUDA(c, cudaMemcpyAsync(l.hhat.p, hhat + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, s));
+    const bool decode_metric = c->is_5g || c->opts.metric_type;
+    DemapParams d = demap_params(c, l, nb, var, 4, decode_metric ? 0 : 1);
+    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+    if (decode_metric) {
+      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
+      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
+      DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
+      p.early_exit = 1;
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      if (soft) {
+        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
+        KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
+      } else {
+        KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
+      }
+      KML_LAUNCH(c, launch_argmin4(nb, l.metric.p, l.kstar.p, s));
+    }
+    if (metric) KML_CUDA(c, cudaMemcpyAsync(metric + (size_t)b0 * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
+    if (kstar) KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    KML_CUDA(c, cudaStreamSynchronize(s));
+  }
+  return KML_OK;
+}
+
+extern "C" int kml_decode(kml_ctx *c, int B, const float *llr, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!llr || iter_count < 1) return fail_arg(c, "kml_decode: bad argument");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.lr.p, llr + (size_t)b0 * c->n_tx, sizeof(float) * nb * c->n_tx, cudaMemcpyHostToDevice, s));
+    DecParams p = dec_params(c, l, nb, l.lr.p, nullptr, 1, 0, iter_count, l.cc_hat_packed.p, l.ret.p, nullptr);
+    KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+    KML_RC(ensure(c, l.bits_io, (size_t)nb * c->N));
+    if (cc_hat) {
+      KML_LAUNCH(c, launch_unpack_bits(nb, c->N, 0, c->words_n, l.cc_hat_packed.p, l.bits_io.p, s));
+      KML_CUDA(c, cudaMemcpyAsync(cc_hat + (size_t)b0 * c->N, l.bits_io.p, sizeof(int32_t) * nb * c->N, cudaMemcpyDeviceToHost, s));
+      KML_CUDA(c, cudaStreamSynchronize(s));
+    }
+    if (uu_hat) {
+      KML_LAUNCH(c, launch_unpack_bits(nb, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.bits_io.p, s));
+      KML_CUDA(c, cudaMemcpyAsync(uu_hat + (size_t)b0 * c->K, l.bits_io.p, sizeof(int32_t) * nb * c->K, cudaMemcpyDeviceToHost, s));
+    }
+    if (ret) KML_CUDA(c, cudaMemcpyAsync(ret + b0, l.ret.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    KML_CUDA(c, cudaStreamSynchronize(s));
+  }
+  return KML_OK;
+}
+
+// Host-buffer receiver: batches alternate between the two lanes so the H2D copy of batch i+1 and the D2H copy of batch
+// i-1 overlap the kernels of batch i (true overlap needs pinned host buffers; pageable ones still work).
+extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                           float *hhat, int32_t *kstar, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive: bad argument");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  // sub-batches: at least 4 per call when the call is large enough, so both lanes stay busy
+  int step = c->max_batch;
+  if (B > 4 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, (B + 3) / 4));
+  int li = 0;
+  for (int b0 = 0; b0 < B; b0 += step, li ^= 1) {
+    Lane &l = c->lane[li];
+    cudaStream_t s = l.stream;
+    const int nb = std::min(step, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
+    if (c->opts.known_h)
+      KML_CUDA(c, cudaMemcpyAsync(l.h.p, true_h + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, s));
+    KML_RC(receive_on_lane(c, l, nb, l.y.p, l.h.p, var));
+    if (uu_hat_packed)
+      KML_CUDA(c, cudaMemcpyAsync(uu_hat_packed + (size_t)b0 * c->k_words, l.uu_hat_packed.p, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyDeviceToHost, s));
+    if (hhat && !c->opts.known_h)
+      KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, s));
+    if (kstar && !c->opts.known_h)
+      KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    if (ret) KML_CUDA(c, cudaMemcpyAsync(ret + b0, l.ret.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+  }
+  KML_CUDA(c, cudaStreamSynchronize(c->lane[0].stream));
+  KML_CUDA(c, cudaStreamSynchronize(c->lane[1].stream));
+  return KML_OK;
+}
+
+extern "C" int kml_count_errors(kml_ctx *c, int B, const uint32_t *u_packed, const uint32_t *uu_hat_packed, uint64_t counters[4]) {
+  KML_RC(check_batch(c, B));
+  if (!u_packed || !uu_hat_packed || !counters) return fail_arg(c, "kml_count_errors: null buffer");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), s));
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.u_packed.p, u_packed + (size_t)b0 * c->k_words, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyHostToDevice, s));
+    KML_CUDA(c, cudaMemcpyAsync(l.uu_hat_packed.p, uu_hat_packed + (size_t)b0 * c->k_words, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyHostToDevice, s));
+    KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, nullptr, c->opts.max_iter, c->counters.p, s));
+  }
+  KML_CUDA(c, cudaMemcpyAsync(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  KML_CUDA(c, cudaStreamSynchronize(s));
+  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
+  return KML_OK;
+}
+
+// ================================================================================================ fused path
+extern "C" int kml_simulate(kml_ctx *c, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
+                            uint64_t max_err_blk, uint64_t counters[4], uint64_t *iters_sum) {
+  if (!c || !counters) return KML_ERR_ARG;
+  KML_CUDA(c, cudaSetDevice(c->device));
+  const double var = std::pow(10.0, -0.1 * snr_db);
+  KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), c->lane[0].stream));
+  KML_CUDA(c, cudaStreamSynchronize(c->lane[0].stream));
+  uint64_t done = 0;
+  int li = 0;
+  cudaEvent_t ev[2];
+  KML_CUDA(c, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  KML_CUDA(c, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  bool pending[2] = {false, false};
+  int rc = KML_OK;
+  auto run = [&]() -> int {
+    while (done < frame_count) {
+      Lane &l = c->lane[li];
+      if (pending[li]) {  // the lane's previous batch must be finished before its buffers are reused
+        KML_CUDA(c, cudaEventSynchronize(ev[li]));
+        pending[li] = false;
+        if (max_err_blk) {  // stop rule with one-batch lag (simulator.cc:117 checks before every frame)
+          KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+          if (counters[1] + c->h_counters[1] >= max_err_blk) break;
+        }
+      }
+      const int nb = (int)std::min<uint64_t>((uint64_t)c->max_batch, frame_count - done);
+      GenParams g = gen_params(c, nb, snr_db, seed, frame_begin + done);
+      KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, l.stream));
+      KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
+      KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, l.stream));
+      KML_RC(receive_on_lane(c, l, nb, l.y.p, l.h.p, var));
+      KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, l.ret.p, c->opts.max_iter,
+                                       c->counters.p, l.stream));
+      KML_CUDA(c, cudaEventRecord(ev[li], l.stream));
+      pending[li] = true;
+      done += nb;
+      li ^= 1;
+    }
+    return KML_OK;
+  };
+  rc = run();
+  cudaStreamSynchronize(c->lane[0].stream);
+  cudaStreamSynchronize(c->lane[1].stream);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  if (rc != KML_OK) return rc;
+  KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
+  if (iters_sum) *iters_sum += c->h_counters[4];
+  return KML_OK;
+}
+
+// ================================================================================================ device-pointer variants
+extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0, uint32_t *u_packed,
+                                float *h, float *y, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!u_packed || !h || !y) return fail_arg(c, "kml_generate_dev: null buffer");
+  if (B > c->max_batch) return fail_arg(c, "kml_generate_dev: B exceeds max_batch");
+  cudaStream_t s = (cudaStream_t)stream;
+  Lane &l = c->lane[0];
+  GenParams g = gen_params(c, B, snr_db, seed, frame0);
+  KML_LAUNCH(c, launch_gen_bits(g, u_packed, s));
+  KML_LAUNCH(c, launch_encode(g, u_packed, l.c_packed.p, s));
+  KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, (float2 *)h, (float2 *)y, s));
+  return KML_OK;
+}
+
+extern "C" int kml_kmeans_dev(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!y || !hhat) return fail_arg(c, "kml_kmeans_dev: null buffer");
+  KML_LAUNCH(c, launch_kmeans(B, (const float2 *)y, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, (float2 *)hhat,
+                             passes, c->num_sms, (cudaStream_t)stream));
+  return KML_OK;
+}
+
+extern "C" int kml_receive_dev(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                               int32_t *ret, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive_dev: bad argument");
+  if (B > c->max_batch) return fail_arg(c, "kml_receive_dev: B exceeds max_batch");
+  Lane &l = c->lane[0];
+  cudaStream_t saved = l.stream;
+  l.stream = (cudaStream_t)stream;  // run the chain on the caller's stream with lane-0 work space
+  int rc = receive_on_lane(c, l, B, (const float2 *)y, (const float2 *)true_h, var);
+  if (rc == KML_OK && uu_hat_packed) {
+    cudaError_t e = cudaMemcpyAsync(uu_hat_packed, l.uu_hat_packed.p, sizeof(uint32_t) * (size_t)B * c->k_words, cudaMemcpyDeviceToDevice, l.stream);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = KML_ERR_CUDA; }
+  }
+  if (rc == KML_OK && ret) {
+    cudaError_t e = cudaMemcpyAsync(ret, l.ret.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, l.stream);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = KML_ERR_CUDA; }
+  }
+  l.stream = saved;
+  return rc;
+}
+
+extern "C" int kml_decode_dev(kml_ctx *c, int B, const float *llr, int in_is_lr, int iter_count, uint32_t *cc_hat_packed,
+                              int32_t *ret, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!llr || !cc_hat_packed || !ret || iter_count < 1) return fail_arg(c, "kml_decode_dev: bad argument");
+  Lane &l = c->lane[0];
+  DecParams p = dec_params(c, l, B, llr, nullptr, 1, in_is_lr, iter_count, cc_hat_packed, ret, nullptr);
+  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, (cudaStream_t)stream));
+  return KML_OK;
+}
+
+extern "C" int kml_count_errors_dev(kml_ctx *c, int B, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
+                                    uint64_t *counters_dev, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!u_packed || !uu_hat_packed || !counters_dev) return fail_arg(c, "kml_count_errors_dev: null buffer");
+  KML_LAUNCH(c, launch_count_errors(B, c->K, c->k_words, u_packed, uu_hat_packed, nullptr, c->opts.max_iter,
+                                   (unsigned long long *)counters_dev, (cudaStream_t)stream));
+  return KML_OK;
+}

@@ -1,0 +1,25 @@
+// Internal declarations shared by the host-side C++ and the CUDA translation units of libkmldpc_b200.so.
+#ifndef KML_INTERNAL_H
+#define KML_INTERNAL_H
+#include <cstdint>
+#include <string>
+
+#include "../../include/kmldpc_b200.h"
+
+namespace kml {
+
+void set_global_error(const std::string &msg);
+const char *global_error();
+
+// Truncated pi of the reference (lib/lab/include/utility.h:10) — the candidate rotations use it.
+constexpr double kRefPi = 3.14159265358979;
+// lib/lab/include/utility.h:12
+constexpr float kSmallProbF = 1.0e-12f;
+constexpr float kLrMin = 1.0e-12f;  // P0/P1 after the reference's clip of P0 to [1e-12, 1-1e-12]
+constexpr float kLrMax = 1.0e12f;
+
+// Philox stream ids (word 3 of the counter)
+enum : uint32_t { STREAM_BITS = 0x5eed0001u, STREAM_FADE = 0x5eed0002u, STREAM_NOISE = 0x5eed0003u };
+
+}  // namespace kml
+#endif

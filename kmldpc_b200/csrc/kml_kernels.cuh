@@ -1,0 +1,100 @@
+// Kernel parameter blocks and launchers of libkmldpc_b200.so (sm_100a only).
+#ifndef KML_KERNELS_CUH
+#define KML_KERNELS_CUH
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace kml {
+
+// ---- belief-propagation decoder -------------------------------------------------------------------------------
+// Edge messages live in shared memory as one 32-bit word per edge at word address k * m_pad + slot(row), k = position
+// of the edge inside its row: check-node threads (one row slot each) touch consecutive words → conflict free, and
+// variable-node threads gather/scatter through per-variable address lists.
+struct DecTables {
+  const uint16_t *vn_addr;  // [n][dv_max] shared-memory word address of each edge of a variable, 0xFFFF = none
+  const uint8_t *vn_deg;    // [n]
+  const uint8_t *cn_deg;    // [m_pad] degree of the row held by a slot (0 = padding)
+  int n, m_pad, n_tx, punct, dv_max, dc_max;
+};
+
+struct DecParams {
+  DecTables t;
+  const float *in;          // [B * n_cand][n_tx] natural-log LLR, or likelihood ratio P0/P1 when in_is_lr
+  const int32_t *sel;       // optional [B]: candidate picked per frame (row f * n_cand + sel[f] of `in`)
+  int n_cand, in_is_lr;
+  int B, iters, max_iter, early_exit;
+  uint32_t *out_bits;       // [B][words_n] hard decisions of all graph variables, bit-packed
+  int32_t *out_ret;         // [B] reference return value: iter + (iter < max_iter)
+  float *out_soft;          // optional [B]: sum over rows of ln(syndrom_soft) after the LAST check-node phase executed
+  unsigned int *work_counter;  // dynamic frame scheduler (zeroed by the launcher)
+  int words_n;
+};
+
+enum DecKernelKind { DEC_REG_6_3 = 0, DEC_REG_12_6 = 1, DEC_GEN_4_8 = 2, DEC_GEN_9_10 = 3, DEC_GEN_16_32 = 4 };
+
+struct DecLaunch {
+  DecKernelKind kind;
+  int threads;
+  int smem_bytes;
+  int ctas_per_sm;  // filled by dec_prepare (occupancy query)
+};
+
+cudaError_t dec_prepare(DecLaunch &l);
+cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
+
+// ---- generation: Philox bits, GF(2) encoder, mapping + block-fading AWGN channel --------------------------------
+struct GenParams {
+  int B, k, k_words, n_tx, tx_words, n_chk, punct, is_5g, encoder_active;
+  int bits_per_symbol, n_sym, q;
+  uint64_t seed, frame0;
+  float sigma_over_sqrt2;
+  const uint32_t *enc_t;  // [k_words][n_chk] transposed parity rows
+  const float2 *points;   // [q]
+};
+cudaError_t launch_gen_bits(const GenParams &g, uint32_t *u_packed, cudaStream_t s);
+cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s);
+// noise == nullptr → Philox noise and fading (h written to h_out); otherwise h is read from h_in, noise as given
+cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
+                           float2 *h_out, float2 *y, cudaStream_t s);
+
+// ---- k-means blind channel estimate ------------------------------------------------------------------------------
+cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, int iters, float2 *hhat,
+                          int32_t *passes, int num_sms, cudaStream_t s);
+
+// ---- soft demapper + candidate resolver ---------------------------------------------------------------------------
+struct DemapParams {
+  int B, n_sym, n_tx, bits_per_symbol, q, n_cand;  // n_cand = 4 (blind) or 1
+  int hard_metric;                                 // compute syndrome weights of the inverted hard decisions
+  int m_rows, punct;
+  const float2 *y;       // [B][n_sym]
+  const float2 *h;       // [B] channel estimate (hhat or true h)
+  float inv_var;
+  float2 rot[4];         // exp(j (kPi/2) k)
+  const float2 *points;  // [q]
+  const int32_t *row_ptr, *col_idx;  // permuted graph (for the hard metric)
+  float *lr;             // [B][n_cand][n_tx] likelihood ratios P0/P1 in [1e-12, 1e12]
+  float *metric;         // [B][4] (hard metric only)
+  int32_t *kstar;        // [B]     (hard metric only; else untouched)
+};
+cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s);
+
+// syndrome weight of packed decisions: bits [F][words_n] → metric[F] (float)
+cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
+                                   const int32_t *col_idx, float *metric, cudaStream_t s);
+cudaError_t launch_abs_inplace(int n, float *v, cudaStream_t s);
+cudaError_t launch_argmin4(int B, const float *metric, int32_t *kstar, cudaStream_t s);
+
+// ---- small utilities ------------------------------------------------------------------------------------------------
+cudaError_t launch_pack_bits(int F, int nbits, const int32_t *bits, uint32_t *packed, cudaStream_t s);
+cudaError_t launch_unpack_bits(int F, int nbits, int bit_offset, int src_words, const uint32_t *packed, int32_t *bits,
+                               cudaStream_t s);
+cudaError_t launch_extract_bits(int F, int nbits, int bit_offset, int src_words, const uint32_t *src, uint32_t *dst,
+                                cudaStream_t s);
+cudaError_t launch_lr_to_llr(size_t n, const float *lr, float *llr, cudaStream_t s);
+// counters[0..3] += tot_blk, err_blk, tot_bit, err_bit ; counters[4] += sum of min(ret, max_iter) when ret != nullptr
+cudaError_t launch_count_errors(int B, int k, int k_words, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
+                                const int32_t *ret, int max_iter, unsigned long long *counters, cudaStream_t s);
+
+}  // namespace kml
+#endif

@@ -1,0 +1,630 @@
+// Everything of the link path that is not the BP decoder: Philox source, GF(2) encoder, mapper + block-fading AWGN
+// channel, k-means blind channel estimate, soft demapper + candidate resolver, error counting (sm_100a).
+// Reference functions are cited at each kernel (paths relative to the reference's kmldpc/ directory).
+#include <cstdio>
+
+#include "kml_internal.h"
+#include "kml_kernels.cuh"
+
+namespace kml {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+// Counter-based RNG replacing the shared, unlocked LCG of the reference (lib/lab/src/randnum.cc:36-45): any sample is
+// a pure function of (seed, stream, frame index, sample index), so results are independent of batching and GPU count.
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                  uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return {c0, c1, c2, c3};
+}
+__device__ __forceinline__ Philox4 philox_at(uint64_t seed, uint32_t stream, uint64_t frame, uint32_t idx) {
+  return philox4x32_10(idx, (uint32_t)frame, (uint32_t)(frame >> 32), stream, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+// Box–Muller: two independent N(0,1) from two 32-bit words
+__device__ __forceinline__ float2 gauss_pair(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;           // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// 32 bits starting at bit position q of the concatenation [A (len_a bits) | B]
+__device__ __forceinline__ uint32_t word_at(const uint32_t *w, int q) {
+  const int i = q >> 5, sh = q & 31;
+  const uint32_t lo = w[i];
+  if (sh == 0) return lo;
+  return __funnelshift_r(lo, w[i + 1], sh);
+}
+
+// ------------------------------------------------------------------------------------------------ source bits
+// SourceSink::GetBitStr (lib/lab/src/sourcesink.cc:5-9): K fair bits per frame.
+__global__ void gen_bits_kernel(GenParams g, uint32_t *u_packed) {
+  const int groups = (g.k_words + 3) / 4;
+  const long long total = (long long)g.B * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / groups), gr = (int)(i % groups);
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (g.encoder_active) {  // [ldpc] active = false → all-zero word (binaryldpccodec.cc:156-161)
+      const Philox4 r = philox_at(g.seed, STREAM_BITS, g.frame0 + f, gr);
+      v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int w = gr * 4 + j;
+      if (w < g.k_words) {
+        uint32_t x = v[j];
+        if (w == g.k_words - 1 && (g.k & 31)) x &= (1u << (g.k & 31)) - 1u;
+        u_packed[(size_t)f * g.k_words + w] = x;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+// BinaryLDPCCodec::Encoder (binaryldpccodec.cc:144-162): cc = [p | u], p_t = XOR_j u_j & enc_h[t][chk + j]
+// Binary5GLDPCCodec::Encoder (binary5gldpccodec.cc:86-109): cc_np = [u | p], transmitted = cc_np[2Z:]
+// One CTA encodes ENC_FT frames: thread t owns parity row t (rows strided by the block), reads its row of the
+// transposed matrix once per word and applies it to all ENC_FT frames (u words are warp-broadcast from shared memory).
+constexpr int ENC_FT = 8;
+constexpr int ENC_THREADS = 256;
+__global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const uint32_t *u_packed, uint32_t *c_packed) {
+  extern __shared__ uint32_t sm[];
+  const int chk_words = (g.n_chk + 31) / 32;
+  uint32_t *su = sm;                                   // [ENC_FT][k_words + 1]
+  uint32_t *sp = su + ENC_FT * (g.k_words + 1);        // [ENC_FT][chk_words + 1]
+  const int f0 = blockIdx.x * ENC_FT;
+  const int nf = min(ENC_FT, g.B - f0);
+  for (int i = threadIdx.x; i < ENC_FT * (g.k_words + 1); i += blockDim.x) {
+    const int f = i / (g.k_words + 1), w = i % (g.k_words + 1);
+    su[i] = (f < nf && w < g.k_words) ? u_packed[(size_t)(f0 + f) * g.k_words + w] : 0u;
+  }
+  for (int i = threadIdx.x; i < ENC_FT * (chk_words + 1); i += blockDim.x) sp[i] = 0u;
+  __syncthreads();
+  const int rows_round = (g.n_chk + 31) & ~31;
+  for (int t = threadIdx.x; t < rows_round; t += blockDim.x) {
+    uint32_t acc[ENC_FT];
+#pragma unroll
+    for (int f = 0; f < ENC_FT; f++) acc[f] = 0;
+    if (t < g.n_chk && g.encoder_active) {
+      for (int w = 0; w < g.k_words; w++) {
+        const uint32_t e = __ldg(g.enc_t + (size_t)w * g.n_chk + t);
+#pragma unroll
+        for (int f = 0; f < ENC_FT; f++) acc[f] ^= e & su[f * (g.k_words + 1) + w];
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < ENC_FT; f++) {
+      const uint32_t word = __ballot_sync(0xffffffffu, __popc(acc[f]) & 1);
+      if ((threadIdx.x & 31) == 0) sp[f * (chk_words + 1) + (t >> 5)] = word;
+    }
+  }
+  __syncthreads();
+  // assemble the transmitted word: S = [p | u] (PEG) or [u | p] (5G), c = S[punct : punct + n_tx]
+  for (int i = threadIdx.x; i < nf * g.tx_words; i += blockDim.x) {
+    const int f = i / g.tx_words, w = i % g.tx_words;
+    const uint32_t *a = g.is_5g ? su + f * (g.k_words + 1) : sp + f * (chk_words + 1);
+    const uint32_t *b = g.is_5g ? sp + f * (chk_words + 1) : su + f * (g.k_words + 1);
+    const int len_a = g.is_5g ? g.k : g.n_chk;
+    const int q = g.punct + 32 * w;  // first S position of this output word
+    uint32_t out;
+    if (q + 32 <= len_a) out = word_at(a, q);
+    else if (q >= len_a) out = word_at(b, q - len_a);
+    else {
+      const int na = len_a - q;  // bits still coming from A
+      out = (word_at(a, q) & ((1u << na) - 1u)) | (b[0] << na);
+    }
+    const int valid = g.n_tx - 32 * w;
+    if (valid < 32) out &= (1u << valid) - 1u;
+    if (!g.encoder_active) out = 0u;  // [ldpc] active = false: all-zero codeword (binaryldpccodec.cc:156-161)
+    c_packed[(size_t)(f0 + f) * g.tx_words + w] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ mapper + channel
+// Modem::Mapping (lib/lab/src/modem.cc:12-20), the fading draw (src/simulator.cc:120-128) and
+// ModemLinearSystem::PartitionHAWGNSystem (lib/lab/src/modemlinearsystem.cc:37-48): y = h x + (sigma/sqrt2) (a + jb)
+__global__ void channel_kernel(GenParams g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
+                               float2 *h_out, float2 *y) {
+  const long long total = (long long)g.B * g.n_sym;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / g.n_sym), sidx = (int)(i % g.n_sym);
+    const uint32_t *c = c_packed + (size_t)f * g.tx_words;
+    int idx = 0;
+    const int b0 = sidx * g.bits_per_symbol;
+    for (int j = 0; j < g.bits_per_symbol; j++) {  // MSB first
+      const int t = b0 + j;
+      idx = (idx << 1) | (int)((c[t >> 5] >> (t & 31)) & 1u);
+    }
+    const float2 x = __ldg(g.points + idx);
+    float2 h, nz;
+    if (noise) {
+      h = h_in[f];
+      nz = noise[i];
+    } else {
+      const Philox4 rh = philox_at(g.seed, STREAM_FADE, g.frame0 + f, 0);
+      const float2 gh = gauss_pair(rh.x, rh.y);
+      h = make_float2(gh.x * 0.70710678118654752f, gh.y * 0.70710678118654752f);  // CN(0,1)
+      const Philox4 rn = philox_at(g.seed, STREAM_NOISE, g.frame0 + f, (uint32_t)sidx);
+      nz = gauss_pair(rn.x, rn.y);
+      if (sidx == 0 && h_out) h_out[f] = h;
+    }
+    float2 o;
+    o.x = h.x * x.x - h.y * x.y + g.sigma_over_sqrt2 * nz.x;
+    o.y = h.x * x.y + h.y * x.x + g.sigma_over_sqrt2 * nz.y;
+    y[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k-means
+// kmldpc::KMeans::Run as COMPILED (src/kmeans.cc:15-84): anchor = first arg max |y|; every pass assigns
+// each sample to its nearest centroid (first minimum) and ADDS to never-reset per-cluster sums; only cluster 0 feeds
+// back: hhat = (sum_0 / cnt_0) / s_0, centroids = s_k * hhat; stop when the centroids repeat bit for bit.
+// One CTA per frame, samples in registers, warp-shuffle + shared-memory block reductions, fp64 cumulative sums.
+constexpr int KM_THREADS = 128;
+template <int SPT>
+__global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 *y, int n, const float2 *points, int q,
+                                                           int iters, float2 *hhat_out, int32_t *passes_out) {
+  extern __shared__ float2 s_c[];  // [q] centroids
+  __shared__ float s_red[3][KM_THREADS / 32];
+  __shared__ unsigned long long s_best[KM_THREADS / 32];
+  __shared__ double s_h[2];
+  __shared__ int s_stop;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int f = blockIdx.x; f < B; f += gridDim.x) {
+    const float2 *yf = y + (size_t)f * n;
+    float2 ys[SPT];
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int j = 0; j < SPT; j++) {
+      const int i = j * KM_THREADS + tid;
+      if (i < n) {
+        ys[j] = yf[i];
+        // |y|^2 is monotone in |y|; ties → smallest index (max_element returns the first maximum)
+        const float a2 = ys[j].x * ys[j].x + ys[j].y * ys[j].y;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
+        best = key > best ? key : best;
+      } else {
+        ys[j] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0, hr = 0.0, hi = 0.0, prev_r = 0.0, prev_i = 0.0;
+    bool have_prev = false;
+    const double s0r = (double)__ldg(&points[0].x), s0i = (double)__ldg(&points[0].y);
+    const double s0n = s0r * s0r + s0i * s0i;
+    if (tid == 0) {
+      unsigned long long b = s_best[0];
+      for (int w = 1; w < KM_THREADS / 32; w++) b = s_best[w] > b ? s_best[w] : b;
+      const int a = 0x7fffffff - (int)(uint32_t)(b & 0xffffffffu);
+      const float2 ya = yf[a];
+      hr = ((double)ya.x * s0r + (double)ya.y * s0i) / s0n;  // y_a / s_0
+      hi = ((double)ya.y * s0r - (double)ya.x * s0i) / s0n;
+      s_h[0] = hr;
+      s_h[1] = hi;
+      s_stop = 0;
+    }
+    __syncthreads();
+    int passes = 0;
+    for (int it = 0; it < iters; it++) {
+      passes++;
+      const float fhr = (float)s_h[0], fhi = (float)s_h[1];
+      for (int k = tid; k < q; k += KM_THREADS) {
+        const float2 s = __ldg(points + k);
+        s_c[k] = make_float2(s.x * fhr - s.y * fhi, s.x * fhi + s.y * fhr);
+      }
+      __syncthreads();
+      const float2 c0 = s_c[0];
+      float cnt = 0.f, sr = 0.f, si = 0.f;
+#pragma unroll
+      for (int j = 0; j < SPT; j++) {
+        const int i = j * KM_THREADS + tid;
+        if (i < n) {
+          const float dx0 = c0.x - ys[j].x, dy0 = c0.y - ys[j].y;
+          const float d0 = dx0 * dx0 + dy0 * dy0;
+          bool in0 = true;
+          for (int k = 1; k < q; k++) {
+            const float2 c = s_c[k];
+            const float dx = c.x - ys[j].x, dy = c.y - ys[j].y;
+            in0 = in0 && (d0 <= dx * dx + dy * dy);  // first minimum wins ties → cluster 0 keeps them
+          }
+          if (in0) {
+            cnt += 1.f;
+            sr += ys[j].x;
+            si += ys[j].y;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      if (lane == 0) {
+        s_red[0][warp] = cnt;
+        s_red[1][warp] = sr;
+        s_red[2][warp] = si;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 0; w < KM_THREADS / 32; w++) {
+          cum_cnt += (double)s_red[0][w];
+          cum_re += (double)s_red[1][w];
+          cum_im += (double)s_red[2][w];
+        }
+        if (have_prev && prev_r == hr && prev_i == hi) {
+          s_stop = 1;  // clusters_ == tempClusters (kmeans.cc:47-56): leave WITHOUT updating
+        } else {
+          prev_r = hr;
+          prev_i = hi;
+          have_prev = true;
+          const double mr = cum_re / cum_cnt, mi = cum_im / cum_cnt;  // cluster 0 is never empty (anchor sample)
+          hr = (mr * s0r + mi * s0i) / s0n;
+          hi = (mi * s0r - mr * s0i) / s0n;
+          s_h[0] = hr;
+          s_h[1] = hi;
+        }
+      }
+      __syncthreads();
+      if (s_stop) break;
+    }
+    if (tid == 0) {
+      hhat_out[f] = make_float2((float)s_h[0], (float)s_h[1]);
+      if (passes_out) passes_out[f] = passes;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ demapper + resolver
+// ModemLinearSystem::SoftAWGNDemodulation (modemlinearsystem.cc:51-79): p_k = softmax(-|s_k h - y|^2 / var), each
+// clipped to [1e-12, 1-1e-12]; Modem::DeMapping (modem.cc:23-79) with priors 0.5: renormalise by the post-clip sum,
+// bit marginals, clip.  Output = likelihood ratio P0/P1 (the clipped pair), MSB first within a symbol.
+// KmCodec::GetMetrics/Metric/GetParityCheck (kmcodec.cc:105-163), hard non-5G metric: rr = (P0 > 0.5) ? 1 : 0
+// (inverted on purpose), metric = number of unsatisfied rows; first argmin (kmcodec.cc:61-65).
+constexpr int DM_THREADS = 256;
+template <int BITS>
+__global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
+  constexpr int Q = 1 << BITS;
+  extern __shared__ unsigned char dsm[];
+  float2 *s_pts = reinterpret_cast<float2 *>(dsm);          // [Q] s_k * h_cand
+  unsigned char *s_rr = dsm + sizeof(float2) * Q;           // [n_tx + punct] inverted hard decisions
+  __shared__ int s_cnt[4];
+  const int tid = threadIdx.x;
+  for (int f = blockIdx.x; f < d.B; f += gridDim.x) {
+    const float2 hb = d.h[f];
+    const float2 *yf = d.y + (size_t)f * d.n_sym;
+    if (tid < 4) s_cnt[tid] = 0;
+    for (int c = 0; c < d.n_cand; c++) {
+      const float2 r = d.rot[c];
+      const float2 hc = make_float2(hb.x * r.x - hb.y * r.y, hb.x * r.y + hb.y * r.x);
+      __syncthreads();  // previous candidate's syndrome pass is done with s_rr / s_pts
+      for (int k = tid; k < Q; k += DM_THREADS) {
+        const float2 s = __ldg(d.points + k);
+        s_pts[k] = make_float2(s.x * hc.x - s.y * hc.y, s.x * hc.y + s.y * hc.x);
+      }
+      if (d.hard_metric)
+        for (int i = tid; i < d.punct; i += DM_THREADS) s_rr[i] = 0;
+      __syncthreads();
+      float *lr_out = d.lr + ((size_t)f * d.n_cand + c) * d.n_tx;
+      for (int i = tid; i < d.n_sym; i += DM_THREADS) {
+        const float2 yy = yf[i];
+        float p[Q];
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+          const float2 s = s_pts[k];
+          const float dx = s.x - yy.x, dy = s.y - yy.y;
+          p[k] = -(dx * dx + dy * dy) * d.inv_var;
+          mx = fmaxf(mx, p[k]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+          p[k] = __expf(p[k] - mx);
+          sum += p[k];
+        }
+        const float inv = 1.0f / sum;
+        float sum2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < Q; k++) {
+          p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
+          sum2 += p[k];
+        }
+        (void)sum2;  // the second normalisation (modem.cc:47-57) cancels in the ratio z0 / z1
+#pragma unroll
+        for (int j = 0; j < BITS; j++) {
+          float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+          for (int k = 0; k < Q; k++) {
+            if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
+            else z1 += p[k];
+          }
+          const float ratio = fminf(fmaxf(z0 / z1, kLrMin), kLrMax);
+          lr_out[i * BITS + j] = ratio;
+          if (d.hard_metric) s_rr[d.punct + i * BITS + j] = z0 > z1 ? 1 : 0;
+        }
+      }
+      if (d.hard_metric) {
+        __syncthreads();
+        int bad = 0;
+        for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
+          int par = 0;
+          for (int e = __ldg(d.row_ptr + rrow); e < __ldg(d.row_ptr + rrow + 1); e++) par ^= s_rr[__ldg(d.col_idx + e)];
+          bad += par;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        if ((tid & 31) == 0 && bad) atomicAdd(&s_cnt[c], bad);
+      }
+    }
+    __syncthreads();
+    if (d.hard_metric && tid == 0) {
+      int best = 0;
+      for (int c = 0; c < d.n_cand; c++) {
+        d.metric[(size_t)f * 4 + c] = (float)s_cnt[c];
+        if (s_cnt[c] < s_cnt[best]) best = c;
+      }
+      for (int c = d.n_cand; c < 4; c++) d.metric[(size_t)f * 4 + c] = 0.f;
+      d.kstar[f] = best;
+    }
+    __syncthreads();
+  }
+}
+
+// BinaryLDPCCodec::ParityCheck (binaryldpccodec.cc:281-299) on bit-packed decisions; one CTA per frame.
+__global__ void syndrome_weight_kernel(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
+                                       const int32_t *col_idx, float *metric) {
+  __shared__ int s_cnt;
+  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const uint32_t *b = bits + (size_t)f * words_n;
+    int bad = 0;
+    for (int r = threadIdx.x; r < m_rows; r += blockDim.x) {
+      uint32_t par = 0;
+      for (int e = __ldg(row_ptr + r); e < __ldg(row_ptr + r + 1); e++) {
+        const int c = __ldg(col_idx + e);
+        par ^= (__ldg(b + (c >> 5)) >> (c & 31));
+      }
+      bad += par & 1u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(&s_cnt, bad);
+    __syncthreads();
+    if (threadIdx.x == 0) metric[f] = (float)s_cnt;
+    __syncthreads();
+  }
+}
+
+__global__ void abs_kernel(int n, float *v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = fabsf(v[i]);
+}
+
+__global__ void argmin4_kernel(int B, const float *metric, int32_t *kstar) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= B) return;
+  int best = 0;
+  for (int c = 1; c < 4; c++)
+    if (metric[f * 4 + c] < metric[f * 4 + best]) best = c;  // std::min_element: first minimum
+  kstar[f] = best;
+}
+
+// ------------------------------------------------------------------------------------------------ utilities
+__global__ void pack_bits_kernel(int F, int nbits, const int32_t *bits, uint32_t *packed) {
+  const int words = (nbits + 31) / 32;
+  const long long total = (long long)F * words * 32;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long wi = i >> 5;
+    const int f = (int)(wi / words), w = (int)(wi % words), t = w * 32 + (int)(i & 31);
+    const int bit = (t < nbits) ? (bits[(size_t)f * nbits + t] != 0) : 0;
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if ((i & 31) == 0) packed[wi] = word;
+  }
+}
+
+__global__ void unpack_bits_kernel(int F, int nbits, int bit_offset, int src_words, const uint32_t *packed, int32_t *bits) {
+  const long long total = (long long)F * nbits;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / nbits), t = (int)(i % nbits) + bit_offset;
+    bits[i] = (int32_t)((packed[(size_t)f * src_words + (t >> 5)] >> (t & 31)) & 1u);
+  }
+}
+
+__global__ void extract_bits_kernel(int F, int nbits, int bit_offset, int src_words, const uint32_t *src, uint32_t *dst) {
+  const int words = (nbits + 31) / 32;
+  const long long total = (long long)F * words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / words), w = (int)(i % words);
+    const uint32_t *s = src + (size_t)f * src_words;
+    const int q = bit_offset + 32 * w, wi = q >> 5, sh = q & 31;
+    uint32_t v = s[wi] >> sh;
+    if (sh && wi + 1 < src_words) v |= s[wi + 1] << (32 - sh);
+    const int valid = nbits - 32 * w;
+    if (valid < 32) v &= (1u << valid) - 1u;
+    dst[i] = v;
+  }
+}
+
+__global__ void lr_to_llr_kernel(size_t n, const float *lr, float *llr) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    llr[i] = logf(lr[i]);
+}
+
+// SourceSink::CntErr (lib/lab/src/sourcesink.cc:29-47), 64-bit counters; one warp per frame.
+__global__ void count_errors_kernel(int B, int k, int k_words, const uint32_t *u, const uint32_t *uh, const int32_t *ret,
+                                    int max_iter, unsigned long long *counters) {
+  __shared__ unsigned long long s_acc[3];
+  if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  unsigned long long err_blk = 0, err_bit = 0, iters = 0;
+  for (int f = blockIdx.x * warps + (threadIdx.x >> 5); f < B; f += gridDim.x * warps) {
+    int ne = 0;
+    for (int w = lane; w < k_words; w += 32) ne += __popc(u[(size_t)f * k_words + w] ^ uh[(size_t)f * k_words + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ne += __shfl_xor_sync(0xffffffffu, ne, o);
+    if (lane == 0) {
+      err_bit += ne;
+      err_blk += ne > 0;
+      if (ret) iters += min(ret[f], max_iter);
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&s_acc[0], err_blk);
+    atomicAdd(&s_acc[1], err_bit);
+    atomicAdd(&s_acc[2], iters);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      atomicAdd(counters + 0, (unsigned long long)B);
+      atomicAdd(counters + 2, (unsigned long long)B * (unsigned long long)k);
+    }
+    if (s_acc[0]) atomicAdd(counters + 1, s_acc[0]);
+    if (s_acc[1]) atomicAdd(counters + 3, s_acc[1]);
+    if (s_acc[2]) atomicAdd(counters + 4, s_acc[2]);
+  }
+}
+
+inline int grid_for(long long total, int threads, int cap = 148 * 16) {
+  long long g = (total + threads - 1) / threads;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+cudaError_t launch_gen_bits(const GenParams &g, uint32_t *u_packed, cudaStream_t s) {
+  const long long total = (long long)g.B * ((g.k_words + 3) / 4);
+  gen_bits_kernel<<<grid_for(total, 256), 256, 0, s>>>(g, u_packed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s) {
+  const int chk_words = (g.n_chk + 31) / 32;
+  const int smem = (ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) * (int)sizeof(uint32_t);
+  encode_kernel<<<(g.B + ENC_FT - 1) / ENC_FT, ENC_THREADS, smem, s>>>(g, u_packed, c_packed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
+                           float2 *h_out, float2 *y, cudaStream_t s) {
+  channel_kernel<<<grid_for((long long)g.B * g.n_sym, 256), 256, 0, s>>>(g, c_packed, h_in, noise, h_out, y);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, int iters, float2 *hhat,
+                          int32_t *passes, int num_sms, cudaStream_t s) {
+  const int spt = (n_sym + KM_THREADS - 1) / KM_THREADS;
+  const int grid = B < num_sms * 8 ? B : num_sms * 8;
+  const int smem = q * (int)sizeof(float2);
+  if (grid < 1) return cudaSuccess;
+  if (spt <= 4) kmeans_kernel<4><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
+  else if (spt <= 9) kmeans_kernel<9><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
+  else if (spt <= 16) kmeans_kernel<16><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
+  else if (spt <= 64) kmeans_kernel<64><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s) {
+  const int grid = d.B < num_sms * 8 ? d.B : num_sms * 8;
+  if (grid < 1) return cudaSuccess;
+  const int smem = (int)sizeof(float2) * d.q + d.n_tx + d.punct + 16;
+  switch (d.bits_per_symbol) {
+    case 1: demap_kernel<1><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 2: demap_kernel<2><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 3: demap_kernel<3><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 4: demap_kernel<4><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 5: demap_kernel<5><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 6: demap_kernel<6><<<grid, DM_THREADS, smem, s>>>(d); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
+                                   const int32_t *col_idx, float *metric, cudaStream_t s) {
+  if (F < 1) return cudaSuccess;
+  syndrome_weight_kernel<<<F < 148 * 8 ? F : 148 * 8, 256, 0, s>>>(F, bits, words_n, m_rows, row_ptr, col_idx, metric);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_abs_inplace(int n, float *v, cudaStream_t s) {
+  if (n < 1) return cudaSuccess;
+  abs_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, v);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_argmin4(int B, const float *metric, int32_t *kstar, cudaStream_t s) {
+  if (B < 1) return cudaSuccess;
+  argmin4_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, metric, kstar);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_bits(int F, int nbits, const int32_t *bits, uint32_t *packed, cudaStream_t s) {
+  const long long total = (long long)F * ((nbits + 31) / 32) * 32;
+  if (total < 1) return cudaSuccess;
+  pack_bits_kernel<<<grid_for(total, 256), 256, 0, s>>>(F, nbits, bits, packed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_bits(int F, int nbits, int bit_offset, int src_words, const uint32_t *packed, int32_t *bits,
+                               cudaStream_t s) {
+  const long long total = (long long)F * nbits;
+  if (total < 1) return cudaSuccess;
+  unpack_bits_kernel<<<grid_for(total, 256), 256, 0, s>>>(F, nbits, bit_offset, src_words, packed, bits);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_bits(int F, int nbits, int bit_offset, int src_words, const uint32_t *src, uint32_t *dst,
+                                cudaStream_t s) {
+  const long long total = (long long)F * ((nbits + 31) / 32);
+  if (total < 1) return cudaSuccess;
+  extract_bits_kernel<<<grid_for(total, 256), 256, 0, s>>>(F, nbits, bit_offset, src_words, src, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lr_to_llr(size_t n, const float *lr, float *llr, cudaStream_t s) {
+  if (n < 1) return cudaSuccess;
+  lr_to_llr_kernel<<<grid_for((long long)n, 256), 256, 0, s>>>(n, lr, llr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_errors(int B, int k, int k_words, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
+                                const int32_t *ret, int max_iter, unsigned long long *counters, cudaStream_t s) {
+  if (B < 1) return cudaSuccess;
+  const int warps = 8;
+  int grid = (B + warps - 1) / warps;
+  if (grid > 148 * 4) grid = 148 * 4;
+  count_errors_kernel<<<grid, warps * 32, 0, s>>>(B, k, k_words, u_packed, uu_hat_packed, ret, max_iter, counters);
+  return cudaGetLastError();
+}
+
+}  // namespace kml

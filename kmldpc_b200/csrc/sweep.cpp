@@ -1,0 +1,279 @@
+// Host-side sweep driver: what Simulator::Simulator + Simulator::Simulate + Simulator::run do around the per-frame loop
+// (src/simulator.cc:3-109), on top of kml_simulate.  One host thread per GPU; frames of an SNR point are handed out in
+// chunks from a shared cursor; the 64-bit counters are summed on the host; lines are formatted exactly like
+// SourceSink::PrintResult (lib/lab/src/sourcesink.cc:50-65) and the result tables of simulator.cc:48-66.
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kml_internal.h"
+
+namespace {
+
+using kml::set_global_error;
+
+// ---- the TOML subset the reference's config.toml uses: [table], key = number | true | false | "string", # comments
+struct Toml {
+  std::map<std::string, std::string> kv;  // "table.key" → raw value (strings unquoted)
+  bool has(const std::string &k) const { return kv.count(k) != 0; }
+};
+
+std::string trim(const std::string &s) {
+  size_t a = 0, b = s.size();
+  while (a < b && std::isspace((unsigned char)s[a])) a++;
+  while (b > a && std::isspace((unsigned char)s[b - 1])) b--;
+  return s.substr(a, b - a);
+}
+
+bool parse_toml(const char *path, Toml &t, std::string &err) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in.is_open()) {
+    err = std::string("cannot open ") + path;
+    return false;
+  }
+  std::string line, table;
+  int ln = 0;
+  while (std::getline(in, line)) {
+    ln++;
+    if (ln == 1 && line.size() >= 3 && (unsigned char)line[0] == 0xEF) line = line.substr(3);  // BOM
+    // strip comments outside strings
+    bool in_str = false;
+    for (size_t i = 0; i < line.size(); i++) {
+      if (line[i] == '"') in_str = !in_str;
+      else if (line[i] == '#' && !in_str) {
+        line.resize(i);
+        break;
+      }
+    }
+    line = trim(line);
+    if (line.empty()) continue;
+    if (line.front() == '[') {
+      if (line.back() != ']') {
+        err = "line " + std::to_string(ln) + ": bad table header";
+        return false;
+      }
+      table = trim(line.substr(1, line.size() - 2));
+      continue;
+    }
+    const size_t eq = line.find('=');
+    if (eq == std::string::npos) {
+      err = "line " + std::to_string(ln) + ": expected key = value";
+      return false;
+    }
+    std::string key = trim(line.substr(0, eq)), val = trim(line.substr(eq + 1));
+    if (key.size() >= 2 && key.front() == '"' && key.back() == '"') key = key.substr(1, key.size() - 2);
+    if (val.size() >= 2 && val.front() == '"' && val.back() == '"') val = val.substr(1, val.size() - 2);
+    t.kv[table.empty() ? key : table + "." + key] = val;
+  }
+  return true;
+}
+
+bool get_num(const Toml &t, const std::string &k, double &out, std::string &err, bool required = true) {
+  auto it = t.kv.find(k);
+  if (it == t.kv.end()) {
+    if (required) err = "missing key " + k;  // toml11 throws here (SURVEY §5 "Config")
+    return !required;
+  }
+  char *end = nullptr;
+  std::string v = it->second;
+  v.erase(std::remove(v.begin(), v.end(), '_'), v.end());
+  out = std::strtod(v.c_str(), &end);
+  if (end == v.c_str() || *end) {
+    err = "key " + k + ": not a number";
+    return false;
+  }
+  return true;
+}
+
+bool get_bool(const Toml &t, const std::string &k, int &out, std::string &err, bool required = true) {
+  auto it = t.kv.find(k);
+  if (it == t.kv.end()) {
+    if (required) err = "missing key " + k;
+    return !required;
+  }
+  if (it->second == "true") out = 1;
+  else if (it->second == "false") out = 0;
+  else {
+    err = "key " + k + ": not a boolean";
+    return false;
+  }
+  return true;
+}
+
+std::string fmt_point_line(double snr, uint64_t tot_blk, uint64_t err_blk, uint64_t err_bit, double ber, double fer) {
+  std::stringstream s;  // sourcesink.cc:50-65
+  s << std::fixed << std::setprecision(3) << std::setfill('0') << "SNR = " << std::setw(3) << std::right << snr << ' '
+    << "Total blk = " << std::setw(7) << std::right << std::setprecision(0) << tot_blk << ' '
+    << "Error blk = " << std::setw(7) << std::right << err_blk << ' '
+    << "Error bit = " << std::setw(7) << std::right << err_bit << ' ' << std::fixed << std::setprecision(14)
+    << "BER = " << ber << ' ' << "FER = " << fer;
+  return s.str();
+}
+
+std::string fmt_table_row(double snr, double v) {
+  std::stringstream s;  // simulator.cc:52-56
+  s << std::fixed << std::setprecision(3) << std::setfill('0') << std::setw(3) << std::right << snr << ' '
+    << std::setprecision(14) << v;
+  return s.str();
+}
+
+}  // namespace
+
+extern "C" int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg) {
+  if (!config_toml || !cfg) return KML_ERR_ARG;
+  Toml t;
+  std::string err;
+  if (!parse_toml(config_toml, t, err)) {
+    set_global_error(err);
+    return KML_ERR_IO;
+  }
+  std::memset(cfg, 0, sizeof *cfg);
+  double d = 0;
+  int b = 0;
+  bool ok = true;
+  ok = ok && get_num(t, "range.minimum_snr", cfg->min_snr, err);
+  ok = ok && get_num(t, "range.maximum_snr", cfg->max_snr, err);
+  ok = ok && get_num(t, "range.step_snr", cfg->step_snr, err);
+  if (ok && (ok = get_num(t, "range.maximum_error_number", d, err))) cfg->max_err_blk = (uint64_t)d;
+  if (ok && (ok = get_num(t, "range.maximum_block_number", d, err))) cfg->max_num_blk = (uint64_t)d;
+  ok = ok && get_num(t, "range.thread_block_number", d, err);  // CPU fan-out granularity: read, unused
+  if (ok && (ok = get_bool(t, "decoder.true_h_arg", b, err))) cfg->known_h = b;
+  if (ok && (ok = get_bool(t, "xcodec.5gldpc", b, err))) cfg->is_5g = b;
+  if (ok && (ok = get_bool(t, "xcodec.metric_type", b, err))) cfg->metric_type = b;
+  if (ok && (ok = get_num(t, "xcodec.metric_iter", d, err))) cfg->metric_iter = (int)d;
+  if (ok && (ok = get_bool(t, "histogram.enable", b, err))) cfg->histogram_enable = b;
+  if (ok && (ok = get_num(t, "ldpc.max_iter", d, err))) cfg->max_iter = (int)d;
+  if (ok && (ok = get_bool(t, "ldpc.active", b, err))) cfg->encoder_active = b;
+  if (ok && !t.has("ldpc.matrix_file")) { ok = false; err = "missing key ldpc.matrix_file"; }
+  if (ok && !t.has("modem.modem_file")) { ok = false; err = "missing key modem.modem_file"; }
+  if (!ok) {
+    set_global_error(std::string(config_toml) + ": " + err);
+    return KML_ERR_IO;
+  }
+  std::snprintf(cfg->matrix_file, sizeof cfg->matrix_file, "%s", t.kv["ldpc.matrix_file"].c_str());
+  std::snprintf(cfg->modem_file, sizeof cfg->modem_file, "%s", t.kv["modem.modem_file"].c_str());
+  // optional [gpu] table — unknown tables are ignored by the reference binary, so one file serves both
+  cfg->seed = 17;  // echo of the reference's fixed LCG state
+  cfg->n_gpus = 1;
+  cfg->max_batch = 0;
+  cfg->early_exit = 1;
+  if (get_num(t, "gpu.seed", d, err, false) && t.has("gpu.seed")) cfg->seed = (uint64_t)d;
+  if (get_num(t, "gpu.gpus", d, err, false) && t.has("gpu.gpus")) cfg->n_gpus = (int)d;
+  if (get_num(t, "gpu.batch", d, err, false) && t.has("gpu.batch")) cfg->max_batch = (int)d;
+  if (get_bool(t, "gpu.early_exit", b, err, false) && t.has("gpu.early_exit")) cfg->early_exit = b;
+  return KML_OK;
+}
+
+extern "C" int kml_sweep_points(const kml_sweep_cfg *cfg) {
+  if (!cfg || !(cfg->step_snr > 0)) return 0;
+  return (int)(unsigned long)((cfg->max_snr - cfg->min_snr) / cfg->step_snr + 1);  // simulator.cc:27
+}
+
+extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
+                             void (*log_cb)(const char *, void *), void *user) {
+  if (!cfg) return KML_ERR_ARG;
+  if (cfg->histogram_enable) {
+    set_global_error("[histogram] enable = true is not supported by the GPU path (SURVEY §2 row 16)");
+    return KML_ERR_ARG;
+  }
+  const int n_pts = kml_sweep_points(cfg);
+  if (n_pts < 1) {
+    set_global_error("empty SNR range");
+    return KML_ERR_ARG;
+  }
+  auto log = [&](const std::string &s) {
+    if (log_cb) log_cb(s.c_str(), user);
+  };
+  auto path_of = [&](const char *f) {
+    std::string p = f;
+    if (data_dir && *data_dir && !p.empty() && p[0] != '/') p = std::string(data_dir) + "/" + p;
+    return p;
+  };
+  {
+    std::stringstream s;  // simulator.cc:16-21
+    s << '[' << std::fixed << std::setprecision(3) << cfg->min_snr << ',' << cfg->step_snr << ',' << cfg->max_snr << ']';
+    log(s.str());
+    s.str("");
+    s << '[' << "MAX_ERROR_BLK = " << cfg->max_err_blk << ',' << "MAX_BLK = " << cfg->max_num_blk << ']';
+    log(s.str());
+  }
+  log(cfg->is_5g ? "Using 5G LDPC." : "Using traditional LDPC.");  // kmcodec.cc:27,32
+  kml_code *code = nullptr;
+  kml_modem *modem = nullptr;
+  int rc = kml_code_load(path_of(cfg->matrix_file).c_str(), cfg->is_5g, cfg->encoder_active, &code);
+  if (rc != KML_OK) return rc;
+  rc = kml_modem_load(path_of(cfg->modem_file).c_str(), &modem);
+  if (rc != KML_OK) {
+    kml_code_free(code);
+    return rc;
+  }
+  const int G = cfg->n_gpus > 0 ? cfg->n_gpus : 1;
+  kml_opts o{};
+  o.max_iter = cfg->max_iter; o.known_h = cfg->known_h; o.metric_type = cfg->metric_type; o.metric_iter = cfg->metric_iter;
+  o.kmeans_iter = 20; o.early_exit = cfg->early_exit; o.max_batch = cfg->max_batch;
+  std::vector<kml_ctx *> ctx(G, nullptr);
+  for (int g = 0; g < G && rc == KML_OK; g++) rc = kml_create(&ctx[g], g, code, modem, &o);
+  if (rc == KML_OK) {
+    int32_t info[8];
+    kml_info(ctx[0], info);
+    const uint64_t chunk = (uint64_t)info[7];
+    for (int i = 0; i < n_pts && rc == KML_OK; i++) {
+      const double snr = cfg->min_snr + cfg->step_snr * i;
+      std::atomic<uint64_t> cursor{0}, err_blk{0};
+      std::mutex mu;
+      uint64_t tot[4] = {0, 0, 0, 0};
+      std::atomic<int> failed{KML_OK};
+      auto worker = [&](int g) {
+        while (failed.load() == KML_OK) {
+          if (cfg->max_err_blk && err_blk.load() >= cfg->max_err_blk) break;  // simulator.cc:117
+          const uint64_t begin = cursor.fetch_add(chunk);
+          if (begin >= cfg->max_num_blk) break;
+          const uint64_t count = std::min<uint64_t>(chunk, cfg->max_num_blk - begin);
+          uint64_t cnt[4] = {0, 0, 0, 0};
+          // the frame index space of a point is offset by the point index so that points use disjoint Philox streams
+          const int r = kml_simulate(ctx[g], snr, cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull, begin, count, 0, cnt, nullptr);
+          if (r != KML_OK) {
+            failed.store(r);
+            set_global_error(kml_last_error(ctx[g]));
+            break;
+          }
+          err_blk.fetch_add(cnt[1]);
+          std::lock_guard<std::mutex> lk(mu);
+          for (int k = 0; k < 4; k++) tot[k] += cnt[k];
+        }
+      };
+      std::vector<std::thread> th;
+      for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+      for (auto &t : th) t.join();
+      rc = failed.load();
+      const double b = tot[2] ? (double)tot[3] / (double)tot[2] : 0.0, f = tot[0] ? (double)tot[1] / (double)tot[0] : 0.0;
+      if (ber) ber[i] = b;
+      if (fer) fer[i] = f;
+      if (counters)
+        for (int k = 0; k < 4; k++) counters[(size_t)i * 4 + k] = tot[k];
+      log(fmt_point_line(snr, tot[0], tot[1], tot[3], b, f));
+    }
+    if (rc == KML_OK && ber && fer) {
+      log("BER Result");
+      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, ber[i]));
+      log("FER Result");
+      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, fer[i]));
+    }
+  }
+  for (auto *c : ctx) kml_destroy(c);
+  kml_modem_free(modem);
+  kml_code_free(code);
+  return rc;
+}
