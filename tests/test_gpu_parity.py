@@ -83,7 +83,7 @@ def test_demapper_llr(name, frames):
     y = np.stack([r.y for r in rs])
     # demap with the channel value the reference finally used: oracle P0 is the demap of h_hat * rot[kstar] (or true h)
     rot = np.exp(1j * (3.14159265358979 / 2) * np.arange(4))
-    h_used = np.array([r.h if olink.opts.known_h else r.hhat * rot[r.kstar] for r in rs])
+    h_used = np.array([r.h if bool(olink.opts.known_h) else r.hhat * rot[r.kstar] for r in rs])
     llr = link.demap(y, h_used, var)
     ref = np.stack([util.llr_of_p0(r.p0) for r in rs])
     tol = 1e-4 * np.maximum(np.abs(ref), 1.0)  # pure relative is ill-posed near 0
@@ -164,11 +164,11 @@ def test_receiver_chain(name, frames, kb):
     soft = bool(olink.opts.metric_type)
     if not olink.opts.known_h:
         assert (kstar == ref_k).mean() >= (0.9 if soft else 0.99)
-    good = (kstar == ref_k) | olink.opts.known_h
+    good = (kstar == ref_k) | bool(olink.opts.known_h)
     assert (ret[good] == ref_ret[good]).mean() >= 0.99
     syn = np.array([olink.code.parity_check(r.cc_hat) for r in rs])
     conv = (syn == 0) & good & (ret == ref_ret)
-    assert np.array_equal(uu[conv], ref_uu[conv])
+    assert np.array_equal(uu[conv], ref_uu[conv]), (np.where(conv)[0], (uu != ref_uu).sum(axis=1), ret, ref_ret, syn)
     fe, ref_fe = (uu != u).any(axis=1), (ref_uu != u).any(axis=1)
     assert (fe == ref_fe).mean() >= 0.98
     # the reference's quirks survive: QPSK-file 0/180 tie, phi1 blind FER = 1
