@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — decoded Mbit/s of the kmldpc link receiver on B200 (and the reference CPU arm).
+
+Workload (config.workload "C1-fixedI50"): BASELINE.json configs[0] — PEG2304 regular R1/2 + 2bits_QPSK.txt, blind
+k-means (20 passes) → 4-rotation resolve → soft demap → flooding sum-product BP, max_iter = 50 — at the FIXED iteration
+count the metric is quoted on: SNR = -5 dB, where the syndrome never clears, so every frame executes exactly 50
+iterations in BOTH arms with the reference's semantics unchanged.  The reported
+`iters_per_frame` proves it.
+
+One step = one batch of B frames through the receiver path (k-means → resolve → demap → decode → error count).
+  value : inputs (received symbols y, float32) already resident in HBM, kml_receive_dev + kml_count_errors_dev on one
+          stream, CUDA events on that stream.  Batches rotate over a pool larger than L2.
+  e2e   : the same batches through the host-buffer C-ABI call kml_receive (pinned host y in → packed decisions out),
+          H2D + D2H inside the timed region.
+  roofline : the BP decoder kernel alone (kml_decode_dev on LLRs resident in HBM), CUDA events, against the shared
+          memory bandwidth bound of SURVEY §8(d) (16 B per edge-iteration); HBM figures for its LLR I/O beside it.
+  cpu_baseline / --impl reference : the UNMODIFIED reference classes (oracle/_ref/ref_harness, built from
+          /root/reference in the build container) on all host cores, receiver stages only; falls back to the C port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MATRIX, MODEM = "PEG2304regular0.5.txt", "2bits_QPSK.txt"
+SNR_DB, MAX_ITER, KMEANS_ITER = -5.0, 50, 20
+K_INFO, N_CODE, N_EDGES, N_SYM = 1152, 2304, 6912, 1152
+METRIC = "LDPC decoded Mbit/s (PEG2304 R1/2 + QPSK, blind k-means detect + BP decode, fixed 50 iterations)"
+CONFIG = {"workload": "C1-fixedI50", "code": "PEG2304 regular R1/2", "modem": "2bits_QPSK", "snr_db": SNR_DB,
+          "max_iter": MAX_ITER, "kmeans_iter": KMEANS_ITER, "detector": "blind k-means + 4-rotation resolve",
+          "decoder": "flooding sum-product (fp32 ratio / small-probability messages)",
+          "path": "receiver: y -> k-means -> resolve -> demap -> BP -> error count"}
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference_sample(frames_per_proc: int, procs: int, seed0: int = 1000):
+    """Runs the reference's own receiver code on `procs` host processes.  Returns dict with decoded Mbit/s of the
+    receiver stages (k-means + resolve + demap + decode), whole-frame Mbit/s, kind, cores, iterations per frame."""
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    cfg = os.path.join(ROOT, "config")
+    if os.path.exists(harness) and os.access(harness, os.X_OK):
+        cmds = [[harness, "time", f"cfgdir={cfg}", f"matrix={MATRIX}", f"modem={MODEM}", f"snr={SNR_DB}",
+                 f"frames={frames_per_proc}", f"max_iter={MAX_ITER}", f"seed={seed0 + 7919 * i}"] for i in range(procs)]
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen(c, stdout=subprocess.PIPE, text=True) for c in cmds]
+        outs = [p.communicate()[0] for p in ps]
+        wall = time.perf_counter() - t0
+        rs = [json.loads(o.strip().splitlines()[-1]) for o in outs]
+        rx = [r["t_kmeans"] + r["t_resolve"] + r["t_demap"] + r["t_decode"] for r in rs]
+        full = [x + r["t_src_enc"] + r["t_chan"] for x, r in zip(rx, rs)]
+        frames = frames_per_proc * procs
+        return {"kind": "reference", "cores": procs, "frames": frames, "wall_s": wall,
+                "rx_mbps": frames * K_INFO / max(rx) / 1e6, "frame_mbps": frames * K_INFO / max(full) / 1e6,
+                "rx_s": max(rx), "iters_per_frame": statistics.mean(r["avg_ret"] for r in rs),
+                "ms_per_frame_per_core": 1e3 * statistics.mean(rx) / frames_per_proc}
+    # C port of the same algorithm (oracle/kml_oracle.c), pthreads; whole frame (its stages are not timed apart)
+    from oracle import kml_oracle as ko
+    link = ko.Link(MATRIX, MODEM, max_iter=MAX_ITER)
+    frames = frames_per_proc * procs
+    t0 = time.perf_counter()
+    cnt, iters = link.run(SNR_DB, frames, threads=procs, seed0=seed0)
+    wall = time.perf_counter() - t0
+    return {"kind": "port", "cores": procs, "frames": frames, "wall_s": wall, "rx_mbps": frames * K_INFO / wall / 1e6,
+            "frame_mbps": frames * K_INFO / wall / 1e6, "rx_s": wall, "iters_per_frame": iters / frames,
+            "ms_per_frame_per_core": 1e3 * wall * procs / frames}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    fpp = args.ref_frames
+    for _ in range(args.warmup if args.warmup < 2 else 1):  # one untimed pass pages the binary and data files in
+        run_reference_sample(max(4, fpp // 8), cores)
+    vals, secs, last = [], [], None
+    for _ in range(args.steps):
+        last = run_reference_sample(fpp, cores)
+        vals.append(last["rx_mbps"])
+        secs.append(last["rx_s"])
+    v = statistics.mean(vals)
+    sample = (f"{args.steps} steps x {cores} processes x {fpp} frames of the workload (LCG-generated, distinct seeds); "
+              f"receiver stages only (k-means+resolve+demap+decode) timed inside the reference harness; "
+              f"{last['iters_per_frame']:.1f} decoder iterations/frame")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mbit/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(secs), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": v, "unit": "Mbit/s", "cores": cores, "kind": last["kind"], "sample": sample},
+            "e2e": {"value": v, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "iters_per_frame": last["iters_per_frame"], "whole_frame_mbps": last["frame_mbps"],
+            "ms_per_frame_per_core": last["ms_per_frame_per_core"]}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------- our arm (GPU)
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import kmldpc_b200 as kb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, pool = args.batch, args.pool
+    link = kb.Link(kb.LdpcCode(MATRIX), kb.Modem(MODEM), max_iter=MAX_ITER, kmeans_iter=KMEANS_ITER, early_exit=True,
+                   max_batch=B, device=local)
+    kw = link.k_words
+    var = kb.snr_to_var(SNR_DB)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic inputs: `pool` batches of B frames, Philox-generated on the device (untimed), > L2 in total
+    ys = [torch.empty((B, N_SYM, 2), dtype=torch.float32, device=dev) for _ in range(pool)]
+    us = [torch.empty((B, kw), dtype=torch.int32, device=dev) for _ in range(pool)]
+    hs = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    for i in range(pool):
+        frame0 = (rank * pool + i) * B
+        link.generate_dev(B, SNR_DB, 17, frame0, us[i].data_ptr(), hs.data_ptr(), ys[i].data_ptr(), stream)
+    uu_hat = torch.empty((B, kw), dtype=torch.int32, device=dev)
+    ret = torch.empty((B,), dtype=torch.int32, device=dev)
+    counters = torch.zeros(4, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def step_dev(i):
+        link.receive_dev(B, ys[i % pool].data_ptr(), var, uu_hat.data_ptr(), ret.data_ptr(), stream=stream)
+        link.count_errors_dev(B, us[i % pool].data_ptr(), uu_hat.data_ptr(), counters.data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident
+    for i in range(args.warmup):
+        step_dev(i)
+    counters.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = link.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    if world > 1:
+        dist.all_reduce(counters)  # the only collective of the path: 4 x int64 error counters (NCCL)
+    ev1.record()
+    barrier()
+    launches = link.launches - l0
+    ms_total = ev0.elapsed_time(ev1)
+    iters_mean = float(ret.float().clamp(max=MAX_ITER).mean().item())
+    cnt = counters.tolist()
+
+    # ---- e2e: host buffers (pinned), H2D + D2H inside the timed region
+    y_host = [torch.empty((B, N_SYM, 2), dtype=torch.float32).pin_memory() for _ in range(min(pool, 3))]
+    for i, yh in enumerate(y_host):
+        yh.copy_(ys[i])
+    uu_host = torch.empty((B, kw), dtype=torch.int32).pin_memory()
+    ret_host = torch.empty((B,), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_host(i):
+        link.receive_raw(B, y_host[i % len(y_host)].data_ptr(), var, uu_host.data_ptr(), ret_host.data_ptr())
+
+    for i in range(max(1, min(args.warmup, 3))):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    # decisions of the host path equal those of the device path on the same batch
+    link.receive_dev(B, ys[(args.steps - 1) % len(y_host)].data_ptr(), var, uu_hat.data_ptr(), ret.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    same = bool((uu_hat.cpu() == uu_host).all().item())
+
+    # ---- roofline leg: the decoder kernel alone on LLRs resident in HBM
+    hhat = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    llr = torch.empty((B, N_CODE), dtype=torch.float32, device=dev)
+    cc_hat = torch.empty((B, link.words_n), dtype=torch.int32, device=dev)
+    link.kmeans_dev(B, ys[0].data_ptr(), hhat.data_ptr(), 0, stream)
+    link.demap_dev(B, ys[0].data_ptr(), hhat.data_ptr(), var, llr.data_ptr(), stream)
+    for _ in range(2):
+        link.decode_dev(B, llr.data_ptr(), False, MAX_ITER, cc_hat.data_ptr(), ret.data_ptr(), stream)
+    torch.cuda.synchronize()
+    reps = max(3, min(10, args.steps))
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(reps):
+        link.decode_dev(B, llr.data_ptr(), False, MAX_ITER, cc_hat.data_ptr(), ret.data_ptr(), stream)
+    d1.record()
+    torch.cuda.synchronize()
+    dec_ms = d0.elapsed_time(d1) / reps
+    dec_iters = float(ret.float().clamp(max=MAX_ITER).mean().item())
+    # k-means alone (the metric's second half: k-means frames/s)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    link.kmeans_dev(B, ys[1 % pool].data_ptr(), hhat.data_ptr(), 0, stream)
+    k0.record()
+    for i in range(reps):
+        link.kmeans_dev(B, ys[i % pool].data_ptr(), hhat.data_ptr(), 0, stream)
+    k1.record()
+    torch.cuda.synchronize()
+    km_ms = k0.elapsed_time(k1) / reps
+
+    # ---- secondary: fused Monte-Carlo path (Philox → … → counters) and the early-exit figure at 15 dB (config.toml SNR)
+    t_f = None
+    if rank == 0 and not args.quick:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fcnt, fit = link.simulate(SNR_DB, B * 4, seed=99)
+        t_f = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ecnt, eit = link.simulate(15.0, B * 8, seed=99)
+        t_e = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- max over ranks
+    times = torch.tensor([ms_total, e2e_s * 1e3, dec_ms, km_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, dec_ms, km_ms = times.tolist()
+    if rank == 0:
+        frames = world * B * args.steps
+        value = frames * K_INFO / (ms_total * 1e-3) / 1e6
+        e2e = frames * K_INFO / (e2e_ms * 1e-3) / 1e6
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        smem_peak = n_sm * 128 * sm_max * 1e6 / 1e9           # GB/s: 128 B/clk/SM (derived — not in MEASURED_PEAKS)
+        alg_bytes = 16.0 * N_EDGES * MAX_ITER * B             # 16 B of shared-memory traffic per edge-iteration
+        achieved = alg_bytes / (dec_ms * 1e-3) / 1e9
+        hbm_bytes = B * (N_CODE * 4 + link.words_n * 4 + 4)  # LLR in + packed decisions + return value out
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "decoder_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            r = run_reference_sample(args.ref_frames, cores)
+            cpu = {"value": r["rx_mbps"], "unit": "Mbit/s", "cores": cores, "kind": r["kind"],
+                   "sample": f"{cores} processes x {args.ref_frames} frames of the same workload, receiver stages only, "
+                             f"{r['iters_per_frame']:.1f} iterations/frame, wall {r['wall_s']:.1f} s",
+                   "whole_frame_mbps": r["frame_mbps"], "ms_per_frame_per_core": r["ms_per_frame_per_core"]}
+        line = {"metric": METRIC, "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(CONFIG, batch_frames_per_gpu=B, input_pool_batches=pool,
+                               l2_policy=f"inputs rotate over {pool} batches = {pool * B * N_SYM * 8 / 2**20:.0f} MiB > 126 MiB L2"),
+                "frames_per_s": frames / (ms_total * 1e-3), "iters_per_frame": iters_mean,
+                "counters": {"tot_blk": cnt[0], "err_blk": cnt[1], "tot_bit": cnt[2], "err_bit": cnt[3]},
+                "e2e": {"value": e2e, "unit": "Mbit/s", "h2d_bytes_per_step": B * N_SYM * 8,
+                        "d2h_bytes_per_step": B * kw * 4 + B * 4, "ms_per_step": e2e_ms / args.steps,
+                        "timer": "host wall clock around the blocking C-ABI call kml_receive (pinned buffers)",
+                        "matches_device_path": same},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "smem", "kernel": "bp_regular_kernel<6,3> (BP decoder)", "achieved": achieved,
+                             "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak, "traffic": traffic,
+                             "peak_source": f"derived: {n_sm} SMs x 128 B/clk x {sm_max:.0f} MHz (shared memory; not in MEASURED_PEAKS.json)",
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dec_ms, "iters_per_frame": dec_iters,
+                             "edge_iterations_per_s": N_EDGES * MAX_ITER * B / (dec_ms * 1e-3),
+                             "decode_only_mbps": B * K_INFO / (dec_ms * 1e-3) / 1e6,
+                             "hbm": {"bound": "hbm", "achieved": hbm_bytes / (dec_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": hbm_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak,
+                                     "note": "LLR in + packed decisions out of the standalone decoder; never binding",
+                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}},
+                "kmeans": {"frames_per_s": world * B / (km_ms * 1e-3), "ms_per_batch": km_ms, "passes": KMEANS_ITER},
+                "clocks": clocks}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if t_f is not None:
+            line["fused_simulate"] = {"mbps": 4 * B * K_INFO / t_f / 1e6, "frames": 4 * B, "iters_per_frame": fit / (4 * B),
+                                      "note": "kml_simulate: Philox bits+encode+map+channel+receiver+count, host wall clock"}
+            line["early_exit_15dB"] = {"mbps": 8 * B * K_INFO / t_e / 1e6, "frames": 8 * B, "iters_per_frame": eit / (8 * B),
+                                       "fer": ecnt[1] / ecnt[0], "ber": ecnt[3] / ecnt[2],
+                                       "note": "config.toml's SNR point through kml_simulate with the reference's early exit"}
+        print(json.dumps(line))
+    link.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="frames per step per GPU")
+    ap.add_argument("--pool", type=int, default=2, help="distinct input batches (pool x batch x 9216 B must exceed L2)")
+    ap.add_argument("--ref-frames", type=int, default=150, help="frames per host process in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary fused / early-exit figures")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -166,6 +166,8 @@ int kml_generate_dev(kml_ctx *ctx, int B, double snr_db, uint64_t seed, uint64_t
 int kml_kmeans_dev(kml_ctx *ctx, int B, const float *y, float *hhat, int32_t *passes, void *stream);
 int kml_receive_dev(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
                     int32_t *ret, void *stream);
+/* y[B][n_sym][2], h[B][2] in HBM -> llr[B][n_tx] (natural log) in HBM; feeds kml_decode_dev for standalone runs. */
+int kml_demap_dev(kml_ctx *ctx, int B, const float *y, const float *h, double var, float *llr, void *stream);
 /* llr/lr in HBM -> packed decisions in HBM.  in_is_lr = 1 when the input already holds likelihood ratios P0/P1. */
 int kml_decode_dev(kml_ctx *ctx, int B, const float *llr, int in_is_lr, int iter_count, uint32_t *cc_hat_packed,
                    int32_t *ret, void *stream);

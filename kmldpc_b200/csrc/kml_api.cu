@@ -705,6 +705,19 @@ extern "C" int kml_receive_dev(kml_ctx *c, int B, const float *y, const float *t
   return rc;
 }
 
+extern "C" int kml_demap_dev(kml_ctx *c, int B, const float *y, const float *h, double var, float *llr, void *stream) {
+  KML_RC(check_batch(c, B));
+  if (!y || !h || !llr || !(var > 0)) return fail_arg(c, "kml_demap_dev: bad argument");
+  Lane &l = c->lane[0];
+  DemapParams d = demap_params(c, l, B, var, 1, 0);
+  d.y = (const float2 *)y;
+  d.h = (const float2 *)h;
+  d.lr = llr;
+  KML_LAUNCH(c, launch_demap(d, c->num_sms, (cudaStream_t)stream));
+  KML_LAUNCH(c, launch_lr_to_llr((size_t)B * c->n_tx, llr, llr, (cudaStream_t)stream));
+  return KML_OK;
+}
+
 extern "C" int kml_decode_dev(kml_ctx *c, int B, const float *llr, int in_is_lr, int iter_count, uint32_t *cc_hat_packed,
                               int32_t *ret, void *stream) {
   KML_RC(check_batch(c, B));

@@ -247,6 +247,9 @@ class Link:
         self._check(self._lib.kml_receive_dev(self._h, B, y_ptr, true_h_ptr or None, var, uu_hat_packed_ptr,
                                               ret_ptr or None, stream), "kml_receive_dev")
 
+    def demap_dev(self, B, y_ptr, h_ptr, var, llr_ptr, stream=0):
+        self._check(self._lib.kml_demap_dev(self._h, B, y_ptr, h_ptr, var, llr_ptr, stream), "kml_demap_dev")
+
     def decode_dev(self, B, llr_ptr, in_is_lr, iter_count, cc_hat_packed_ptr, ret_ptr, stream=0):
         self._check(self._lib.kml_decode_dev(self._h, B, llr_ptr, int(in_is_lr), iter_count, cc_hat_packed_ptr, ret_ptr,
                                              stream), "kml_decode_dev")

@@ -14,7 +14,7 @@
 //
 // Usage: ref_harness <dump|time> key=value ...
 //   cfgdir=<dir with H + constellation files>  matrix=<file> modem=<file> g5=0|1 active=0|1
-//   known_h=0|1 metric_type=0|1 metric_iter=5 max_iter=50 snr=10 frames=8 out=<dir> skip=<frames>
+//   known_h=0|1 metric_type=0|1 metric_iter=5 max_iter=50 snr=10 frames=8 out=<dir> skip=<frames> seed=<LCG state>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -189,6 +189,19 @@ main(int argc, char **argv) {
   lab::logger::Log::get().set_log_level(lab::logger::Error);
 
   lab::CLCRandNum::Get().SetSeed(-1);// state = 17
+  const long seed = a.i("seed", 17);
+  if (seed != 17 && seed > 0) {
+    // any other start state: SetSeed(flag > 0) reads it from stdin (lib/lab/src/randnum.cc:19-25)
+    char tmpl[] = "/tmp/kml_seed_XXXXXX";
+    int fd = mkstemp(tmpl);
+    if (fd >= 0) {
+      dprintf(fd, "%ld\n", seed);
+      close(fd);
+      if (freopen(tmpl, "r", stdin)) lab::CLCRandNum::Get().SetSeed(1);
+      unlink(tmpl);
+      printf("\n");
+    }
+  }
   lab::CWHRandNum::Get().SetSeed(-1);
 
   std::ostringstream ts;
