@@ -93,6 +93,10 @@ const char *kml_last_error(const kml_ctx *ctx);  /* ctx may be NULL: message of 
 int kml_set_early_exit(kml_ctx *ctx, int early_exit);
 /* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
 int kml_info(const kml_ctx *ctx, int32_t info[8]);
+/* Decoder launch facts: info[0..7] = kernel kind, threads per CTA, dynamic shared memory bytes, CTAs per SM,
+ * layout annealing residual, shared-memory wavefronts above one per variable-node gather (0 = conflict free),
+ * variable-node gather instructions per iteration (the ideal wavefront count), row slots. */
+int kml_decoder_info(const kml_ctx *ctx, int32_t info[8]);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t kml_launch_count(const kml_ctx *ctx);
 

@@ -57,6 +57,7 @@ SYMBOLS = {
     "kml_last_error": (C.c_char_p, [C.c_void_p]),
     "kml_set_early_exit": (C.c_int, [C.c_void_p, C.c_int]),
     "kml_info": (C.c_int, [C.c_void_p, c_i32p]),
+    "kml_decoder_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_launch_count": (C.c_uint64, [C.c_void_p]),
     "kml_encode": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_i32p]),
     "kml_generate": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, c_i32p, c_i32p, c_f32p, c_f32p]),

@@ -66,12 +66,12 @@ __device__ __forceinline__ float load_channel_ratio(const float *in, int idx, in
 // (3,6)-regular codes (PEG2304, PEG8064): N = VPT * T variables, M = CPT * T checks, everything unrolled,
 // edge addresses and channel ratios resident in registers.
 // ---------------------------------------------------------------------------------------------------------------
-template <int VPT, int CPT>
-__global__ void __launch_bounds__(VPT == 6 ? 384 : 672, VPT == 6 ? 3 : 1) bp_regular_kernel(const DecParams p) {
+template <int VPT, int CPT, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
   extern __shared__ uint32_t msg[];
   __shared__ int s_frame;
-  const int T = blockDim.x, tid = threadIdx.x;
-  const int mpad = p.t.m_pad;
+  const int tid = threadIdx.x;
+  constexpr int mpad = CPT * T + 1;  // words between the k planes: bank = (slot + k) mod 32 (see layout_opt.cpp)
 
   uint32_t va[VPT][3];
 #pragma unroll
@@ -193,9 +193,9 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
   extern __shared__ uint32_t smem[];
   __shared__ int s_frame;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-  const int mpad = p.t.m_pad, n = p.t.n, dcm = p.t.dc_max;
-  uint32_t *msg = smem;                                  // [dc_max * m_pad]
-  float *chan = reinterpret_cast<float *>(smem + dcm * mpad);  // [n]
+  const int mpad = p.t.m_pad, plane = p.t.plane, n = p.t.n, dcm = p.t.dc_max;
+  uint32_t *msg = smem;                                  // [dc_max * plane]
+  float *chan = reinterpret_cast<float *>(smem + dcm * plane);  // [n]
   uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);      // [2][words_n] decisions, double buffered
   const int n_round = (n + 31) & ~31;
 
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     for (int v = tid; v < n; v += T)  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
       chan[v] = v < p.t.punct ? 1.0f : load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
-    for (int i = tid; i < dcm * mpad; i += T) msg[i] = 0x3f800000u;
+    for (int i = tid; i < dcm * plane; i += T) msg[i] = 0x3f800000u;
     __syncthreads();
 
     int ret = p.iters + (p.iters < p.max_iter);
@@ -220,14 +220,14 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
       for (int v = tid; v < n_round; v += T) {
         uint32_t bit = 0;
         if (v < n) {
-          const int d = __ldg(p.t.vn_deg + v);
+          // the i-th gather instruction of a variable fetches the edge the layout optimiser coloured i; 0xFFFF = none
           const uint16_t *ad = p.t.vn_addr + (size_t)v * p.t.dv_max;
           uint32_t a[DV];
           float x[DV];
 #pragma unroll
           for (int k = 0; k < DV; k++) {
-            a[k] = k < d ? __ldg(ad + k) : 0u;
-            x[k] = k < d ? __uint_as_float(msg[a[k]]) : 1.0f;
+            a[k] = k < p.t.dv_max ? __ldg(ad + k) : 0xFFFFu;
+            x[k] = a[k] != 0xFFFFu ? __uint_as_float(msg[a[k]]) : 1.0f;
           }
           float pre[DV + 1], suf[DV + 1];
           pre[0] = chan[v];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
           bit = (pre[DV] > 1.0f) ? 0u : 1u;
 #pragma unroll
           for (int k = 0; k < DV; k++)
-            if (k < d) msg[a[k]] = v2c_word(fminf(fmaxf(pre[k] * suf[k + 1], kClampLo), kClampHi), bit);
+            if (a[k] != 0xFFFFu) msg[a[k]] = v2c_word(fminf(fmaxf(pre[k] * suf[k + 1], kClampLo), kClampHi), bit);
         }
         const uint32_t word = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) dcur[v >> 5] = word;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
         uint32_t x = 0;
 #pragma unroll
         for (int k = 0; k < DC; k++) {
-          w[k] = k < d ? msg[k * mpad + slot] : 0u;
+          w[k] = k < d ? msg[k * plane + slot] : 0u;
           x ^= w[k];
           s[k] = __uint_as_float(w[k] & 0x3fffffffu);  // s = 0 is the neutral element
           tt[k] = fmaf(-2.0f, s[k], 1.0f);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
 #pragma unroll
         for (int k = 0; k < DC; k++)
           if (k < d)
-            msg[k * mpad + slot] = __float_as_uint(c2v_ratio(sp_combine(pre[k], suf[k + 1]), ((x ^ w[k]) >> 31) & 1u));
+            msg[k * plane + slot] = __float_as_uint(c2v_ratio(sp_combine(pre[k], suf[k + 1]), ((x ^ w[k]) >> 31) & 1u));
         if (p.out_soft) soft += __logf((x >> 31) ? pre[DC] : 1.0f - pre[DC]);
       }
       const int any_fail = __syncthreads_or(fail);
@@ -302,8 +302,8 @@ typedef void (*dec_kernel_t)(const DecParams);
 
 dec_kernel_t kernel_of(DecKernelKind k) {
   switch (k) {
-    case DEC_REG_6_3: return bp_regular_kernel<6, 3>;
-    case DEC_REG_12_6: return bp_regular_kernel<12, 6>;
+    case DEC_REG_6_3: return bp_regular_kernel<6, 3, 384, 3>;
+    case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
     case DEC_GEN_16_32: return bp_generic_kernel<16, 32>;

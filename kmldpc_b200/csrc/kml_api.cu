@@ -62,6 +62,7 @@ struct kml_ctx {
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
   uint64_t launches = 0;
+  int layout_residual = 0, layout_excess = 0;  // layout_opt.cpp: annealing cost left / wavefronts above the ideal
   std::string err;
 };
 
@@ -129,10 +130,12 @@ void free_lane(Lane &l) {
   l.stream = nullptr;
 }
 
-// Builds the shared-memory layout of the decoder: row r sits in slot r, its k-th edge at word k * m_pad + r.
+// Builds the shared-memory layout of the decoder: edge (row r, position k) at word k * plane + slot(r); slot() and the
+// in-row order come from layout_opt.cpp so that variable-node gathers are (nearly) bank-conflict free.
 int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   const int M = c->M, N = c->N;
   const int mpad = (M + 31) & ~31;
+  const int plane = mpad + 1;
   std::vector<int> rdeg(M), cdeg(N, 0);
   int dcm = 0, dvm = 0;
   for (int r = 0; r < M; r++) {
@@ -141,18 +144,18 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     for (int e = code->row_ptr[r]; e < code->row_ptr[r + 1]; e++) cdeg[code->col_idx[e]]++;
   }
   for (int v = 0; v < N; v++) dvm = std::max(dvm, cdeg[v]);
-  if ((size_t)dcm * mpad >= 0xFFFFu) return fail_arg(c, "code too large for 16-bit shared-memory edge addresses");
+  if ((size_t)dcm * plane >= 0xFFFFu) return fail_arg(c, "code too large for 16-bit shared-memory edge addresses");
   const bool regular = std::all_of(rdeg.begin(), rdeg.end(), [](int d) { return d == 6; }) &&
                        std::all_of(cdeg.begin(), cdeg.end(), [](int d) { return d == 3; }) && c->punct == 0 &&
                        mpad == M && N == 2 * M;
   DecLaunch dl{};
   int dv_tab;
-  if (regular && N % 6 == 0 && (N / 6) % 32 == 0 && N / 6 <= 384) {
-    dl.kind = DEC_REG_6_3; dl.threads = N / 6; dv_tab = 3;
-    dl.smem_bytes = 6 * mpad * 4;
-  } else if (regular && N % 12 == 0 && (N / 12) % 32 == 0 && N / 12 <= 672) {
-    dl.kind = DEC_REG_12_6; dl.threads = N / 12; dv_tab = 3;
-    dl.smem_bytes = 6 * mpad * 4;
+  if (regular && N == 6 * 384) {
+    dl.kind = DEC_REG_6_3; dl.threads = 384; dv_tab = 3;
+    dl.smem_bytes = 6 * plane * 4;
+  } else if (regular && N == 12 * 672) {
+    dl.kind = DEC_REG_12_6; dl.threads = 672; dv_tab = 3;
+    dl.smem_bytes = 6 * plane * 4;
   } else {
     if (dvm <= 4 && dcm <= 8) { dl.kind = DEC_GEN_4_8; }
     else if (dvm <= 9 && dcm <= 10) { dl.kind = DEC_GEN_9_10; }
@@ -161,16 +164,27 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     dv_tab = dvm;
     int t = ((N + 5) / 6 + 31) & ~31;
     dl.threads = std::min(1024, std::max(128, t));
-    dl.smem_bytes = (dcm * mpad + N + 2 * c->words_n) * 4;
+    dl.smem_bytes = (dcm * plane + N + 2 * c->words_n) * 4;
   }
   if (dl.smem_bytes > 227 * 1024) return fail_arg(c, "code too large for one frame per SM in shared memory");
+  // every kernel hands 32 consecutive variables to one warp instruction
+  std::vector<int> group(N);
+  for (int v = 0; v < N; v++) group[v] = v / 32;
+  std::vector<int> slot, pos;
+  std::vector<std::vector<int>> order;
+  c->layout_residual = optimize_decoder_layout(M, N, mpad, plane, code->row_ptr, code->col_idx, group, (N + 31) / 32, dv_tab,
+                                               slot, pos, order, &c->layout_excess);
+  std::vector<int> erow(code->n_edges);
+  for (int r = 0; r < M; r++)
+    for (int e = code->row_ptr[r]; e < code->row_ptr[r + 1]; e++) erow[e] = r;
   std::vector<uint16_t> vaddr((size_t)N * dv_tab, 0xFFFFu);
   std::vector<uint8_t> vdeg(N, 0), cndeg(mpad, 0);
-  for (int r = 0; r < M; r++) {
-    cndeg[r] = (uint8_t)rdeg[r];
-    for (int e = code->row_ptr[r], k = 0; e < code->row_ptr[r + 1]; e++, k++) {
-      const int v = code->col_idx[e];
-      vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(k * mpad + r);
+  for (int r = 0; r < M; r++) cndeg[slot[r]] = (uint8_t)rdeg[r];
+  for (int v = 0; v < N; v++) {
+    vdeg[v] = (uint8_t)cdeg[v];
+    for (int i = 0; i < dv_tab; i++) {
+      const int e = order[v][i];
+      if (e >= 0) vaddr[(size_t)v * dv_tab + i] = (uint16_t)(pos[e] * plane + slot[erow[e]]);
     }
   }
   KML_CUDA(c, c->vn_addr.alloc(vaddr.size()));
@@ -180,7 +194,8 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   KML_CUDA(c, c->cn_deg.alloc(mpad));
   KML_CUDA(c, cudaMemcpy(c->cn_deg.p, cndeg.data(), mpad, cudaMemcpyHostToDevice));
   c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
-  c->dt.n = N; c->dt.m_pad = mpad; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct; c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
+  c->dt.n = N; c->dt.m_pad = mpad; c->dt.plane = plane; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct;
+  c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
   KML_CUDA(c, dec_prepare(dl));
   c->dl = dl;
   return KML_OK;
@@ -356,6 +371,13 @@ extern "C" int kml_info(const kml_ctx *c, int32_t info[8]) {
   if (!c || !info) return KML_ERR_ARG;
   info[0] = c->M; info[1] = c->N; info[2] = c->n_tx; info[3] = c->K;
   info[4] = c->bits; info[5] = c->Q; info[6] = c->n_sym; info[7] = c->max_batch;
+  return KML_OK;
+}
+
+extern "C" int kml_decoder_info(const kml_ctx *c, int32_t info[8]) {
+  if (!c || !info) return KML_ERR_ARG;
+  info[0] = (int)c->dl.kind; info[1] = c->dl.threads; info[2] = c->dl.smem_bytes; info[3] = c->dl.ctas_per_sm;
+  info[4] = c->layout_residual; info[5] = c->layout_excess; info[6] = ((c->N + 31) / 32) * c->dt.dv_max; info[7] = c->dt.m_pad;
   return KML_OK;
 }
 

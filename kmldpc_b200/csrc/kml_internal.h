@@ -3,6 +3,7 @@
 #define KML_INTERNAL_H
 #include <cstdint>
 #include <string>
+#include <vector>
 
 #include "../../include/kmldpc_b200.h"
 
@@ -20,6 +21,12 @@ constexpr float kLrMax = 1.0e12f;
 
 // Philox stream ids (word 3 of the counter)
 enum : uint32_t { STREAM_BITS = 0x5eed0001u, STREAM_FADE = 0x5eed0002u, STREAM_NOISE = 0x5eed0003u };
+
+// layout_opt.cpp
+int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t *row_ptr, const int32_t *col_idx,
+                            const std::vector<int> &group_of_var, int n_groups, int slots_per_var,
+                            std::vector<int> &slot_of_row, std::vector<int> &pos_of_edge,
+                            std::vector<std::vector<int>> &edge_order, int *excess_wavefronts);
 
 }  // namespace kml
 #endif

@@ -8,14 +8,14 @@
 namespace kml {
 
 // ---- belief-propagation decoder -------------------------------------------------------------------------------
-// Edge messages live in shared memory as one 32-bit word per edge at word address k * m_pad + slot(row), k = position
+// Edge messages live in shared memory as one 32-bit word per edge at word address k * plane + slot(row), k = position
 // of the edge inside its row: check-node threads (one row slot each) touch consecutive words → conflict free, and
-// variable-node threads gather/scatter through per-variable address lists.
+// variable-node threads gather/scatter through per-variable address lists that layout_opt.cpp makes conflict free.
 struct DecTables {
   const uint16_t *vn_addr;  // [n][dv_max] shared-memory word address of each edge of a variable, 0xFFFF = none
   const uint8_t *vn_deg;    // [n]
   const uint8_t *cn_deg;    // [m_pad] degree of the row held by a slot (0 = padding)
-  int n, m_pad, n_tx, punct, dv_max, dc_max;
+  int n, m_pad, plane, n_tx, punct, dv_max, dc_max;  // m_pad = row slots (multiple of 32), plane = m_pad + 1
 };
 
 struct DecParams {

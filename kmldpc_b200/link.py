@@ -121,6 +121,13 @@ class Link:
         if rc != 0:
             raise KmlError(f"{what}: {self._lib.kml_last_error(self._h).decode()} (rc={rc})")
 
+    def decoder_info(self) -> dict:
+        info = (C.c_int32 * 8)()
+        self._check(self._lib.kml_decoder_info(self._h, info), "kml_decoder_info")
+        keys = ("kernel_kind", "threads", "smem_bytes", "ctas_per_sm", "layout_residual", "excess_wavefronts",
+                "gather_instructions", "row_slots")
+        return dict(zip(keys, list(info)))
+
     @property
     def launches(self) -> int:
         return int(self._lib.kml_launch_count(self._h))
