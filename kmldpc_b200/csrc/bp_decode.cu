@@ -21,6 +21,7 @@
 // 4 shared-memory word accesses (16 B), 2 MUFU.RCP and ~27 issue slots; nothing but the channel ratios (4 B/variable,
 // coalesced) and the packed decisions (1 bit/variable) touches HBM.
 #include <cstdio>
+#include <cstdlib>
 
 #include "kml_internal.h"
 #include "kml_kernels.cuh"
@@ -302,7 +303,13 @@ typedef void (*dec_kernel_t)(const DecParams);
 
 dec_kernel_t kernel_of(DecKernelKind k) {
   switch (k) {
-    case DEC_REG_6_3: return bp_regular_kernel<6, 3, 384, 3>;
+    case DEC_REG_6_3: {
+      const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
+      const int b = e ? atoi(e) : 3;
+      if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
+      if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
+      return bp_regular_kernel<6, 3, 384, 3>;
+    }
     case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
