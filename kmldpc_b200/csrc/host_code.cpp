@@ -237,6 +237,53 @@ extern "C" int kml_modem_load(const char *modem_file, kml_modem **out) {
   return KML_OK;
 }
 
+namespace kml {
+// Voronoi neighbours of constellation point 0: the only points whose bisector bounds the cell of s_0.  The k-means
+// kernel needs just "is the nearest centroid cluster 0?" (kmeans.cc:36-46 feeds only cluster 0 back), and the centroids
+// are always the constellation scaled and rotated by one complex number, so the neighbour set never changes.
+// Half-plane clipping of a large square; a point is kept when its half-plane cuts area off the cell built from all the
+// others (a bisector that only touches the cell at a vertex never decides a sample: there d_0 = d_k exactly).
+std::vector<int> voronoi_neighbours_of_first(const double *pts, int q) {
+  struct P { double x, y; };
+  const P s0{pts[0], pts[1]};
+  double scale = 1.0;
+  for (int k = 0; k < q; k++) scale = std::max(scale, std::hypot(pts[2 * k], pts[2 * k + 1]));
+  const double R = 1.0e3 * scale, eps = 1.0e-9 * scale * scale;
+  auto clip = [&](std::vector<P> poly, int j) {  // keep { p : (p - mid) . (s_j - s_0) <= 0 }
+    const double dx = pts[2 * j] - s0.x, dy = pts[2 * j + 1] - s0.y;
+    const double mx = 0.5 * (pts[2 * j] + s0.x), my = 0.5 * (pts[2 * j + 1] + s0.y);
+    auto side = [&](const P &p) { return (p.x - mx) * dx + (p.y - my) * dy; };
+    std::vector<P> out;
+    for (size_t i = 0; i < poly.size(); i++) {
+      const P a = poly[i], b = poly[(i + 1) % poly.size()];
+      const double sa = side(a), sb = side(b);
+      if (sa <= 0) out.push_back(a);
+      if ((sa < 0 && sb > 0) || (sa > 0 && sb < 0)) {
+        const double t = sa / (sa - sb);
+        out.push_back({a.x + t * (b.x - a.x), a.y + t * (b.y - a.y)});
+      }
+    }
+    return out;
+  };
+  std::vector<int> nb;
+  for (int k = 1; k < q; k++) {
+    const double dx = pts[2 * k] - s0.x, dy = pts[2 * k + 1] - s0.y;
+    if (dx * dx + dy * dy < 1e-24) continue;  // coincides with s_0: never strictly closer
+    std::vector<P> poly = {{s0.x - R, s0.y - R}, {s0.x + R, s0.y - R}, {s0.x + R, s0.y + R}, {s0.x - R, s0.y + R}};
+    for (int j = 1; j < q && !poly.empty(); j++)
+      if (j != k) {
+        const double ex = pts[2 * j] - s0.x, ey = pts[2 * j + 1] - s0.y;
+        if (ex * ex + ey * ey >= 1e-24) poly = clip(poly, j);
+      }
+    const double mx = 0.5 * (pts[2 * k] + s0.x), my = 0.5 * (pts[2 * k + 1] + s0.y);
+    bool touches = false;
+    for (const P &v : poly) touches = touches || ((v.x - mx) * dx + (v.y - my) * dy > eps);
+    if (touches) nb.push_back(k);
+  }
+  return nb;
+}
+}  // namespace kml
+
 extern "C" void kml_modem_free(kml_modem *modem) {
   if (modem) delete reinterpret_cast<ModemOwner *>(modem);
 }

@@ -53,7 +53,8 @@ struct kml_ctx {
   // device tables
   DevBuf<uint32_t> enc_t;
   DevBuf<float2> points;
-  DevBuf<int32_t> row_ptr, col_idx;
+  DevBuf<int32_t> row_ptr, col_idx, km_nb;
+  int km_n_nb = 0;
   DevBuf<uint16_t> vn_addr;
   DevBuf<uint8_t> vn_deg, cn_deg;
   DecTables dt{};
@@ -228,7 +229,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
     d.h = true_h; d.n_cand = 1; d.hard_metric = 0;
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
   } else {
-    KML_LAUNCH(c, launch_kmeans(B, y, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, l.hhat.p, l.passes.p,
+    KML_LAUNCH(c, launch_kmeans(B, y, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, l.hhat.p, l.passes.p,
                                c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
@@ -329,6 +330,10 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     for (int i = 0; i < c->Q; i++) pts[i] = make_float2((float)modem->points[2 * i], (float)modem->points[2 * i + 1]);
     KML_CUDA(c, c->points.alloc(c->Q));
     KML_CUDA(c, cudaMemcpy(c->points.p, pts.data(), sizeof(float2) * c->Q, cudaMemcpyHostToDevice));
+    const std::vector<int> nb = voronoi_neighbours_of_first(modem->points, c->Q);
+    c->km_n_nb = (int)nb.size();
+    KML_CUDA(c, c->km_nb.alloc(nb.size()));
+    if (!nb.empty()) KML_CUDA(c, cudaMemcpy(c->km_nb.p, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->row_ptr.alloc(c->M + 1));
     KML_CUDA(c, cudaMemcpy(c->row_ptr.p, code->row_ptr, sizeof(int32_t) * (c->M + 1), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->col_idx.alloc(c->E));
@@ -353,7 +358,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   cudaDeviceSynchronize();
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
-  c->enc_t.release(); c->points.release(); c->row_ptr.release(); c->col_idx.release();
+  c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
   c->vn_addr.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
@@ -479,7 +484,7 @@ extern "C" int kml_kmeans(kml_ctx *c, int B, const float *y, float *hhat, int32_
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
-    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, l.hhat.p, l.passes.p, c->num_sms, l.stream));
+    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, l.hhat.p, l.passes.p, c->num_sms, l.stream));
     KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
     if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
     KML_CUDA(c, cudaStreamSynchronize(l.stream));
@@ -701,7 +706,7 @@ extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed,
 extern "C" int kml_kmeans_dev(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes, void *stream) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat) return fail_arg(c, "kml_kmeans_dev: null buffer");
-  KML_LAUNCH(c, launch_kmeans(B, (const float2 *)y, c->n_sym, c->points.p, c->Q, c->opts.kmeans_iter, (float2 *)hhat,
+  KML_LAUNCH(c, launch_kmeans(B, (const float2 *)y, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, (float2 *)hhat,
                              passes, c->num_sms, (cudaStream_t)stream));
   return KML_OK;
 }

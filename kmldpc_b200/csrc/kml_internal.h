@@ -22,6 +22,9 @@ constexpr float kLrMax = 1.0e12f;
 // Philox stream ids (word 3 of the counter)
 enum : uint32_t { STREAM_BITS = 0x5eed0001u, STREAM_FADE = 0x5eed0002u, STREAM_NOISE = 0x5eed0003u };
 
+// host_code.cpp
+std::vector<int> voronoi_neighbours_of_first(const double *pts, int q);
+
 // layout_opt.cpp
 int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t *row_ptr, const int32_t *col_idx,
                             const std::vector<int> &group_of_var, int n_groups, int slots_per_var,

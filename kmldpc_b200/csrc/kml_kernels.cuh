@@ -59,8 +59,9 @@ cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const f
                            float2 *h_out, float2 *y, cudaStream_t s);
 
 // ---- k-means blind channel estimate ------------------------------------------------------------------------------
-cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, int iters, float2 *hhat,
-                          int32_t *passes, int num_sms, cudaStream_t s);
+// nb[n_nb] = Voronoi neighbours of constellation point 0 (host_code.cpp); nullptr → full comparison kernel
+cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, const int *nb, int n_nb,
+                          int iters, float2 *hhat, int32_t *passes, int num_sms, cudaStream_t s);
 
 // ---- soft demapper + candidate resolver ---------------------------------------------------------------------------
 struct DemapParams {

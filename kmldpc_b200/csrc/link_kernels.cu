@@ -1,6 +1,7 @@
 // Everything of the link path that is not the BP decoder: Philox source, GF(2) encoder, mapper + block-fading AWGN
 // channel, k-means blind channel estimate, soft demapper + candidate resolver, error counting (sm_100a).
 // Reference functions are cited at each kernel (paths relative to the reference's kmldpc/ directory).
+#include <algorithm>
 #include <cstdio>
 
 #include "kml_internal.h"
@@ -298,6 +299,99 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 
   }
 }
 
+// Warp-per-frame variant (the fast path): no block barriers, samples in registers (lane l holds samples l, l+32, …),
+// and the nearest-is-cluster-0 predicate evaluated only against the Voronoi neighbours of s_0 as half-plane tests
+//   |y - c_0|^2 <= |y - c_k|^2   <=>   Re(conj(c_k - c_0) y) <= (|c_k|^2 - |c_0|^2) / 2 ,
+// 2 FMA + 1 compare per neighbour instead of a full distance per constellation point.  Every lane carries the same fp64
+// cumulative sums (xor-shuffle reductions give all lanes the same value), so no broadcast is needed.
+constexpr int KMW_WARPS = 4;
+template <int SPL, int MAXNB>
+__global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, const float2 *y, int n, const float2 *points,
+                                                                     const int *nb, int n_nb, int iters,
+                                                                     float2 *hhat_out, int32_t *passes_out) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
+  const float2 s0f = __ldg(points);
+  const double s0r = (double)s0f.x, s0i = (double)s0f.y, s0n = s0r * s0r + s0i * s0i;
+  float2 snb[MAXNB];
+#pragma unroll
+  for (int t = 0; t < MAXNB; t++) snb[t] = t < n_nb ? __ldg(points + __ldg(nb + t)) : s0f;
+  for (int f = wglobal; f < B; f += wstride) {
+    const float2 *yf = y + (size_t)f * n;
+    float2 ys[SPL];
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int j = 0; j < SPL; j++) {
+      const int i = j * 32 + lane;
+      if (i < n) {
+        ys[j] = yf[i];
+        const float a2 = ys[j].x * ys[j].x + ys[j].y * ys[j].y;
+        const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
+        best = key > best ? key : best;
+      } else {
+        ys[j] = make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    const float2 ya = yf[0x7fffffff - (int)(uint32_t)(best & 0xffffffffu)];
+    double hr = ((double)ya.x * s0r + (double)ya.y * s0i) / s0n;  // y_a / s_0
+    double hi = ((double)ya.y * s0r - (double)ya.x * s0i) / s0n;
+    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0, prev_r = 0.0, prev_i = 0.0;
+    bool have_prev = false;
+    int passes = 0;
+    for (int it = 0; it < iters; it++) {
+      passes++;
+      const float fhr = (float)hr, fhi = (float)hi;
+      const float2 c0 = make_float2(s0f.x * fhr - s0f.y * fhi, s0f.x * fhi + s0f.y * fhr);
+      const float n0 = c0.x * c0.x + c0.y * c0.y;
+      float ax[MAXNB], ay[MAXNB], th[MAXNB];
+#pragma unroll
+      for (int t = 0; t < MAXNB; t++) {
+        const float2 ck = make_float2(snb[t].x * fhr - snb[t].y * fhi, snb[t].x * fhi + snb[t].y * fhr);
+        ax[t] = ck.x - c0.x;
+        ay[t] = ck.y - c0.y;
+        th[t] = t < n_nb ? 0.5f * (ck.x * ck.x + ck.y * ck.y - n0) : 3.0e38f;
+      }
+      float cnt = 0.f, sr = 0.f, si = 0.f;
+#pragma unroll
+      for (int j = 0; j < SPL; j++) {
+        bool in0 = (j * 32 + lane) < n;
+#pragma unroll
+        for (int t = 0; t < MAXNB; t++) in0 = in0 && (fmaf(ax[t], ys[j].x, ay[t] * ys[j].y) <= th[t]);
+        if (in0) {
+          cnt += 1.f;
+          sr += ys[j].x;
+          si += ys[j].y;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+      }
+      cum_cnt += (double)cnt;
+      cum_re += (double)sr;
+      cum_im += (double)si;
+      if (have_prev && prev_r == hr && prev_i == hi) break;  // clusters_ == tempClusters (kmeans.cc:47-56)
+      prev_r = hr;
+      prev_i = hi;
+      have_prev = true;
+      const double mr = cum_re / cum_cnt, mi = cum_im / cum_cnt;
+      hr = (mr * s0r + mi * s0i) / s0n;
+      hi = (mi * s0r - mr * s0i) / s0n;
+    }
+    if (lane == 0) {
+      hhat_out[f] = make_float2((float)hr, (float)hi);
+      if (passes_out) passes_out[f] = passes;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ demapper + resolver
 // ModemLinearSystem::SoftAWGNDemodulation (modemlinearsystem.cc:51-79): p_k = softmax(-|s_k h - y|^2 / var), each
 // clipped to [1e-12, 1-1e-12]; Modem::DeMapping (modem.cc:23-79) with priors 0.5: renormalise by the post-clip sum,
@@ -539,12 +633,27 @@ cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const f
   return cudaGetLastError();
 }
 
-cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, int iters, float2 *hhat,
-                          int32_t *passes, int num_sms, cudaStream_t s) {
+cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, const int *nb, int n_nb,
+                          int iters, float2 *hhat, int32_t *passes, int num_sms, cudaStream_t s) {
+  if (B < 1) return cudaSuccess;
+  if (nb && n_nb >= 1 && n_nb <= 8 && n_sym <= 32 * 64) {  // warp per frame, Voronoi-neighbour half-plane tests
+    const int spl = (n_sym + 31) / 32;
+    const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
+#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, points, nb, n_nb, iters, hhat, passes)
+    if (n_nb <= 2) {
+      if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
+    } else if (n_nb <= 4) {
+      if (spl <= 16) KMW(16, 4); else if (spl <= 24) KMW(24, 4); else if (spl <= 36) KMW(36, 4); else if (spl <= 48) KMW(48, 4); else KMW(64, 4);
+    } else {
+      if (spl <= 16) KMW(16, 8); else if (spl <= 24) KMW(24, 8); else if (spl <= 36) KMW(36, 8); else if (spl <= 48) KMW(48, 8); else KMW(64, 8);
+    }
+#undef KMW
+    return cudaGetLastError();
+  }
+  // general fallback: one CTA per frame, full distance comparison against every constellation point
   const int spt = (n_sym + KM_THREADS - 1) / KM_THREADS;
   const int grid = B < num_sms * 8 ? B : num_sms * 8;
   const int smem = q * (int)sizeof(float2);
-  if (grid < 1) return cudaSuccess;
   if (spt <= 4) kmeans_kernel<4><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
   else if (spt <= 9) kmeans_kernel<9><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
   else if (spt <= 16) kmeans_kernel<16><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
