@@ -201,6 +201,7 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     if (data_dir && *data_dir && !p.empty() && p[0] != '/') p = std::string(data_dir) + "/" + p;
     return p;
   };
+  log(cfg->is_5g ? "Using 5G LDPC." : "Using traditional LDPC.");  // kmcodec.cc:27,32 (member init precedes the ctor body)
   {
     std::stringstream s;  // simulator.cc:16-21
     s << '[' << std::fixed << std::setprecision(3) << cfg->min_snr << ',' << cfg->step_snr << ',' << cfg->max_snr << ']';
@@ -209,7 +210,6 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     s << '[' << "MAX_ERROR_BLK = " << cfg->max_err_blk << ',' << "MAX_BLK = " << cfg->max_num_blk << ']';
     log(s.str());
   }
-  log(cfg->is_5g ? "Using 5G LDPC." : "Using traditional LDPC.");  // kmcodec.cc:27,32
   kml_code *code = nullptr;
   kml_modem *modem = nullptr;
   int rc = kml_code_load(path_of(cfg->matrix_file).c_str(), cfg->is_5g, cfg->encoder_active, &code);

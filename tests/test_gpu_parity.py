@@ -293,7 +293,8 @@ batch = 128
     snr, ber, fer, cnt = sim.simulate(echo=False)
     assert list(snr) == [4.0, 6.0, 8.0] and (cnt[:, 0] == 256).all()
     assert fer[0] >= fer[2]
-    assert sim.lines[0] == "[4.000,2.000,8.000]" and sim.lines[1] == "[MAX_ERROR_BLK = 1000000,MAX_BLK = 256]"
+    assert sim.lines[0] == "Using traditional LDPC."
+    assert sim.lines[1] == "[4.000,2.000,8.000]" and sim.lines[2] == "[MAX_ERROR_BLK = 1000000,MAX_BLK = 256]"
     line = [l for l in sim.lines if l.startswith("SNR = 6.000")][0]
     assert line.startswith("SNR = 6.000 Total blk = 0000256 Error blk = ")
     i = sim.lines.index("BER Result")
