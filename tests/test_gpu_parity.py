@@ -299,3 +299,36 @@ batch = 128
     assert line.startswith("SNR = 6.000 Total blk = 0000256 Error blk = ")
     i = sim.lines.index("BER Result")
     assert sim.lines[i + 1].startswith("4.000 0.") and sim.lines[i + 4] == "FER Result"
+
+
+def test_unchanged_reference_driver_runs_on_gpu(tmp_path):
+    """build/kmldpc_gpu = the reference's UNCHANGED kmldpc.cpp linked against the Simulator façade + libkmldpc_b200.so
+    (built in the build container by `make -C kmldpc_b200/host`; /root/reference is not needed at run time)."""
+    import os
+    import re
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "kmldpc_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("build/kmldpc_gpu not built (needs the reference tree at build time)")
+    for f in os.listdir(os.path.join(root, "config")):
+        shutil.copy(os.path.join(root, "config", f), tmp_path)
+    os.makedirs(tmp_path / "logs")
+    cfg = (tmp_path / "config.toml").read_text()
+    cfg = cfg.replace("maximum_error_number = 1", "maximum_error_number = 100000")
+    cfg = cfg.replace("maximum_block_number = 1", "maximum_block_number = 2000")
+    cfg = cfg.replace("minimum_snr = 15.0", "minimum_snr = 10.0")
+    (tmp_path / "config.toml").write_text(cfg + "\n[gpu]\nseed = 5\nbatch = 512\n")
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "kmldpc_b200", "lib"))
+    out = subprocess.run([exe], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300).stdout
+    plain = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    assert "Using traditional LDPC." in plain and "[10.000,5.000,15.000]" in plain
+    assert "[MAX_ERROR_BLK = 100000,MAX_BLK = 2000]" in plain
+    m = re.findall(r"SNR = (\d+\.\d+) Total blk = (\d+) Error blk = (\d+) Error bit = (\d+) BER = ([\d.]+) FER = ([\d.]+)", plain)
+    assert [x[0] for x in m] == ["10.000", "15.000"] and all(int(x[1]) == 2048 for x in m)  # batch granularity
+    fer = [float(x[5]) for x in m]
+    # 16QAM Gray blind, reference FER 0.43 @ 10 dB and 0.177 @ 15 dB (BASELINE.md §2.5, 300 frames)
+    assert 0.33 < fer[0] < 0.53 and 0.11 < fer[1] < 0.25
+    assert "BER Result" in plain and "FER Result" in plain and "Total time cost" in plain
+    assert os.listdir(tmp_path / "logs"), "the reference's log file was not written"
