@@ -148,6 +148,7 @@ def gpu_arm(args):
     import torch
     import torch.distributed as dist
     import kmldpc_b200 as kb
+    from kmldpc_b200 import shard
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -171,9 +172,9 @@ def gpu_arm(args):
     ys = [torch.empty((B, N_SYM, 2), dtype=torch.float32, device=dev) for _ in range(pool)]
     us = [torch.empty((B, kw), dtype=torch.int32, device=dev) for _ in range(pool)]
     hs = torch.empty((B, 2), dtype=torch.float32, device=dev)
-    for i in range(pool):
-        frame0 = (rank * pool + i) * B
-        link.generate_dev(B, SNR_DB, 17, frame0, us[i].data_ptr(), hs.data_ptr(), ys[i].data_ptr(), stream)
+    lo, hi = shard.frame_range(rank, world, world * pool * B)  # this rank's slice of the global frame index space
+    for i, (frame0, nfr) in enumerate(shard.batches(lo, hi, B)):
+        link.generate_dev(nfr, SNR_DB, 17, frame0, us[i].data_ptr(), hs.data_ptr(), ys[i].data_ptr(), stream)
     uu_hat = torch.empty((B, kw), dtype=torch.int32, device=dev)
     ret = torch.empty((B,), dtype=torch.int32, device=dev)
     counters = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -201,8 +202,7 @@ def gpu_arm(args):
     ev0.record()
     for i in range(args.steps):
         step_dev(args.warmup + i)
-    if world > 1:
-        dist.all_reduce(counters)  # the only collective of the path: 4 x int64 error counters (NCCL)
+    shard.reduce_counters(counters)  # the only collective of the path: 4 x int64 error counters (NCCL)
     ev1.record()
     barrier()
     launches = link.launches - l0
