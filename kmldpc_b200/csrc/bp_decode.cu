@@ -43,18 +43,23 @@ __device__ __forceinline__ float sp_combine(float a, float b) { return fmaf(-2.0
 // same with t_b = 1 - 2 s_b precomputed
 __device__ __forceinline__ float sp_chain(float acc, float s, float t) { return fmaf(acc, t, s); }
 
-__device__ __forceinline__ uint32_t v2c_word(float ext, uint32_t post_bit) {
-  // ext = P0/P1 of the extrinsic.  hard = 1 when P1 > P0 ; s = min(P0, P1) = min(ext, 1) / (1 + ext)
+// v2c word: s = min(P0, P1) = min(ext, 1) / (1 + ext); bit 31 = extrinsic hard decision (P1 > P0, i.e. ext < 1), taken
+// from the sign of (ext - 1) — one FADD on the FMA pipe instead of FSETP + SEL on the (binding) ALU pipe; `pb` = the
+// variable's posterior decision already shifted to bit 30.
+__device__ __forceinline__ uint32_t v2c_word(float ext, uint32_t pb) {
   const float s = fminf(ext, 1.0f) * rcp_approx(1.0f + ext);
-  return __float_as_uint(s) | (ext < 1.0f ? 0x80000000u : 0u) | (post_bit << 30);
+  return (__float_as_uint(ext - 1.0f) & 0x80000000u) | __float_as_uint(s) | pb;
 }
 
-__device__ __forceinline__ float c2v_ratio(float s, uint32_t hard) {
-  // clip of c2v0 to [1e-12, 1-1e-12] (binaryldpccodec.cc:259-263) acts on the small side only
+// c2v ratio P0/P1 from the small probability s and the output's hard decision (sign bit of xw).  The clip of c2v0 to
+// [1e-12, 1-1e-12] (binaryldpccodec.cc:259-263) acts on the small side only.  q = (1-s)/s is the ratio for hard = 0;
+// hard = 1 takes a second (predicated) reciprocal — cheaper on this ALU-bound kernel than selecting numerator and
+// denominator (2 FSEL): the XU pipe has head-room (profiles/r1b).
+__device__ __forceinline__ float c2v_ratio(float s, uint32_t xw) {
   s = fmaxf(s, kSmallProbF);
-  const float big = 1.0f - s;
-  const float num = hard ? s : big, den = hard ? big : s;
-  return num * rcp_approx(den);
+  float q = (1.0f - s) * rcp_approx(s);
+  if ((int)xw < 0) q = rcp_approx(q);
+  return q;
 }
 
 __device__ __forceinline__ float load_channel_ratio(const float *in, int idx, int in_is_lr) {
@@ -111,9 +116,10 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         const float post = e2 * x2;
         const uint32_t bit = (post > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
         bits |= bit << j;
-        msg[va[j][0]] = v2c_word(e0, bit);
-        msg[va[j][1]] = v2c_word(e1, bit);
-        msg[va[j][2]] = v2c_word(e2, bit);
+        const uint32_t pb = bit << 30;
+        msg[va[j][0]] = v2c_word(e0, pb);
+        msg[va[j][1]] = v2c_word(e1, pb);
+        msg[va[j][2]] = v2c_word(e2, pb);
       }
       __syncthreads();
       // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
 #pragma unroll
         for (int k = 0; k < 6; k++)
-          msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], ((x ^ w[k]) >> 31) & 1u));
+          msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x ^ w[k]));
         if (p.out_soft) {  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
           const float sall = sp_chain(pre[5], s[5], tt[5]);
           soft += __logf((x >> 31) ? sall : 1.0f - sall);
@@ -186,11 +192,86 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Any Tanner graph with column degree <= DV and row degree <= DC (5G BG2, irregular codes, odd sizes).
-// Runtime loops over the thread's variables / row slots, degree tables and address lists through the read-only
-// path, channel ratios staged in shared memory, clamped prefix/suffix products in the variable nodes.
+// Runtime loops over the thread's variables / row slots; the node update is dispatched on the node's EXACT degree
+// (warp-uniform for quasi-cyclic codes: 32 consecutive variables / rows share a degree), so no work is spent on padding.
+// Address lists come through the read-only path, channel ratios are staged in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
+template <int D>
+__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, float ch) {
+  uint32_t a[D];
+  float x[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    a[k] = __ldg(ad + k);
+    x[k] = __uint_as_float(msg[a[k]]);
+  }
+  // up to 3 edges the products stay inside fp32 (1e12^3); above, partial products are clamped to 1e±36, which only
+  // acts where the ratio is already far beyond the 1e±12 clip of every check message (see the header comment)
+  constexpr bool kClamp = D > 3;
+  float pre[D + 1], suf[D + 1];
+  pre[0] = ch;
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    pre[k + 1] = pre[k] * x[k];
+    if (kClamp) pre[k + 1] = fminf(fmaxf(pre[k + 1], kClampLo), kClampHi);
+  }
+  suf[D] = 1.0f;
+#pragma unroll
+  for (int k = D - 1; k >= 0; k--) {
+    suf[k] = suf[k + 1] * x[k];
+    if (kClamp) suf[k] = fminf(fmaxf(suf[k], kClampLo), kClampHi);
+  }
+  const uint32_t bit = (pre[D] > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    float e = pre[k] * suf[k + 1];
+    if (kClamp) e = fminf(fmaxf(e, kClampLo), kClampHi);
+    msg[a[k]] = v2c_word(e, bit << 30);
+  }
+  return bit;
+}
+
+// returns the XOR of the row's words (bit 30 = syndrome of the current decisions, bit 31 = parity of the extrinsic hard
+// bits); *s_all = small probability of the whole row (for syndrom_soft)
+template <int D>
+__device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, float *s_all) {
+  uint32_t w[D], x = 0;
+  float s[D], tt[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    w[k] = msg[k * plane + slot];
+    x ^= w[k];
+    s[k] = __uint_as_float(w[k] & 0x3fffffffu);
+    tt[k] = fmaf(-2.0f, s[k], 1.0f);
+  }
+  float pre[D + 1], suf[D + 1];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}; 0 is the neutral element
+  pre[0] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D; k++) pre[k + 1] = k == 0 ? s[0] : sp_chain(pre[k], s[k], tt[k]);
+  suf[D] = 0.0f;
+#pragma unroll
+  for (int k = D - 1; k >= 0; k--) suf[k] = k == D - 1 ? s[k] : sp_chain(suf[k + 1], s[k], tt[k]);
+#pragma unroll
+  for (int k = 0; k < D; k++) {
+    const float so = k == 0 ? suf[1] : (k == D - 1 ? pre[D - 1] : sp_combine(pre[k], suf[k + 1]));
+    msg[k * plane + slot] = __float_as_uint(c2v_ratio(so, x ^ w[k]));
+  }
+  *s_all = pre[D];
+  return x;
+}
+
+#define KML_VN_CASE(D)                                  \
+  case D:                                               \
+    if (D <= DV) bit = vn_node<(D <= DV ? D : 1)>(msg, ad, chan[v]); \
+    break;
+#define KML_CN_CASE(D)                                  \
+  case D:                                               \
+    if (D <= DC) x = cn_node<(D <= DC ? D : 1)>(msg, plane, slot, &s_all); \
+    break;
+
 template <int DV, int DC>
-__global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
+__global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
+  static_assert(DV <= 16 && DC <= 16, "add switch cases");
   extern __shared__ uint32_t smem[];
   __shared__ int s_frame;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
@@ -221,26 +302,15 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
       for (int v = tid; v < n_round; v += T) {
         uint32_t bit = 0;
         if (v < n) {
-          // the i-th gather instruction of a variable fetches the edge the layout optimiser coloured i; 0xFFFF = none
+          // edges in the order the layout optimiser coloured them (= gather instruction index inside the warp)
           const uint16_t *ad = p.t.vn_addr + (size_t)v * p.t.dv_max;
-          uint32_t a[DV];
-          float x[DV];
-#pragma unroll
-          for (int k = 0; k < DV; k++) {
-            a[k] = k < p.t.dv_max ? __ldg(ad + k) : 0xFFFFu;
-            x[k] = a[k] != 0xFFFFu ? __uint_as_float(msg[a[k]]) : 1.0f;
+          switch (__ldg(p.t.vn_deg + v)) {
+            case 0: bit = (chan[v] > 1.0f) ? 0u : 1u; break;
+            KML_VN_CASE(1) KML_VN_CASE(2) KML_VN_CASE(3) KML_VN_CASE(4) KML_VN_CASE(5) KML_VN_CASE(6) KML_VN_CASE(7) KML_VN_CASE(8)
+            KML_VN_CASE(9) KML_VN_CASE(10) KML_VN_CASE(11) KML_VN_CASE(12) KML_VN_CASE(13) KML_VN_CASE(14) KML_VN_CASE(15)
+            KML_VN_CASE(16)
+            default: break;
           }
-          float pre[DV + 1], suf[DV + 1];
-          pre[0] = chan[v];
-#pragma unroll
-          for (int k = 0; k < DV; k++) pre[k + 1] = fminf(fmaxf(pre[k] * x[k], kClampLo), kClampHi);
-          suf[DV] = 1.0f;
-#pragma unroll
-          for (int k = DV - 1; k >= 0; k--) suf[k] = fminf(fmaxf(suf[k + 1] * x[k], kClampLo), kClampHi);
-          bit = (pre[DV] > 1.0f) ? 0u : 1u;
-#pragma unroll
-          for (int k = 0; k < DV; k++)
-            if (a[k] != 0xFFFFu) msg[a[k]] = v2c_word(fminf(fmaxf(pre[k] * suf[k + 1], kClampLo), kClampHi), bit);
         }
         const uint32_t word = __ballot_sync(0xffffffffu, bit);
         if (lane == 0) dcur[v >> 5] = word;
@@ -250,31 +320,16 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
       const float soft_before = soft;
       soft = 0.0f;
       for (int slot = tid; slot < mpad; slot += T) {
-        const int d = __ldg(p.t.cn_deg + slot);
-        if (d == 0) continue;
-        uint32_t w[DC];
-        float s[DC], tt[DC];
         uint32_t x = 0;
-#pragma unroll
-        for (int k = 0; k < DC; k++) {
-          w[k] = k < d ? msg[k * plane + slot] : 0u;
-          x ^= w[k];
-          s[k] = __uint_as_float(w[k] & 0x3fffffffu);  // s = 0 is the neutral element
-          tt[k] = fmaf(-2.0f, s[k], 1.0f);
+        float s_all = 0.0f;
+        switch (__ldg(p.t.cn_deg + slot)) {
+          KML_CN_CASE(1) KML_CN_CASE(2) KML_CN_CASE(3) KML_CN_CASE(4) KML_CN_CASE(5) KML_CN_CASE(6) KML_CN_CASE(7) KML_CN_CASE(8)
+          KML_CN_CASE(9) KML_CN_CASE(10) KML_CN_CASE(11) KML_CN_CASE(12) KML_CN_CASE(13) KML_CN_CASE(14) KML_CN_CASE(15)
+          KML_CN_CASE(16)
+          default: continue;  // padding slot
         }
         fail |= (int)((x >> 30) & 1u);
-        float pre[DC + 1], suf[DC + 1];
-        pre[0] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < DC; k++) pre[k + 1] = sp_chain(pre[k], s[k], tt[k]);
-        suf[DC] = 0.0f;
-#pragma unroll
-        for (int k = DC - 1; k >= 0; k--) suf[k] = sp_chain(suf[k + 1], s[k], tt[k]);
-#pragma unroll
-        for (int k = 0; k < DC; k++)
-          if (k < d)
-            msg[k * plane + slot] = __float_as_uint(c2v_ratio(sp_combine(pre[k], suf[k + 1]), ((x ^ w[k]) >> 31) & 1u));
-        if (p.out_soft) soft += __logf((x >> 31) ? pre[DC] : 1.0f - pre[DC]);
+        if (p.out_soft) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
       }
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -298,6 +353,8 @@ __global__ void __launch_bounds__(1024) bp_generic_kernel(const DecParams p) {
     }
   }
 }
+#undef KML_VN_CASE
+#undef KML_CN_CASE
 
 typedef void (*dec_kernel_t)(const DecParams);
 
@@ -313,7 +370,7 @@ dec_kernel_t kernel_of(DecKernelKind k) {
     case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
-    case DEC_GEN_16_32: return bp_generic_kernel<16, 32>;
+    case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;
   }
   return nullptr;
 }

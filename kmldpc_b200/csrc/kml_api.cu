@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -160,11 +161,13 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   } else {
     if (dvm <= 4 && dcm <= 8) { dl.kind = DEC_GEN_4_8; }
     else if (dvm <= 9 && dcm <= 10) { dl.kind = DEC_GEN_9_10; }
-    else if (dvm <= 16 && dcm <= 32) { dl.kind = DEC_GEN_16_32; }
-    else return fail_arg(c, "row/column degree beyond the compiled decoder kernels (max 32/16)");
+    else if (dvm <= 16 && dcm <= 16) { dl.kind = DEC_GEN_16_32; }
+    else return fail_arg(c, "row/column degree beyond the compiled decoder kernels (max 16/16)");
     dv_tab = dvm;
-    int t = ((N + 5) / 6 + 31) & ~31;
-    dl.threads = std::min(1024, std::max(128, t));
+    int t = std::min(512, std::max(128, ((N + 5) / 6 + 31) & ~31));
+    for (int cand = 512; cand >= 256; cand -= 32)  // prefer a block size that tiles the row slots exactly
+      if (mpad % cand == 0 && cand * 8 >= N) { t = cand; break; }
+    dl.threads = t;
     dl.smem_bytes = (dcm * plane + N + 2 * c->words_n) * 4;
   }
   if (dl.smem_bytes > 227 * 1024) return fail_arg(c, "code too large for one frame per SM in shared memory");
@@ -181,11 +184,10 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   std::vector<uint16_t> vaddr((size_t)N * dv_tab, 0xFFFFu);
   std::vector<uint8_t> vdeg(N, 0), cndeg(mpad, 0);
   for (int r = 0; r < M; r++) cndeg[slot[r]] = (uint8_t)rdeg[r];
-  for (int v = 0; v < N; v++) {
-    vdeg[v] = (uint8_t)cdeg[v];
+  for (int v = 0; v < N; v++) {  // compact list in colour order (no holes: the kernels unroll on the exact degree)
     for (int i = 0; i < dv_tab; i++) {
       const int e = order[v][i];
-      if (e >= 0) vaddr[(size_t)v * dv_tab + i] = (uint16_t)(pos[e] * plane + slot[erow[e]]);
+      if (e >= 0) vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(pos[e] * plane + slot[erow[e]]);
     }
   }
   KML_CUDA(c, c->vn_addr.alloc(vaddr.size()));
@@ -591,9 +593,11 @@ extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_
   KML_RC(check_batch(c, B));
   if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive: bad argument");
   KML_CUDA(c, cudaSetDevice(c->device));
-  // sub-batches: at least 4 per call when the call is large enough, so both lanes stay busy
+  // sub-batches of ~2048 frames (measured best on B200: the first H2D and the last D2H are the only exposed copies,
+  // and the other lane's kernels fill the tail of each decoder launch); never fewer than ~1 frame per resident CTA
   int step = c->max_batch;
-  if (B > 4 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, (B + 3) / 4));
+  if (B > 2 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, std::min(2048, (B + 1) / 2)));
+  if (const char *e = getenv("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));  // tuning knob
   int li = 0;
   for (int b0 = 0; b0 < B; b0 += step, li ^= 1) {
     Lane &l = c->lane[li];

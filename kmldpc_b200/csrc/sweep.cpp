@@ -220,6 +220,7 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     return rc;
   }
   const int G = cfg->n_gpus > 0 ? cfg->n_gpus : 1;
+  std::vector<double> ber_v(n_pts, 0.0), fer_v(n_pts, 0.0);
   kml_opts o{};
   o.max_iter = cfg->max_iter; o.known_h = cfg->known_h; o.metric_type = cfg->metric_type; o.metric_iter = cfg->metric_iter;
   o.kmeans_iter = 20; o.early_exit = cfg->early_exit; o.max_batch = cfg->max_batch;
@@ -259,17 +260,19 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
       for (auto &t : th) t.join();
       rc = failed.load();
       const double b = tot[2] ? (double)tot[3] / (double)tot[2] : 0.0, f = tot[0] ? (double)tot[1] / (double)tot[0] : 0.0;
+      ber_v[i] = b;
+      fer_v[i] = f;
       if (ber) ber[i] = b;
       if (fer) fer[i] = f;
       if (counters)
         for (int k = 0; k < 4; k++) counters[(size_t)i * 4 + k] = tot[k];
       log(fmt_point_line(snr, tot[0], tot[1], tot[3], b, f));
     }
-    if (rc == KML_OK && ber && fer) {
+    if (rc == KML_OK) {
       log("BER Result");
-      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, ber[i]));
+      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, ber_v[i]));
       log("FER Result");
-      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, fer[i]));
+      for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, fer_v[i]));
     }
   }
   for (auto *c : ctx) kml_destroy(c);
