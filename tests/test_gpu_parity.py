@@ -332,3 +332,69 @@ def test_unchanged_reference_driver_runs_on_gpu(tmp_path):
     assert 0.33 < fer[0] < 0.53 and 0.11 < fer[1] < 0.25
     assert "BER Result" in plain and "FER Result" in plain and "Total time cost" in plain
     assert os.listdir(tmp_path / "logs"), "the reference's log file was not written"
+
+
+def test_ragged_and_empty_batches(kb):
+    """Empty input, a single frame, batches that straddle max_batch and are not multiples of any tile size."""
+    name = "peg2304_4psk_6db"
+    olink, rs = util.oracle_frames(name, 100)
+    link = util.gpu_link(name, max_batch=48)
+    var = 10 ** -0.6
+    y = np.stack([r.y for r in rs])
+    uu0, h0, k0, r0 = link.receive(y[:0], var)
+    assert uu0.shape == (0, 36) and r0.shape == (0,)
+    full = link.receive(y, var)                      # 100 frames = 48 + 48 + 4
+    one = link.receive(y[37:38], var)
+    assert np.array_equal(one[0][0], full[0][37]) and one[3][0] == full[3][37] and one[2][0] == full[2][37]
+    part = link.receive(y[5:71], var)                # 66 frames
+    assert np.array_equal(part[0], full[0][5:71]) and np.array_equal(part[3], full[3][5:71])
+    llr = np.stack([util.llr_of_p0(r.p0) for r in rs]).astype(np.float32)
+    cc_a, uu_a, ret_a = link.decode(llr)
+    cc_b, uu_b, ret_b = link.decode(llr[91:])        # 9 frames
+    assert np.array_equal(cc_a[91:], cc_b) and np.array_equal(ret_a[91:], ret_b)
+    u = np.stack([r.u for r in rs]).astype(np.int32)
+    assert np.array_equal(link.encode(u[:1]), olink.code.encode(u[0])[None])
+    cnt = link.count_errors(kb.pack_bits(u), full[0])
+    assert cnt[0] == 100 and cnt[2] == 100 * 1152
+    assert cnt[3] == int((kb.unpack_bits(full[0], 1152) != u).sum())
+    link.close()
+
+
+def test_llr_extremes_and_clipping(kb):
+    """LLRs beyond the reference's clip, zeros and infinities behave like the clipped reference input."""
+    olink = util.oracle_link("peg2304_4psk_6db")
+    link = util.gpu_link("peg2304_4psk_6db")
+    rng = np.random.default_rng(5)
+    u = rng.integers(0, 2, size=(4, 1152), dtype=np.int32)
+    c = np.stack([olink.code.encode(x) for x in u])
+    sign = 1.0 - 2.0 * c
+    llr = np.stack([sign[0] * 100.0, sign[1] * np.inf, sign[2] * 27.0, np.zeros(2304)]).astype(np.float32)
+    cc, uu, ret = link.decode(llr)
+    assert np.array_equal(cc[:3], c[:3]) and np.array_equal(ret[:3], [1, 1, 1])   # clean words: zero syndrome at t = 0
+    p0 = np.clip(1.0 / (1.0 + np.exp(-np.clip(llr[3].astype(np.float64), -50, 50))), 1e-12, 1 - 1e-12)
+    oret, _, occ, _ = olink.code.decode(p0, 50, 50)
+    assert ret[3] == oret and np.array_equal(cc[3], occ)   # all-erasure input: every posterior ties → all ones → codeword
+    link.close()
+
+
+def test_context_errors_are_reported_not_fatal(kb, tmp_path):
+    link = util.gpu_link("peg2304_qpsk_10db")
+    with pytest.raises(kb.KmlError, match="bad argument"):
+        link.receive(np.zeros((2, 1152), np.complex64), -1.0)
+    with pytest.raises(kb.KmlError):
+        link.decode(np.zeros((2, 2304), np.float32), iter_count=-3)
+    # the context is still usable afterwards
+    cnt, _ = link.simulate(10.0, 64, seed=1)
+    assert cnt[0] == 64
+    link.close()
+    code, mod = kb.LdpcCode("PEG2304regular0.5.txt"), kb.Modem("6bits_64QAM_Gray.txt")
+    kb.Link(code, mod).close()                                   # 2304 % 6 == 0: fine
+    # cc_len % bits_per_symbol != 0 is an error (the reference exit(-1)s, modemlinearsystem.cc:7-13)
+    f = tmp_path / "5bits.txt"
+    lines = ["number_of_bits_per_symbol", "5", "number_of_symbols_per_constallation_point", "2", "header"]
+    for i in range(32):
+        lines.append(f"{i} " + " ".join(str((i >> (4 - j)) & 1) for j in range(5)) +
+                     f" {np.cos(2 * np.pi * i / 32):.10f} {np.sin(2 * np.pi * i / 32):.10f}")
+    f.write_text("\n".join(lines) + "\n")
+    with pytest.raises(kb.KmlError, match="multiple"):
+        kb.Link(code, kb.Modem(str(f)))
