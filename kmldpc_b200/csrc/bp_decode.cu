@@ -70,11 +70,34 @@ __device__ __forceinline__ float load_channel_ratio(const float *in, int idx, in
   return fminf(fmaxf(v, kLrMin), kLrMax);
 }
 
+// Blackwell packed fp32 (PTX mul/add/fma.rn.f32x2 → SASS FMUL2 / FADD2 / FFMA2, sm_100+).  ptxas folds {x, x} and
+// {b.y, b.x} operand constructions into the instruction's .F32 (broadcast) and .LO_HI (swap) selectors — no moves.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
+
 // ---------------------------------------------------------------------------------------------------------------
 // (3,6)-regular codes (PEG2304, PEG8064): N = VPT * T variables, M = CPT * T checks, everything unrolled,
 // edge addresses and channel ratios resident in registers.
 // ---------------------------------------------------------------------------------------------------------------
-template <int VPT, int CPT, int T, int MINB>
+template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2>
 __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
   extern __shared__ uint32_t msg[];
   __shared__ int s_frame;
@@ -113,15 +136,35 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         const float x0 = __uint_as_float(msg[va[j][0]]);
         const float x1 = __uint_as_float(msg[va[j][1]]);
         const float x2 = __uint_as_float(msg[va[j][2]]);
-        const float a = ch[j] * x0, b = ch[j] * x1;
-        const float e2 = a * x1, e1 = a * x2, e0 = b * x2;
-        const float post = e2 * x2;
-        const uint32_t bit = (post > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
+        uint32_t w0, w1, w2, bit;
+        if (PACK) {
+          // (a, b) = ch (x0, x1);  (e1, e0) = (a, b) x2;  e2 = a x1;  post = e2 x2  — 2 FMUL2 + 2 FMUL instead of 6 FMUL
+          const float2 ab = mul2(splat(ch[j]), make_float2(x0, x1));
+          const float2 e10 = mul2(ab, splat(x2));
+          const float e2 = ab.x * x1;
+          const float post = e2 * x2;
+          bit = (post > 1.0f) ? 0u : 1u;
+          const uint32_t pb = bit << 30;
+          const float2 den = add2(e10, splat(1.0f)), sgn = add2(e10, splat(-1.0f));
+          const float2 s10 = mul2(make_float2(fminf(e10.x, 1.0f), fminf(e10.y, 1.0f)),
+                                  make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+          w1 = (__float_as_uint(sgn.x) & 0x80000000u) | __float_as_uint(s10.x) | pb;
+          w0 = (__float_as_uint(sgn.y) & 0x80000000u) | __float_as_uint(s10.y) | pb;
+          w2 = v2c_word(e2, pb);
+        } else {
+          const float a = ch[j] * x0, b = ch[j] * x1;
+          const float e2 = a * x1, e1 = a * x2, e0 = b * x2;
+          const float post = e2 * x2;
+          bit = (post > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
+          const uint32_t pb = bit << 30;
+          w0 = v2c_word(e0, pb);
+          w1 = v2c_word(e1, pb);
+          w2 = v2c_word(e2, pb);
+        }
         bits |= bit << j;
-        const uint32_t pb = bit << 30;
-        msg[va[j][0]] = v2c_word(e0, pb);
-        msg[va[j][1]] = v2c_word(e1, pb);
-        msg[va[j][2]] = v2c_word(e2, pb);
+        msg[va[j][0]] = w0;
+        msg[va[j][1]] = w1;
+        msg[va[j][2]] = w2;
       }
       __syncthreads();
       // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
@@ -132,35 +175,77 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
       for (int j = 0; j < CPT; j++) {
         const int slot = j * T + tid;
         uint32_t w[6];
-        float s[6], tt[6];
+        float s[6];
         uint32_t x = 0;
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           w[k] = msg[k * mpad + slot];
           x ^= w[k];
           s[k] = __uint_as_float(w[k] & 0x3fffffffu);
-          tt[k] = fmaf(-2.0f, s[k], 1.0f);
         }
         fail |= (int)((x >> 30) & 1u);
-        float pre[6], suf[6];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}, suf[k] = s_k ⊕ … ⊕ s_5
-        pre[1] = s[0];
+        float so[6], sall = 0.0f;
+        if (PACK) {
+          // prefix and suffix chains advance in lock step in the two halves of one FFMA2:
+          //   C_i = (pre_i, suf_{6-i}),  C_{i+1} = C_i (t_i, t_{5-i}) + (s_i, s_{5-i}),  C_1 = (s_0, s_5)
+          // and the outputs pair up as (so_1, so_4) = C_1 ⊕ swap(C_4), (so_2, so_3) = C_2 ⊕ swap(C_3), (so_5, so_0) = C_5.
+          const float2 s05 = make_float2(s[0], s[5]), s14 = make_float2(s[1], s[4]), s23 = make_float2(s[2], s[3]);
+          const float2 t14 = fma2(s14, splat(-2.0f), splat(1.0f)), t23 = fma2(s23, splat(-2.0f), splat(1.0f));
+          const float2 c1 = s05;
+          const float2 c2 = fma2(c1, t14, s14);
+          const float2 c3 = fma2(c2, t23, s23);
+          const float2 c4 = fma2(c3, make_float2(t23.y, t23.x), make_float2(s23.y, s23.x));
+          const float2 c5 = fma2(c4, make_float2(t14.y, t14.x), make_float2(s14.y, s14.x));
+          const float2 c4s = make_float2(c4.y, c4.x), c3s = make_float2(c3.y, c3.x);
+          const float2 o14 = fma2(mul2(c1, splat(-2.0f)), c4s, add2(c1, c4s));
+          const float2 o23 = fma2(mul2(c2, splat(-2.0f)), c3s, add2(c2, c3s));
+          so[1] = o14.x; so[4] = o14.y; so[2] = o23.x; so[3] = o23.y; so[5] = c5.x; so[0] = c5.y;
+          if (p.out_soft) sall = sp_chain(c5.x, s[5], fmaf(-2.0f, s[5], 1.0f));
+          // ratios two at a time: clip, 1 - s, reciprocal, product
+          const int ka[3] = {1, 2, 5}, kb[3] = {4, 3, 0};
 #pragma unroll
-        for (int k = 2; k < 6; k++) pre[k] = sp_chain(pre[k - 1], s[k - 1], tt[k - 1]);
-        suf[5] = s[5];
+          for (int i = 0; i < 3; i++) {
+            const float2 sc = make_float2(fmaxf(so[ka[i]], kSmallProbF), fmaxf(so[kb[i]], kSmallProbF));
+            const float2 big = fma2(sc, splat(-1.0f), splat(1.0f));
+            const bool ha = (int)(x ^ w[ka[i]]) < 0, hb = (int)(x ^ w[kb[i]]) < 0;
+            float2 q;
+            if (RATIO == 0) {         // second, predicated reciprocal for hard = 1 (XU pipe)
+              q = mul2(big, make_float2(rcp_approx(sc.x), rcp_approx(sc.y)));
+              if (ha) q.x = rcp_approx(q.x);
+              if (hb) q.y = rcp_approx(q.y);
+            } else if (RATIO == 1) {  // select numerator / denominator (ALU pipe)
+              const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
+              const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);
+              q = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+            } else {                  // one of each: balances the XU and ALU pipes
+              const float numb = hb ? sc.y : big.y, denb = hb ? big.y : sc.y;
+              q = mul2(make_float2(big.x, numb), make_float2(rcp_approx(sc.x), rcp_approx(denb)));
+              if (ha) q.x = rcp_approx(q.x);
+            }
+            msg[ka[i] * mpad + slot] = __float_as_uint(q.x);
+            msg[kb[i] * mpad + slot] = __float_as_uint(q.y);
+          }
+        } else {
+          float tt[6];
 #pragma unroll
-        for (int k = 4; k >= 1; k--) suf[k] = sp_chain(suf[k + 1], s[k], tt[k]);
-        float so[6];
-        so[0] = suf[1];
-        so[5] = pre[5];
+          for (int k = 0; k < 6; k++) tt[k] = fmaf(-2.0f, s[k], 1.0f);
+          float pre[6], suf[6];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}, suf[k] = s_k ⊕ … ⊕ s_5
+          pre[1] = s[0];
 #pragma unroll
-        for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
+          for (int k = 2; k < 6; k++) pre[k] = sp_chain(pre[k - 1], s[k - 1], tt[k - 1]);
+          suf[5] = s[5];
 #pragma unroll
-        for (int k = 0; k < 6; k++)
-          msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x ^ w[k]));
-        if (p.out_soft) {  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
-          const float sall = sp_chain(pre[5], s[5], tt[5]);
-          soft += __logf((x >> 31) ? sall : 1.0f - sall);
+          for (int k = 4; k >= 1; k--) suf[k] = sp_chain(suf[k + 1], s[k], tt[k]);
+          so[0] = suf[1];
+          so[5] = pre[5];
+#pragma unroll
+          for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
+#pragma unroll
+          for (int k = 0; k < 6; k++) msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x ^ w[k]));
+          if (p.out_soft) sall = sp_chain(pre[5], s[5], tt[5]);
         }
+        if (p.out_soft)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
+          soft += __logf((x >> 31) ? sall : 1.0f - sall);
       }
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -365,11 +450,15 @@ dec_kernel_t kernel_of(DecKernelKind k) {
     case DEC_REG_6_3: {
       const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
       const int b = e ? atoi(e) : 3;
+      const char *pe = getenv("KML_DEC_NOPACK");  // A/B knob: scalar fp32 instead of FMUL2/FADD2/FFMA2
+      if (pe && atoi(pe)) return bp_regular_kernel<6, 3, 384, 3, false>;
+      const char *re = getenv("KML_DEC_RATIO");
+      if (re && atoi(re) == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0>;
+      if (re && atoi(re) == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1>;
       if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
       if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
       return bp_regular_kernel<6, 3, 384, 3>;
     }
-    case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
     case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;

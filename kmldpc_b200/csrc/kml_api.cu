@@ -152,10 +152,10 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
                        mpad == M && N == 2 * M;
   DecLaunch dl{};
   int dv_tab;
-  if (regular && N == 6 * 384) {
+  if (regular && N == 6 * 384) {  // PEG2304: 384 threads x (6 variables, 3 checks), 3 CTAs per SM
     dl.kind = DEC_REG_6_3; dl.threads = 384; dv_tab = 3;
     dl.smem_bytes = 6 * plane * 4;
-  } else if (regular && N == 12 * 672) {
+  } else if (regular && N == 12 * 672) {  // PEG8064: 672 threads x (12, 6), one CTA (97 KB of messages) per SM
     dl.kind = DEC_REG_12_6; dl.threads = 672; dv_tab = 3;
     dl.smem_bytes = 6 * plane * 4;
   } else {
