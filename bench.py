@@ -49,18 +49,25 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc:
@@ -69,17 +76,24 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r[1:] for r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()]
+        if self.t_begin is not None and self.t_end is not None:  # samples taken while the timed legs were running
+            inside = [r[1:] for r in self.rows if len(r) >= 10 and r[2].replace(".", "").isdigit()
+                      and self.t_begin <= r[0] <= self.t_end]
+            if len(inside) >= 3:
+                rows = inside
+        sm = [float(r[1]) for r in rows]
+        mx = [float(r[2]) for r in rows]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "window": "value + e2e + roofline legs (GPU under load)"}
 
 
 # ------------------------------------------------------------------------------------------------- reference arm (CPU)
@@ -168,6 +182,9 @@ def gpu_arm(args):
     var = kb.snr_to_var(SNR_DB)
     stream = torch.cuda.current_stream().cuda_stream
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs ~1 s to come up: start it before the (untimed) input generation
     # ---- synthetic inputs: `pool` batches of B frames, Philox-generated on the device (untimed), > L2 in total
     ys = [torch.empty((B, N_SYM, 2), dtype=torch.float32, device=dev) for _ in range(pool)]
     us = [torch.empty((B, kw), dtype=torch.int32, device=dev) for _ in range(pool)]
@@ -194,9 +211,7 @@ def gpu_arm(args):
         step_dev(i)
     counters.zero_()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     l0 = link.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -261,6 +276,7 @@ def gpu_arm(args):
     k1.record()
     torch.cuda.synchronize()
     km_ms = k0.elapsed_time(k1) / reps
+    sampler.mark_end()
 
     # ---- secondary: fused Monte-Carlo path (Philox → … → counters) and the early-exit figure at 15 dB (config.toml SNR)
     t_f = None

@@ -459,6 +459,7 @@ dec_kernel_t kernel_of(DecKernelKind k) {
       if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
       return bp_regular_kernel<6, 3, 384, 3>;
     }
+    case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
     case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;
