@@ -162,6 +162,15 @@ int kml_count_errors(kml_ctx *ctx, int B, const uint32_t *u_packed, const uint32
 int kml_simulate(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
                  uint64_t max_err_blk, uint64_t counters[4], uint64_t *iters_sum);
 
+/* Histogram mode of Simulator::run_blocks (simulator.cc:154-162) + KmCodec::GetHistogramData (kmcodec.cc:74-79): frames
+ * [frame_begin, frame_begin+frame_count) are generated and detected but NOT finally decoded; metrics[frame][4] receives
+ * the four candidate metrics (in candidate order 0°, 90°, 180°, 270°; the caller rotates them to start at the minimum
+ * like simulator.cc:155-160).  counters[4] are accumulated exactly as the reference does in this mode: CntErr runs on a
+ * uu_hat the final decoder never wrote — the last metric decode's decisions (5G / soft metric) or an untouched
+ * (zero) buffer (hard metric). */
+int kml_histogram(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count, float *metrics,
+                  uint64_t counters[4]);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Device-pointer variants (inputs already resident in HBM; asynchronous on `stream`)
  * ---------------------------------------------------------------------------------------------------------- */
@@ -187,7 +196,7 @@ typedef struct kml_sweep_cfg {
   uint64_t max_err_blk, max_num_blk;                 /* [range] maximum_error_number / maximum_block_number */
   int32_t known_h, is_5g, metric_type, metric_iter;  /* [decoder] / [xcodec] */
   int32_t max_iter, encoder_active;                  /* [ldpc] */
-  int32_t histogram_enable, reserved;                /* [histogram] (unsupported: must be 0) */
+  int32_t histogram_enable, reserved;                /* [histogram] enable: writes histogram_<snr>.txt */
   char matrix_file[512];                             /* [ldpc] matrix_file */
   char modem_file[512];                              /* [modem] modem_file */
   /* optional [gpu] table (ignored by the reference binary) */

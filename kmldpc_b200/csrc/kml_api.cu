@@ -692,6 +692,55 @@ extern "C" int kml_simulate(kml_ctx *c, double snr_db, uint64_t seed, uint64_t f
   return KML_OK;
 }
 
+extern "C" int kml_histogram(kml_ctx *c, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
+                             float *metrics, uint64_t counters[4]) {
+  if (!c || !metrics || !counters) return KML_ERR_ARG;
+  if (c->opts.known_h) return fail_arg(c, "kml_histogram: needs the four blind candidates (true_h_arg = false)");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  const double var = std::pow(10.0, -0.1 * snr_db);
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), s));
+  const bool decode_metric = c->is_5g || c->opts.metric_type;
+  for (uint64_t done = 0; done < frame_count;) {
+    const int nb = (int)std::min<uint64_t>((uint64_t)c->max_batch, frame_count - done);
+    GenParams g = gen_params(c, nb, snr_db, seed, frame_begin + done);
+    KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, s));
+    KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, s));
+    KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, s));
+    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter,
+                               l.hhat.p, l.passes.p, c->num_sms, s));
+    DemapParams d = demap_params(c, l, nb, var, 4, decode_metric ? 0 : 1);
+    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+    if (decode_metric) {
+      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
+      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
+      DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
+      p.early_exit = 1;
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      if (soft) {
+        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
+        KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
+      } else {
+        KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
+      }
+      // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)
+      KML_LAUNCH(c, launch_extract_bits(nb, c->K, c->info_offset, 4 * c->words_n, l.cc_hat_packed.p + 3 * c->words_n,
+                                       l.uu_hat_packed.p, s));
+    } else {
+      KML_CUDA(c, cudaMemsetAsync(l.uu_hat_packed.p, 0, sizeof(uint32_t) * (size_t)nb * c->k_words, s));
+    }
+    KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, nullptr, c->opts.max_iter,
+                                     c->counters.p, s));
+    KML_CUDA(c, cudaMemcpyAsync(metrics + done * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
+    KML_CUDA(c, cudaStreamSynchronize(s));
+    done += nb;
+  }
+  KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
+  return KML_OK;
+}
+
 // ================================================================================================ device-pointer variants
 extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0, uint32_t *u_packed,
                                 float *h, float *y, void *stream) {

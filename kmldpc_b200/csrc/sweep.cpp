@@ -184,8 +184,8 @@ extern "C" int kml_sweep_points(const kml_sweep_cfg *cfg) {
 extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
                              void (*log_cb)(const char *, void *), void *user) {
   if (!cfg) return KML_ERR_ARG;
-  if (cfg->histogram_enable) {
-    set_global_error("[histogram] enable = true is not supported by the GPU path (SURVEY §2 row 16)");
+  if (cfg->histogram_enable && cfg->known_h) {
+    set_global_error("[histogram] enable = true needs blind detection (true_h_arg = false): one candidate has no histogram");
     return KML_ERR_ARG;
   }
   const int n_pts = kml_sweep_points(cfg);
@@ -236,8 +236,29 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
       std::mutex mu;
       uint64_t tot[4] = {0, 0, 0, 0};
       std::atomic<int> failed{KML_OK};
+      // histogram mode (simulator.cc:81-84,154-162): "histogram_<snr>.txt" in the working directory, one line per frame
+      // with the four metrics rotated to start at the (first) minimum; frames in index order on GPU 0.
+      if (cfg->histogram_enable) {
+        const std::string fname = "histogram_" + std::to_string(snr) + ".txt";
+        std::ofstream hout(fname);
+        std::vector<float> met((size_t)chunk * 4);
+        for (uint64_t begin = 0; begin < cfg->max_num_blk && rc == KML_OK; begin += chunk) {
+          if (cfg->max_err_blk && tot[1] >= cfg->max_err_blk) break;
+          const uint64_t count = std::min<uint64_t>(chunk, cfg->max_num_blk - begin);
+          rc = kml_histogram(ctx[0], snr, cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull, begin, count, met.data(), tot);
+          if (rc != KML_OK) set_global_error(kml_last_error(ctx[0]));
+          for (uint64_t f = 0; rc == KML_OK && f < count; f++) {
+            const float *m = &met[f * 4];
+            int lo = 0;
+            for (int k = 1; k < 4; k++)
+              if (m[k] < m[lo]) lo = k;
+            for (int k = lo; k < lo + 4; k++) hout << m[k % 4] << ' ';
+            hout << std::endl;
+          }
+        }
+      }
       auto worker = [&](int g) {
-        while (failed.load() == KML_OK) {
+        while (!cfg->histogram_enable && failed.load() == KML_OK) {
           if (cfg->max_err_blk && err_blk.load() >= cfg->max_err_blk) break;  // simulator.cc:117
           const uint64_t begin = cursor.fetch_add(chunk);
           if (begin >= cfg->max_num_blk) break;
@@ -258,7 +279,7 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
       std::vector<std::thread> th;
       for (int g = 0; g < G; g++) th.emplace_back(worker, g);
       for (auto &t : th) t.join();
-      rc = failed.load();
+      if (rc == KML_OK) rc = failed.load();
       const double b = tot[2] ? (double)tot[3] / (double)tot[2] : 0.0, f = tot[0] ? (double)tot[1] / (double)tot[0] : 0.0;
       ber_v[i] = b;
       fer_v[i] = f;

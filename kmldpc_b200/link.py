@@ -242,6 +242,15 @@ class Link:
                                            _ptr(cnt, C.c_uint64), C.byref(it)), "kml_simulate")
         return cnt, int(it.value)
 
+    def histogram(self, snr_db: float, frames: int, *, seed: int = 17, frame_begin: int = 0):
+        """Histogram mode (simulator.cc:154-162): the four candidate metrics per frame + the counters the reference
+        accumulates in that mode."""
+        met = np.empty((frames, 4), np.float32)
+        cnt = np.zeros(4, np.uint64)
+        self._check(self._lib.kml_histogram(self._h, snr_db, seed, frame_begin, frames, _ptr(met, C.c_float),
+                                            _ptr(cnt, C.c_uint64)), "kml_histogram")
+        return met, cnt
+
     # ---- device-pointer variants (pointers as ints, stream as int)
     def generate_dev(self, B, snr_db, seed, frame0, u_packed_ptr, h_ptr, y_ptr, stream=0):
         self._check(self._lib.kml_generate_dev(self._h, B, snr_db, seed, frame0, u_packed_ptr, h_ptr, y_ptr, stream),

@@ -398,3 +398,28 @@ def test_context_errors_are_reported_not_fatal(kb, tmp_path):
     f.write_text("\n".join(lines) + "\n")
     with pytest.raises(kb.KmlError, match="multiple"):
         kb.Link(code, kb.Modem(str(f)))
+
+
+def test_histogram_mode(tmp_path, kb, monkeypatch):
+    """[histogram] enable = true (simulator.cc:81-84,154-162): the four candidate metrics per frame, rotated to start at the
+    minimum, in histogram_<snr>.txt; the metrics equal the resolver's on the same frames."""
+    link = util.gpu_link("peg2304_4psk_6db", max_batch=64)
+    met, cnt = link.histogram(6.0, 150, seed=9)
+    u, c, h, y = link.generate(150, 6.0, seed=9)
+    hhat, _ = link.kmeans(y)
+    ref_m, ref_k = link.resolve(y, hhat, 10 ** -0.6)
+    assert np.array_equal(met, ref_m) and cnt[0] == 150
+    assert cnt[3] == int(u.sum())          # CntErr against the untouched (zero) uu_hat of the hard-metric path
+    link.close()
+    cfg = tmp_path / "config.toml"
+    cfg.write_text(open(util.ko.CONFIG_DIR + "/config.toml").read()
+                   .replace("maximum_error_number = 1", "maximum_error_number = 1000000")
+                   .replace("maximum_block_number = 1", "maximum_block_number = 100")
+                   .replace("enable = false", "enable = true")
+                   .replace("4bit_16QAM_Gray.txt", "2bits_4PSK.txt") + "\n[gpu]\nseed = 9\nbatch = 64\n")
+    monkeypatch.chdir(tmp_path)
+    sim = kb.Simulator(str(cfg), data_dir=util.ko.CONFIG_DIR)
+    snr, ber, fer, counters = sim.simulate(echo=False)
+    rows = [list(map(float, l.split())) for l in open(tmp_path / "histogram_15.000000.txt")]
+    assert len(rows) == 100 and all(len(r) == 4 for r in rows)
+    assert all(r[0] == min(r) for r in rows) and counters[0, 0] == 100
