@@ -423,3 +423,20 @@ def test_histogram_mode(tmp_path, kb, monkeypatch):
     rows = [list(map(float, l.split())) for l in open(tmp_path / "histogram_15.000000.txt")]
     assert len(rows) == 100 and all(len(r) == 4 for r in rows)
     assert all(r[0] == min(r) for r in rows) and counters[0, 0] == 100
+
+
+def test_multi_gpu_sweep_counters_identical(tmp_path, kb):
+    """kml_sweep_run on 1 and on all GPUs of the box: same frames (global Philox index) → identical counters."""
+    import torch
+    G = torch.cuda.device_count()
+    if G < 2:
+        pytest.skip("needs at least 2 GPUs")
+    base = open(util.ko.CONFIG_DIR + "/config.toml").read()
+    base = base.replace("maximum_error_number = 1", "maximum_error_number = 100000000").replace(
+        "maximum_block_number = 1", "maximum_block_number = 20000").replace("4bit_16QAM_Gray.txt", "2bits_4PSK.txt")
+    out = {}
+    for g in (1, G):
+        cfg = tmp_path / f"c{g}.toml"
+        cfg.write_text(base + f"\n[gpu]\nseed = 17\ngpus = {g}\nbatch = 2048\n")
+        out[g] = kb.Simulator(str(cfg), data_dir=util.ko.CONFIG_DIR).simulate(echo=False)[3]
+    assert np.array_equal(out[1], out[G]) and out[1][0, 0] == 20000
