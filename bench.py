@@ -278,6 +278,40 @@ def gpu_arm(args):
     km_ms = k0.elapsed_time(k1) / reps
     sampler.mark_end()
 
+    # ---- secondary: throughput-mode decoders (NOT the reference's algorithm: normalised min-sum, gated by BER/FER tests)
+    thr = {}
+    if rank == 0 and not args.quick:
+        def time_decode(alg, iters):
+            link.set_algorithm(alg, 0.8)
+            for _ in range(2):
+                link.decode_dev(B, llr.data_ptr(), False, iters, cc_hat.data_ptr(), ret.data_ptr(), stream)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                link.decode_dev(B, llr.data_ptr(), False, iters, cc_hat.data_ptr(), ret.data_ptr(), stream)
+            b.record()
+            torch.cuda.synchronize()
+            return B * K_INFO / (a.elapsed_time(b) / 5 * 1e-3) / 1e6
+        link.set_early_exit(False)
+        for alg, label in ((1, "minsum_fp32"), (2, "minsum_fp16x2")):
+            for iters in (50, 10, 5):
+                thr[f"{label}_I{iters}_decode_mbps"] = time_decode(alg, iters)
+        thr["sum_product_I10_decode_mbps"] = time_decode(0, 10)
+        thr["sum_product_I5_decode_mbps"] = time_decode(0, 5)
+        link.set_algorithm(2, 0.8)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_dev(0)
+        a.record()
+        for i in range(5):
+            step_dev(i)
+        b.record()
+        torch.cuda.synchronize()
+        thr["minsum_fp16x2_I50_receiver_mbps"] = 5 * B * K_INFO / (a.elapsed_time(b) * 1e-3) / 1e6
+        thr["note"] = ("decode-only = kml_decode_dev on HBM-resident LLRs, early exit off, CUDA events; min-sum is not in the "
+                       "reference (no parity claim): gated by tests/test_gpu_minsum.py against the sum-product decoder")
+        link.set_algorithm(0)
+        link.set_early_exit(True)
+
     # ---- secondary: fused Monte-Carlo path (Philox → … → counters) and the early-exit figure at 15 dB (config.toml SNR)
     t_f = None
     if rank == 0 and not args.quick:
@@ -350,6 +384,8 @@ def gpu_arm(args):
                 "clocks": clocks}
         if cpu:
             line["cpu_baseline"] = cpu
+        if thr:
+            line["throughput_mode"] = thr
         if t_f is not None:
             line["fused_simulate"] = {"mbps": 4 * B * K_INFO / t_f / 1e6, "frames": 4 * B, "iters_per_frame": fit / (4 * B),
                                       "note": "kml_simulate: Philox bits+encode+map+channel+receiver+count, host wall clock"}

@@ -82,7 +82,11 @@ typedef struct kml_opts {
                             0 = fixed-iteration timing mode: all max_iter iterations are executed but the decision
                             and return value are latched at the first zero syndrome, so RESULTS ARE IDENTICAL */
   int32_t max_batch;     /* frames per launch the workspaces are sized for (0 = default 16384) */
-  int32_t reserved;
+  int32_t algorithm;     /* 0 = flooding sum-product = the reference's decoder (parity mode);
+                            1 = normalised min-sum, fp32 messages (throughput mode; NOT in the reference, hence not
+                                reference-pinned: checked against oracle/minsum_ref.py and gated by BER/FER against 0);
+                            2 = the same with fp16 messages, two frames per shared-memory word ((3,6)-regular codes;
+                                other graphs run algorithm 1) */
 } kml_opts;
 
 typedef struct kml_ctx kml_ctx;
@@ -91,6 +95,8 @@ int kml_create(kml_ctx **out, int device, const kml_code *code, const kml_modem 
 void kml_destroy(kml_ctx *ctx);
 const char *kml_last_error(const kml_ctx *ctx);  /* ctx may be NULL: message of the last failed create/load */
 int kml_set_early_exit(kml_ctx *ctx, int early_exit);
+/* Switches the decoder of every later call (also the 5G metric decodes); alpha = min-sum normalisation in (0, 1]. */
+int kml_set_algorithm(kml_ctx *ctx, int algorithm, double alpha);
 /* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
 int kml_info(const kml_ctx *ctx, int32_t info[8]);
 /* Decoder launch facts: info[0..7] = kernel kind, threads per CTA, dynamic shared memory bytes, CTAs per SM,
@@ -201,7 +207,7 @@ typedef struct kml_sweep_cfg {
   char modem_file[512];                              /* [modem] modem_file */
   /* optional [gpu] table (ignored by the reference binary) */
   uint64_t seed;
-  int32_t n_gpus, max_batch, early_exit, reserved2;
+  int32_t n_gpus, max_batch, early_exit, algorithm;  /* [gpu] gpus / batch / early_exit / algorithm (0 SPA, 1 min-sum) */
 } kml_sweep_cfg;
 
 /* Minimal TOML reader for exactly the keys above (the reference parses the same file with toml11, kmldpc.cpp:29-31). */

@@ -30,7 +30,7 @@ class KmlModem(C.Structure):
 class KmlOpts(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("known_h", C.c_int32), ("metric_type", C.c_int32),
                 ("metric_iter", C.c_int32), ("kmeans_iter", C.c_int32), ("early_exit", C.c_int32),
-                ("max_batch", C.c_int32), ("reserved", C.c_int32)]
+                ("max_batch", C.c_int32), ("algorithm", C.c_int32)]
 
 
 class KmlSweepCfg(C.Structure):
@@ -41,7 +41,7 @@ class KmlSweepCfg(C.Structure):
                 ("histogram_enable", C.c_int32), ("reserved", C.c_int32),
                 ("matrix_file", C.c_char * 512), ("modem_file", C.c_char * 512),
                 ("seed", C.c_uint64),
-                ("n_gpus", C.c_int32), ("max_batch", C.c_int32), ("early_exit", C.c_int32), ("reserved2", C.c_int32)]
+                ("n_gpus", C.c_int32), ("max_batch", C.c_int32), ("early_exit", C.c_int32), ("algorithm", C.c_int32)]
 
 
 LOG_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
@@ -56,6 +56,7 @@ SYMBOLS = {
     "kml_destroy": (None, [C.c_void_p]),
     "kml_last_error": (C.c_char_p, [C.c_void_p]),
     "kml_set_early_exit": (C.c_int, [C.c_void_p, C.c_int]),
+    "kml_set_algorithm": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "kml_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_decoder_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_launch_count": (C.c_uint64, [C.c_void_p]),

@@ -443,9 +443,8 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
 #undef KML_VN_CASE
 #undef KML_CN_CASE
 
-typedef void (*dec_kernel_t)(const DecParams);
-
-dec_kernel_t kernel_of(DecKernelKind k) {
+dec_kernel_t kernel_of(DecKernelKind k, int alg) {
+  if (alg != 0) return minsum_kernel_of(k, alg);
   switch (k) {
     case DEC_REG_6_3: {
       const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
@@ -470,7 +469,7 @@ dec_kernel_t kernel_of(DecKernelKind k) {
 }  // namespace
 
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind);
+  dec_kernel_t k = kernel_of(l.kind, l.alg);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -486,9 +485,10 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   int grid = num_sms * l.ctas_per_sm;
-  if (grid > p.B) grid = p.B;
+  const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
+  if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  kernel_of(l.kind)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  kernel_of(l.kind, l.alg)<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -59,7 +59,8 @@ struct kml_ctx {
   DevBuf<uint16_t> vn_addr;
   DevBuf<uint8_t> vn_deg, cn_deg;
   DecTables dt{};
-  DecLaunch dl{};
+  DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
+  float alpha = 0.8f;
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
@@ -199,8 +200,12 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
   c->dt.n = N; c->dt.m_pad = mpad; c->dt.plane = plane; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct;
   c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
-  KML_CUDA(c, dec_prepare(dl));
-  c->dl = dl;
+  for (int alg = 0; alg < 3; alg++) {
+    dl.alg = alg;
+    KML_CUDA(c, dec_prepare(dl));
+    c->dl_alg[alg] = dl;
+  }
+  c->dl = c->dl_alg[c->opts.algorithm];
   return KML_OK;
 }
 
@@ -211,7 +216,7 @@ DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t 
   p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
   p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
   p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
-  p.work_counter = l.work_counter.p; p.words_n = c->words_n;
+  p.work_counter = l.work_counter.p; p.words_n = c->words_n; p.alpha = c->alpha;
   return p;
 }
 
@@ -292,6 +297,9 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     return fail_arg(nullptr, "kml_create: n_tx is not a multiple of bits_per_symbol");
   if (modem->bits_per_symbol > 6) return fail_arg(nullptr, "kml_create: constellations above 64 points are not built");
   if (opts->max_iter < 1) return fail_arg(nullptr, "kml_create: max_iter < 1");
+  if (opts->algorithm < 0 || opts->algorithm > 2) return fail_arg(nullptr, "kml_create: unknown algorithm");
+  if (opts->algorithm != 0 && opts->metric_type)
+    return fail_arg(nullptr, "kml_create: the soft-syndrome metric needs the sum-product decoder (algorithm = 0)");
   auto *c = new kml_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
@@ -371,6 +379,18 @@ extern "C" const char *kml_last_error(const kml_ctx *c) { return c ? c->err.c_st
 extern "C" int kml_set_early_exit(kml_ctx *c, int early_exit) {
   if (!c) return KML_ERR_ARG;
   c->opts.early_exit = early_exit ? 1 : 0;
+  return KML_OK;
+}
+
+extern "C" int kml_set_algorithm(kml_ctx *c, int algorithm, double alpha) {
+  if (!c) return KML_ERR_ARG;
+  if (algorithm < 0 || algorithm > 2)
+    return fail_arg(c, "kml_set_algorithm: 0 = sum-product, 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames");
+  if (algorithm != 0 && c->opts.metric_type) return fail_arg(c, "kml_set_algorithm: soft-syndrome metric needs sum-product");
+  if (algorithm != 0 && !(alpha > 0.0 && alpha <= 1.0)) return fail_arg(c, "kml_set_algorithm: alpha must be in (0, 1]");
+  c->opts.algorithm = algorithm;
+  if (algorithm != 0) c->alpha = (float)alpha;
+  c->dl = c->dl_alg[algorithm];
   return KML_OK;
 }
 

@@ -29,17 +29,22 @@ struct DecParams {
   float *out_soft;          // optional [B]: sum over rows of ln(syndrom_soft) after the LAST check-node phase executed
   unsigned int *work_counter;  // dynamic frame scheduler (zeroed by the launcher)
   int words_n;
+  float alpha;              // min-sum normalisation (algorithm = 1 only)
 };
 
 enum DecKernelKind { DEC_REG_6_3 = 0, DEC_REG_12_6 = 1, DEC_GEN_4_8 = 2, DEC_GEN_9_10 = 3, DEC_GEN_16_32 = 4 };
 
 struct DecLaunch {
   DecKernelKind kind;
+  int alg;  // 0 = sum-product (reference semantics, bp_decode.cu), 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
 };
 
+typedef void (*dec_kernel_t)(const DecParams);
+dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
+inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 

@@ -173,6 +173,7 @@ extern "C" int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg) {
   if (get_num(t, "gpu.gpus", d, err, false) && t.has("gpu.gpus")) cfg->n_gpus = (int)d;
   if (get_num(t, "gpu.batch", d, err, false) && t.has("gpu.batch")) cfg->max_batch = (int)d;
   if (get_bool(t, "gpu.early_exit", b, err, false) && t.has("gpu.early_exit")) cfg->early_exit = b;
+  if (get_num(t, "gpu.algorithm", d, err, false) && t.has("gpu.algorithm")) cfg->algorithm = (int)d;
   return KML_OK;
 }
 
@@ -223,7 +224,7 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
   std::vector<double> ber_v(n_pts, 0.0), fer_v(n_pts, 0.0);
   kml_opts o{};
   o.max_iter = cfg->max_iter; o.known_h = cfg->known_h; o.metric_type = cfg->metric_type; o.metric_iter = cfg->metric_iter;
-  o.kmeans_iter = 20; o.early_exit = cfg->early_exit; o.max_batch = cfg->max_batch;
+  o.kmeans_iter = 20; o.early_exit = cfg->early_exit; o.max_batch = cfg->max_batch; o.algorithm = cfg->algorithm;
   std::vector<kml_ctx *> ctx(G, nullptr);
   for (int g = 0; g < G && rc == KML_OK; g++) rc = kml_create(&ctx[g], g, code, modem, &o);
   if (rc == KML_OK) {

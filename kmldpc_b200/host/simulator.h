@@ -6,7 +6,7 @@
 // src/simulator.cc:3-22, src/kmcodec.cc:20-40, lib/lab/src/binaryldpccodec.cc:62-73 and lib/lab/src/modem.cc:4-9
 // (missing key → toml11 throws, as in the reference); Simulate() hands the sweep to libkmldpc_b200.so
 // (kml_sweep_run) and forwards its lines to the reference's logger, so logs and BER/FER tables look the same.
-// Optional GPU-only knobs live in a [gpu] table the CPU binary ignores: seed, gpus, batch, early_exit.
+// Optional GPU-only knobs live in a [gpu] table the CPU binary ignores: seed, gpus, batch, early_exit, algorithm.
 #ifndef KMLDPC_B200_SIMULATOR_FACADE_H
 #define KMLDPC_B200_SIMULATOR_FACADE_H
 
@@ -51,6 +51,7 @@ class Simulator {
       cfg_.n_gpus = (int)toml::find_or<std::int64_t>(gpu, "gpus", 1);
       cfg_.max_batch = (int)toml::find_or<std::int64_t>(gpu, "batch", 0);
       cfg_.early_exit = toml::find_or<bool>(gpu, "early_exit", true) ? 1 : 0;
+      cfg_.algorithm = (int)toml::find_or<std::int64_t>(gpu, "algorithm", 0);  // 1 = normalised min-sum (throughput mode)
     }
   }
   virtual ~Simulator() = default;

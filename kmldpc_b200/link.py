@@ -90,11 +90,11 @@ class Modem:
 
 class Link:
     def __init__(self, code: LdpcCode, modem: Modem, *, max_iter=50, known_h=False, metric_type=False, metric_iter=5,
-                 kmeans_iter=20, early_exit=True, max_batch=0, device=0):
+                 kmeans_iter=20, early_exit=True, max_batch=0, device=0, algorithm=0):
         self._lib = capi.load()
         self.code, self.modem = code, modem
         self.opts = capi.KmlOpts(max_iter, int(known_h), int(metric_type), metric_iter, kmeans_iter, int(early_exit),
-                                 max_batch, 0)
+                                 max_batch, int(algorithm))
         self._h = C.c_void_p()
         rc = self._lib.kml_create(C.byref(self._h), device, code._p, modem._p, C.byref(self.opts))
         if rc != 0:
@@ -134,6 +134,10 @@ class Link:
 
     def set_early_exit(self, flag: bool):
         self._check(self._lib.kml_set_early_exit(self._h, int(flag)), "kml_set_early_exit")
+
+    def set_algorithm(self, algorithm: int, alpha: float = 0.8):
+        """0 = sum-product (the reference's decoder), 1 = normalised min-sum (throughput mode, not reference-pinned)."""
+        self._check(self._lib.kml_set_algorithm(self._h, int(algorithm), float(alpha)), "kml_set_algorithm")
 
     # ---- stages (host buffers)
     def encode(self, u: np.ndarray) -> np.ndarray:

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE ONLY — numpy (float32) restatement of the normalised min-sum flooding decoder offered as
+`algorithm = 1` (throughput mode).  NOT reference-pinned: the reference has no min-sum; this file
+exists so the CUDA min-sum kernel has an independent statement of the same algorithm to be checked against, and the
+algorithm itself is gated by BER/FER against the sum-product oracle (tests/test_gpu_minsum.py).
+
+Schedule, stopping rule and return value are the reference decoder's (binaryldpccodec.cc:175-277); only the node
+updates differ:  VN  total = L_ch + sum c2v,  v2c_e = total - c2v_e,  bit = (total > 0) ? 0 : 1
+                 CN  c2v_e = alpha * min_{e' != e} |v2c_e'| * prod sign,  clipped to +-ln((1-1e-12)/1e-12)."""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+LLR_CLIP = f32(27.631021)
+
+
+def decode(row_ptr, col_idx, n_graph, punct, llr, iters, max_iter, alpha=0.8):
+    """llr [B, n_tx] float32 (ln P0/P1).  Returns ret[B], cc_hat[B, n_graph]."""
+    rp, ci = np.asarray(row_ptr), np.asarray(col_idx)
+    M, E = len(rp) - 1, len(ci)
+    B = llr.shape[0]
+    edge_row = np.repeat(np.arange(M), np.diff(rp))
+    ch = np.zeros((B, n_graph), f32)
+    ch[:, punct:] = np.clip(llr.astype(f32), -LLR_CLIP, LLR_CLIP)
+    c2v = np.zeros((B, E), f32)
+    ret = np.full(B, iters + (1 if iters < max_iter else 0), np.int32)
+    done = np.zeros(B, bool)
+    out = np.zeros((B, n_graph), np.int8)
+    alpha = f32(alpha)
+    for t in range(iters):
+        total = ch.copy()
+        np.add.at(total, (slice(None), ci), c2v)
+        bits = (~(total > 0)).astype(np.int8)
+        synd = np.zeros((B, M), np.int8)
+        np.bitwise_xor.at(synd, (slice(None), edge_row), bits[:, ci])
+        ok = ~synd.any(axis=1)
+        out[~done] = bits[~done]
+        ret[ok & ~done] = t + (1 if t < max_iter else 0)
+        done |= ok
+        if done.all():
+            break
+        v2c = (total[:, ci] - c2v).astype(f32)
+        mag = np.abs(v2c)
+        neg = v2c < 0  # sign bit; -0.0 cannot occur because total - c2v of finite values
+        new = np.zeros_like(c2v)
+        for r in range(M):
+            a, b = rp[r], rp[r + 1]
+            m = mag[:, a:b]
+            srt = np.sort(m, axis=1)
+            min1, min2 = srt[:, :1], srt[:, 1:2] if b - a > 1 else srt[:, :1]
+            par = np.logical_xor.reduce(neg[:, a:b], axis=1, keepdims=True)
+            o = np.where(m == min1, min2, min1) * alpha
+            o = np.minimum(o, LLR_CLIP)
+            sgn = par ^ neg[:, a:b]
+            new[:, a:b] = np.where(sgn, -o, o)
+        c2v = np.where(done[:, None], c2v, new).astype(f32)
+    return ret, out

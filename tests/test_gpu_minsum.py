@@ -1,0 +1,89 @@
+"""Throughput-mode decoder (algorithm = 1, normalised min-sum).  NOT reference-pinned — the reference has no min-sum
+(SURVEY §0.3).  Two gates instead: (1) the CUDA kernel against an independent numpy statement of the same algorithm
+(oracle/minsum_ref.py) on the reference's own frames; (2) BER/FER against the sum-product decoder (the reference's
+algorithm) on the same Philox frames, inside the binomial interval plus the small known min-sum loss."""
+import numpy as np
+import pytest
+
+from oracle import minsum_ref
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,frames", [("peg2304_4psk_6db", 120), ("peg2304_16qam_gray_12db", 120),
+                                         ("5g_16qam_gray_10db", 60), ("peg8064_64qam_20db", 12)])
+def test_minsum_kernel_matches_numpy_statement(name, frames):
+    olink, rs = util.oracle_frames(name, frames)
+    link = util.gpu_link(name, algorithm=1)
+    ex = olink.code.export(with_enc=False)
+    llr = np.stack([util.llr_of_p0(r.p0) for r in rs]).astype(np.float32)
+    cc, uu, ret = link.decode(llr)
+    rret, rcc = minsum_ref.decode(ex["row_ptr"], ex["col_idx"], olink.code.N, olink.code.two_z, llr, 50, 50, alpha=0.8)
+    # fp32 summation order differs (gather order vs CSR order) and the kernel borrows the mantissa LSB: allow a few
+    # frames to leave one iteration apart, demand identical words wherever both stop at the same iteration
+    assert (ret == rret).mean() >= 0.95, np.where(ret != rret)[0][:8]
+    both = (ret == rret) & (rret < 50)
+    assert both.sum() > 0 or "8064" in name
+    assert np.array_equal(cc[both], rcc[both])
+    link.close()
+
+
+@pytest.mark.parametrize("name,snr,frames", [("peg2304_4psk_6db", 6.0, 30000), ("peg2304_4psk_6db", 12.0, 30000),
+                                             ("peg2304_16qam_gray_12db", 15.0, 30000)])
+def test_minsum_ber_fer_gate_against_sum_product(name, snr, frames):
+    link = util.gpu_link(name, max_batch=8192)
+    spa, it_spa = link.simulate(snr, frames, seed=23)
+    link.set_algorithm(1, 0.8)
+    ms, it_ms = link.simulate(snr, frames, seed=23)          # the same frames
+    link.set_algorithm(0)
+    again, _ = link.simulate(snr, frames, seed=23)
+    assert np.array_equal(again, spa)                         # switching back restores the reference decoder exactly
+    fer_spa, fer_ms = spa[1] / spa[0], ms[1] / ms[0]
+    sd = np.sqrt(fer_spa * (1 - fer_spa) / frames)
+    # same frames → the difference is far below the binomial spread; min-sum may lose a little, never gain much
+    assert fer_ms <= fer_spa + 3 * sd + 0.01, (fer_ms, fer_spa)
+    assert fer_ms >= fer_spa - 3 * sd - 0.005, (fer_ms, fer_spa)
+    ber_spa, ber_ms = spa[3] / spa[2], ms[3] / ms[2]
+    assert abs(ber_ms - ber_spa) <= 0.1 * ber_spa + 2e-3, (ber_ms, ber_spa)
+    assert it_ms <= 1.3 * it_spa + frames                     # converges in a comparable number of iterations
+    link.close()
+
+
+def test_minsum_rejects_soft_metric():
+    import kmldpc_b200 as kb
+    code, mod = kb.LdpcCode("PEG2304regular0.5.txt"), kb.Modem("2bits_4PSK.txt")
+    with pytest.raises(kb.KmlError, match="sum-product"):
+        kb.Link(code, mod, metric_type=True, algorithm=1)
+    link = kb.Link(code, mod, metric_type=True)
+    with pytest.raises(kb.KmlError, match="sum-product"):
+        link.set_algorithm(1)
+    link.close()
+
+
+@pytest.mark.parametrize("name,snr,frames", [("peg2304_4psk_6db", 6.0, 30000), ("peg2304_16qam_gray_12db", 15.0, 30000),
+                                             ("peg8064_64qam_20db", 22.0, 6000)])
+def test_fp16_two_frame_minsum_gate(name, snr, frames):
+    """algorithm = 2 (fp16 messages, two frames per shared-memory word): BER/FER gate against the sum-product decoder on the
+    same frames, and pairing must not couple frames: odd batches and shifted pairings give the same per-frame answers."""
+    link = util.gpu_link(name, max_batch=4096)
+    spa, _ = link.simulate(snr, frames, seed=29)
+    link.set_algorithm(2, 0.8)
+    ms, it_ms = link.simulate(snr, frames, seed=29)
+    fer_spa, fer_ms = spa[1] / spa[0], ms[1] / ms[0]
+    sd = np.sqrt(max(fer_spa * (1 - fer_spa), 1e-4) / frames)
+    assert fer_ms <= fer_spa + 3 * sd + 0.01 and fer_ms >= fer_spa - 3 * sd - 0.005, (fer_ms, fer_spa)
+    assert abs(ms[3] / ms[2] - spa[3] / spa[2]) <= 0.1 * spa[3] / spa[2] + 2e-3
+    # pairing independence
+    u, c, h, y = link.generate(65, snr, seed=31)
+    llr = link.demap(y, h, 10 ** (-0.1 * snr))
+    cc_all, _, ret_all = link.decode(llr)              # pairs (0,1), (2,3) … (64, 64)
+    cc_odd, _, ret_odd = link.decode(llr[1:])          # pairs (1,2), (3,4) …
+    assert np.array_equal(cc_all[1:], cc_odd) and np.array_equal(ret_all[1:], ret_odd)
+    cc_one, _, ret_one = link.decode(llr[64:65])
+    assert np.array_equal(cc_one[0], cc_all[64]) and ret_one[0] == ret_all[64]
+    # fixed-iteration mode latches per frame
+    link.set_early_exit(False)
+    cc_fix, _, ret_fix = link.decode(llr)
+    assert np.array_equal(ret_fix, ret_all) and np.array_equal(cc_fix[ret_all < 50], cc_all[ret_all < 50])
+    link.close()

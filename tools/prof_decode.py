@@ -10,7 +10,7 @@ snr = float(sys.argv[3]) if len(sys.argv) > 3 else -5.0
 matrix = sys.argv[4] if len(sys.argv) > 4 else "PEG2304regular0.5.txt"
 modem = sys.argv[5] if len(sys.argv) > 5 else "2bits_QPSK.txt"
 code, mod = kb.LdpcCode(matrix, is_5g=matrix.startswith("5G")), kb.Modem(modem)
-link = kb.Link(code, mod, max_iter=50, max_batch=B)
+link = kb.Link(code, mod, max_iter=50, max_batch=B, algorithm=int(os.environ.get('KML_ALG', '0')))
 dev = torch.device("cuda", 0)
 s = torch.cuda.current_stream().cuda_stream
 y = torch.empty((B, link.n_sym, 2), dtype=torch.float32, device=dev)
