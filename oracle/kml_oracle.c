@@ -653,3 +653,48 @@ int64_t kmo_run(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double
   free(ar);
   return iters;
 }
+
+typedef struct {
+  const kmo_code *c; const kmo_modem *m; const kmo_opts *o;
+  double snr; long frame0, frames; int tid, threads;
+  double *yy, *h, *hhat; int32_t *kstar, *ret, *nerr; uint8_t *converged, *uu, *uu_hat;
+} bulk_arg;
+
+static void *bulk_thread(void *p) {
+  bulk_arg *a = p;
+  const int n_sym = a->c->n_tx / a->m->bits, k = a->c->k;
+  int *u = malloc(sizeof(int) * k), *uh = malloc(sizeof(int) * k), *cch = malloc(sizeof(int) * a->c->n);
+  double *y = malloc(sizeof(double) * 2 * n_sym);
+  for (long f = a->tid; f < a->frames; f += a->threads) {
+    kmo_lcg g;
+    kmo_lcg_seed(&g, (17 + 1000003L * (f + a->frame0)) % (LCG_M - 1) + 1);
+    kmo_frame_out fo;
+    kmo_frame(a->c, a->m, a->o, &g, a->snr, &fo, u, 0, y, 0, 0, cch, uh);
+    if (a->yy) memcpy(a->yy + (size_t)f * 2 * n_sym, y, sizeof(double) * 2 * n_sym);
+    if (a->h) { a->h[2 * f] = fo.h[0]; a->h[2 * f + 1] = fo.h[1]; }
+    if (a->hhat) { a->hhat[2 * f] = fo.hhat[0]; a->hhat[2 * f + 1] = fo.hhat[1]; }
+    if (a->kstar) a->kstar[f] = fo.kstar;
+    if (a->ret) a->ret[f] = fo.ret;
+    if (a->nerr) a->nerr[f] = fo.nerr;
+    if (a->converged) a->converged[f] = (uint8_t)(kmo_parity_check(a->c, cch) == 0);
+    if (a->uu) for (int t = 0; t < k; t++) a->uu[(size_t)f * k + t] = (uint8_t)u[t];
+    if (a->uu_hat) for (int t = 0; t < k; t++) a->uu_hat[(size_t)f * k + t] = (uint8_t)uh[t];
+  }
+  free(u); free(uh); free(cch); free(y);
+  return NULL;
+}
+
+void kmo_bulk(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double snr_db, long frame0, long frames, int threads,
+              double *yy, double *h, double *hhat, int32_t *kstar, int32_t *ret, int32_t *nerr, uint8_t *converged,
+              uint8_t *uu, uint8_t *uu_hat) {
+  if (threads < 1) threads = 1;
+  pthread_t *th = malloc(sizeof(pthread_t) * threads);
+  bulk_arg *ar = calloc(threads, sizeof(bulk_arg));
+  for (int t = 0; t < threads; t++) {
+    ar[t] = (bulk_arg){c, m, o, snr_db, frame0, frames, t, threads, yy, h, hhat, kstar, ret, nerr, converged, uu, uu_hat};
+    pthread_create(&th[t], NULL, bulk_thread, &ar[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(ar);
+}

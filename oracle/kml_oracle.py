@@ -234,6 +234,24 @@ class Link:
         return FrameResult(true_h, complex(*fo.hhat), np.array(fo.metric), fo.kstar, fo.ret, -1,
                            None, None, y, cl.view(np.complex128), p0, cch, uh)
 
+    def bulk(self, snr_db: float, frames: int, threads: int | None = None, frame0: int = 0) -> dict:
+        """`frames` independent reference frames (frame f has its own LCG), computed on `threads` host threads."""
+        c, m = self.code, self.modem
+        threads = threads or (os.cpu_count() or 1)
+        out = dict(y=np.empty((frames, self.n_sym, 2), np.float64), h=np.empty((frames, 2), np.float64),
+                   hhat=np.empty((frames, 2), np.float64), kstar=np.empty(frames, np.int32), ret=np.empty(frames, np.int32),
+                   nerr=np.empty(frames, np.int32), converged=np.empty(frames, np.uint8),
+                   u=np.empty((frames, c.K), np.uint8), uu_hat=np.empty((frames, c.K), np.uint8))
+        lib().kmo_bulk(C.c_void_p(c._h), C.c_void_p(m._h), C.byref(self.opts), C.c_double(snr_db), C.c_long(frame0),
+                       C.c_long(frames), C.c_int(threads), _p(out["y"], C.c_double), _p(out["h"], C.c_double),
+                       _p(out["hhat"], C.c_double), _p(out["kstar"], C.c_int32), _p(out["ret"], C.c_int32),
+                       _p(out["nerr"], C.c_int32), _p(out["converged"], C.c_uint8), _p(out["u"], C.c_uint8),
+                       _p(out["uu_hat"], C.c_uint8))
+        out["y"] = out["y"].view(np.complex128).reshape(frames, self.n_sym)
+        out["h"] = out["h"].view(np.complex128).reshape(frames)
+        out["hhat"] = out["hhat"].view(np.complex128).reshape(frames)
+        return out
+
     def run(self, snr_db: float, frames: int, threads: int = 1, seed0: int = 17):
         cnt = (C.c_uint64 * 4)()
         iters = lib().kmo_run(C.c_void_p(self.code._h), C.c_void_p(self.modem._h), C.byref(self.opts),

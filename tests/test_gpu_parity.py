@@ -440,3 +440,35 @@ def test_multi_gpu_sweep_counters_identical(tmp_path, kb):
         cfg.write_text(base + f"\n[gpu]\nseed = 17\ngpus = {g}\nbatch = 2048\n")
         out[g] = kb.Simulator(str(cfg), data_dir=util.ko.CONFIG_DIR).simulate(echo=False)[3]
     assert np.array_equal(out[1], out[G]) and out[1][0, 0] == 20000
+
+
+@pytest.mark.parametrize("name,frames", [("peg2304_4psk_6db", 12000), ("peg2304_16qam_gray_12db", 8000),
+                                         ("peg2304_qpsk_10db", 6000), ("5g_16qam_gray_10db", 3000)])
+def test_parity_statistics_at_scale(name, frames, kb):
+    """north_star's acceptance numbers on thousands of reference frames (oracle ≡ reference bit for bit, run on all host
+    cores): centroids within 1e-4 relative, rotation choice / decoder return value / frame-error flag identical,
+    hard decisions bit-identical on >= 99.99 % of the frames the reference converges on."""
+    olink = util.oracle_link(name)
+    snr = util.CASES[name][2]
+    ref = olink.bulk(snr, frames)
+    link = util.gpu_link(name, max_batch=4096)
+    uu_p, hhat, kstar, ret = link.receive(ref["y"], 10 ** (-0.1 * snr))
+    uu = kb.unpack_bits(uu_p, olink.code.K)
+    rel = np.abs(hhat.astype(np.complex128) - ref["hhat"]) / np.abs(ref["hhat"])
+    k_same = kstar == ref["kstar"]
+    ret_same = ret == ref["ret"]
+    bits_same = (uu == ref["uu_hat"]).all(axis=1)
+    conv = ref["converged"].astype(bool)
+    fe = (uu != ref["u"]).any(axis=1)
+    ref_fe = ref["nerr"] > 0
+    stats = dict(frames=frames, hhat_rel_p999=float(np.quantile(rel, 0.999)), hhat_rel_max=float(rel.max()),
+                 kstar_same=float(k_same.mean()), ret_same=float(ret_same.mean()), converged=int(conv.sum()),
+                 converged_bits_same=float(bits_same[conv].mean()), frame_error_same=float((fe == ref_fe).mean()),
+                 fer_gpu=float(fe.mean()), fer_ref=float(ref_fe.mean()))
+    print(name, stats)
+    assert stats["hhat_rel_p999"] <= 1e-4 and stats["hhat_rel_max"] <= 2e-2, stats
+    assert stats["kstar_same"] >= 0.999, stats          # syndrome weights within 1 of each other can swap the argmin
+    assert stats["ret_same"] >= 0.998, stats
+    assert stats["converged_bits_same"] >= 0.9999, stats
+    assert stats["frame_error_same"] >= 0.999, stats
+    link.close()

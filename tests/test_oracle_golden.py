@@ -113,3 +113,17 @@ def test_pinned_quirks():
     assert p2["fer"] < 0.35
     _, pm5 = load("peg2304_qpsk_m5db")
     assert pm5["fer"] == 1.0
+
+
+def test_bulk_frames_are_thread_invariant_and_equal_single_frames():
+    link = ko.Link("PEG2304regular0.5.txt", "2bits_4PSK.txt")
+    a = link.bulk(6.0, 12, threads=1)
+    b = link.bulk(6.0, 12, threads=5)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # frame 3 of the bulk run = a single kmo_frame from that frame's LCG state
+    g = ko.Lcg((17 + 1000003 * 3) % (2147483647 - 1) + 1)
+    r = link.frame(g, 6.0)
+    assert np.array_equal(r.y, a["y"][3]) and r.ret == a["ret"][3] and r.kstar == a["kstar"][3]
+    assert np.array_equal(r.uu_hat.astype(np.uint8), a["uu_hat"][3]) and r.nerr == a["nerr"][3]
+    assert a["converged"][3] == (link.code.parity_check(r.cc_hat) == 0)
