@@ -240,7 +240,15 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
                                c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
+    // hard metric: the four ratio vectors stay in shared memory, only the winner's reaches HBM (if one frame's fit)
+    d.winner_only = (!decode_metric && 16 * (size_t)c->n_tx + c->n_tx + 64 * (size_t)c->Q < 200 * 1024) ? 1 : 0;
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+    if (d.winner_only) {
+      DecParams p = dec_params(c, l, B, l.lr.p, nullptr, 1, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
+      return KML_OK;
+    }
     if (decode_metric) {  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
       float *soft = c->opts.metric_type ? l.soft.p : nullptr;
       if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * B, s));

@@ -72,6 +72,8 @@ cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *point
 struct DemapParams {
   int B, n_sym, n_tx, bits_per_symbol, q, n_cand;  // n_cand = 4 (blind) or 1
   int hard_metric;                                 // compute syndrome weights of the inverted hard decisions
+  int winner_only;                                 // (hard_metric, 4 candidates) keep the ratios in shared memory and
+                                                   // write only the chosen candidate's: lr is then [B][n_tx]
   int m_rows, punct;
   const float2 *y;       // [B][n_sym]
   const float2 *h;       // [B] channel estimate (hhat or true h)

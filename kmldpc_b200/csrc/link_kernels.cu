@@ -399,37 +399,42 @@ __global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, cons
 // KmCodec::GetMetrics/Metric/GetParityCheck (kmcodec.cc:105-163), hard non-5G metric: rr = (P0 > 0.5) ? 1 : 0
 // (inverted on purpose), metric = number of unsatisfied rows; first argmin (kmcodec.cc:61-65).
 constexpr int DM_THREADS = 256;
+// One CTA per frame.  Each symbol is read once and demapped against all candidates; the inverted hard decisions of the
+// candidates share one byte per variable (bit c = candidate c), so ONE pass over the Tanner graph yields the four
+// syndrome weights.  With `winner_only` the four ratio vectors stay in shared memory and only the chosen candidate's
+// goes to HBM (4x less write traffic, and the decoder needs no per-frame indirection).
 template <int BITS>
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
   constexpr int Q = 1 << BITS;
   extern __shared__ unsigned char dsm[];
-  float2 *s_pts = reinterpret_cast<float2 *>(dsm);          // [Q] s_k * h_cand
-  unsigned char *s_rr = dsm + sizeof(float2) * Q;           // [n_tx + punct] inverted hard decisions
-  __shared__ int s_cnt[4];
+  float2 *s_pts = reinterpret_cast<float2 *>(dsm);                        // [n_cand][Q] s_k * h_cand
+  float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * Q * 4);   // [n_cand][n_tx]   (winner_only)
+  unsigned char *s_rr = dsm + sizeof(float2) * Q * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0);
+  __shared__ int s_cnt[4], s_best;
   const int tid = threadIdx.x;
   for (int f = blockIdx.x; f < d.B; f += gridDim.x) {
     const float2 hb = d.h[f];
     const float2 *yf = d.y + (size_t)f * d.n_sym;
     if (tid < 4) s_cnt[tid] = 0;
-    for (int c = 0; c < d.n_cand; c++) {
-      const float2 r = d.rot[c];
+    for (int i = tid; i < d.n_cand * Q; i += DM_THREADS) {
+      const float2 r = d.rot[i / Q], s = __ldg(d.points + (i % Q));
       const float2 hc = make_float2(hb.x * r.x - hb.y * r.y, hb.x * r.y + hb.y * r.x);
-      __syncthreads();  // previous candidate's syndrome pass is done with s_rr / s_pts
-      for (int k = tid; k < Q; k += DM_THREADS) {
-        const float2 s = __ldg(d.points + k);
-        s_pts[k] = make_float2(s.x * hc.x - s.y * hc.y, s.x * hc.y + s.y * hc.x);
-      }
-      if (d.hard_metric)
-        for (int i = tid; i < d.punct; i += DM_THREADS) s_rr[i] = 0;
-      __syncthreads();
-      float *lr_out = d.lr + ((size_t)f * d.n_cand + c) * d.n_tx;
-      for (int i = tid; i < d.n_sym; i += DM_THREADS) {
-        const float2 yy = yf[i];
+      s_pts[i] = make_float2(s.x * hc.x - s.y * hc.y, s.x * hc.y + s.y * hc.x);
+    }
+    if (d.hard_metric)
+      for (int i = tid; i < d.punct; i += DM_THREADS) s_rr[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < d.n_sym; i += DM_THREADS) {
+      const float2 yy = yf[i];
+      unsigned int rr[BITS];
+#pragma unroll
+      for (int j = 0; j < BITS; j++) rr[j] = 0;
+      for (int c = 0; c < d.n_cand; c++) {
         float p[Q];
         float mx = -3.0e38f;
 #pragma unroll
         for (int k = 0; k < Q; k++) {
-          const float2 s = s_pts[k];
+          const float2 s = s_pts[c * Q + k];
           const float dx = s.x - yy.x, dy = s.y - yy.y;
           p[k] = -(dx * dx + dy * dy) * d.inv_var;
           mx = fmaxf(mx, p[k]);
@@ -440,14 +445,11 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
           p[k] = __expf(p[k] - mx);
           sum += p[k];
         }
-        const float inv = 1.0f / sum;
-        float sum2 = 0.f;
+        const float inv = __fdividef(1.0f, sum);
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-          p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
-          sum2 += p[k];
-        }
-        (void)sum2;  // the second normalisation (modem.cc:47-57) cancels in the ratio z0 / z1
+        for (int k = 0; k < Q; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
+        // (the second normalisation, modem.cc:47-57, cancels in the ratio z0 / z1)
+        float *lr_out = d.winner_only ? s_lr + (size_t)c * d.n_tx : d.lr + ((size_t)f * d.n_cand + c) * d.n_tx;
 #pragma unroll
         for (int j = 0; j < BITS; j++) {
           float z0 = 0.f, z1 = 0.f;
@@ -456,33 +458,47 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
             if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
             else z1 += p[k];
           }
-          const float ratio = fminf(fmaxf(z0 / z1, kLrMin), kLrMax);
-          lr_out[i * BITS + j] = ratio;
-          if (d.hard_metric) s_rr[d.punct + i * BITS + j] = z0 > z1 ? 1 : 0;
+          lr_out[i * BITS + j] = fminf(fmaxf(__fdividef(z0, z1), kLrMin), kLrMax);
+          rr[j] |= (z0 > z1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
         }
       }
       if (d.hard_metric) {
-        __syncthreads();
-        int bad = 0;
-        for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
-          int par = 0;
-          for (int e = __ldg(d.row_ptr + rrow); e < __ldg(d.row_ptr + rrow + 1); e++) par ^= s_rr[__ldg(d.col_idx + e)];
-          bad += par;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
-        if ((tid & 31) == 0 && bad) atomicAdd(&s_cnt[c], bad);
+        for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
       }
     }
-    __syncthreads();
-    if (d.hard_metric && tid == 0) {
-      int best = 0;
-      for (int c = 0; c < d.n_cand; c++) {
-        d.metric[(size_t)f * 4 + c] = (float)s_cnt[c];
-        if (s_cnt[c] < s_cnt[best]) best = c;
+    if (d.hard_metric) {
+      __syncthreads();
+      int bad[4] = {0, 0, 0, 0};
+      for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
+        unsigned int par = 0;
+        for (int e = __ldg(d.row_ptr + rrow); e < __ldg(d.row_ptr + rrow + 1); e++) par ^= s_rr[__ldg(d.col_idx + e)];
+#pragma unroll
+        for (int c = 0; c < 4; c++) bad[c] += (par >> c) & 1u;
       }
-      for (int c = d.n_cand; c < 4; c++) d.metric[(size_t)f * 4 + c] = 0.f;
-      d.kstar[f] = best;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) bad[c] += __shfl_xor_sync(0xffffffffu, bad[c], o);
+        if ((tid & 31) == 0 && bad[c]) atomicAdd(&s_cnt[c], bad[c]);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int best = 0;
+        for (int c = 0; c < d.n_cand; c++) {
+          d.metric[(size_t)f * 4 + c] = (float)s_cnt[c];
+          if (s_cnt[c] < s_cnt[best]) best = c;  // std::min_element: first minimum (kmcodec.cc:61-65)
+        }
+        for (int c = d.n_cand; c < 4; c++) d.metric[(size_t)f * 4 + c] = 0.f;
+        d.kstar[f] = best;
+        s_best = best;
+      }
+      if (d.winner_only) {
+        __syncthreads();
+        const float *w = s_lr + (size_t)s_best * d.n_tx;
+        float *out = d.lr + (size_t)f * d.n_tx;
+        for (int i = tid; i < d.n_tx; i += DM_THREADS) out[i] = w[i];
+      }
     }
     __syncthreads();
   }
@@ -665,7 +681,19 @@ cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *point
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s) {
   const int grid = d.B < num_sms * 8 ? d.B : num_sms * 8;
   if (grid < 1) return cudaSuccess;
-  const int smem = (int)sizeof(float2) * d.q + d.n_tx + d.punct + 16;
+  const int smem = (int)sizeof(float2) * d.q * 4 + (d.winner_only ? (int)sizeof(float) * 4 * d.n_tx : 0) + d.n_tx + d.punct + 16;
+  if (smem > 48 * 1024 && d.bits_per_symbol >= 1 && d.bits_per_symbol <= 6) {  // per device: set on every large launch
+    cudaError_t e = cudaSuccess;
+    switch (d.bits_per_symbol) {
+      case 1: e = cudaFuncSetAttribute(demap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+      case 2: e = cudaFuncSetAttribute(demap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+      case 3: e = cudaFuncSetAttribute(demap_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+      case 4: e = cudaFuncSetAttribute(demap_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+      case 5: e = cudaFuncSetAttribute(demap_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+      case 6: e = cudaFuncSetAttribute(demap_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
+    }
+    if (e != cudaSuccess) return e;
+  }
   switch (d.bits_per_symbol) {
     case 1: demap_kernel<1><<<grid, DM_THREADS, smem, s>>>(d); break;
     case 2: demap_kernel<2><<<grid, DM_THREADS, smem, s>>>(d); break;
