@@ -305,14 +305,32 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 
 // 2 FMA + 1 compare per neighbour instead of a full distance per constellation point.  Every lane carries the same fp64
 // cumulative sums (xor-shuffle reductions give all lanes the same value), so no broadcast is needed.
 constexpr int KMW_WARPS = 4;
+// Blackwell packed fp32 (SASS FMUL2 / FFMA2): two neighbour half-plane tests per instruction
+__device__ __forceinline__ float2 km_mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 km_fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 template <int SPL, int MAXNB>
-__global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, const float2 *y, int n, const float2 *points,
-                                                                     const int *nb, int n_nb, int iters,
-                                                                     float2 *hhat_out, int32_t *passes_out) {
+__global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 24 ? 6 : (SPL <= 36 ? 5 : (SPL <= 48 ? 4 : 3)))
+kmeans_warp_kernel(int B, const float2 *y, int n, const float2 *points, const int *nb, int n_nb, int iters,
+                   float2 *hhat_out, int32_t *passes_out) {
+  static_assert(MAXNB % 2 == 0, "neighbours are tested in pairs");
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
   const float2 s0f = __ldg(points);
-  const double s0r = (double)s0f.x, s0i = (double)s0f.y, s0n = s0r * s0r + s0i * s0i;
+  // 1 / s_0 = conj(s_0) / |s_0|^2, so that hhat = (cluster-0 mean) / s_0 is one complex multiply
+  const double s0n = (double)s0f.x * s0f.x + (double)s0f.y * s0f.y;
+  const float is0r = (float)((double)s0f.x / s0n), is0i = (float)(-(double)s0f.y / s0n);
   float2 snb[MAXNB];
 #pragma unroll
   for (int t = 0; t < MAXNB; t++) snb[t] = t < n_nb ? __ldg(points + __ldg(nb + t)) : s0f;
@@ -320,6 +338,7 @@ __global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, cons
     const float2 *yf = y + (size_t)f * n;
     float2 ys[SPL];
     unsigned long long best = 0ull;
+    const float qnan = __int_as_float(0x7fc00000);
 #pragma unroll
     for (int j = 0; j < SPL; j++) {
       const int i = j * 32 + lane;
@@ -329,7 +348,7 @@ __global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, cons
         const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
         best = key > best ? key : best;
       } else {
-        ys[j] = make_float2(0.f, 0.f);
+        ys[j] = make_float2(qnan, qnan);  // fails every half-plane test → never counted
       }
     }
 #pragma unroll
@@ -338,30 +357,33 @@ __global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, cons
       best = other > best ? other : best;
     }
     const float2 ya = yf[0x7fffffff - (int)(uint32_t)(best & 0xffffffffu)];
-    double hr = ((double)ya.x * s0r + (double)ya.y * s0i) / s0n;  // y_a / s_0
-    double hi = ((double)ya.y * s0r - (double)ya.x * s0i) / s0n;
-    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0, prev_r = 0.0, prev_i = 0.0;
+    float hr = ya.x * is0r - ya.y * is0i, hi = ya.x * is0i + ya.y * is0r;  // y_a / s_0
+    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0;  // cumulative over passes (never reset: kmeans.cc:33-34 as compiled)
+    float prev_r = 0.f, prev_i = 0.f;
     bool have_prev = false;
     int passes = 0;
     for (int it = 0; it < iters; it++) {
       passes++;
-      const float fhr = (float)hr, fhi = (float)hi;
-      const float2 c0 = make_float2(s0f.x * fhr - s0f.y * fhi, s0f.x * fhi + s0f.y * fhr);
+      const float2 c0 = make_float2(s0f.x * hr - s0f.y * hi, s0f.x * hi + s0f.y * hr);
       const float n0 = c0.x * c0.x + c0.y * c0.y;
-      float ax[MAXNB], ay[MAXNB], th[MAXNB];
+      float2 ax[MAXNB / 2], ay[MAXNB / 2], th[MAXNB / 2];
 #pragma unroll
       for (int t = 0; t < MAXNB; t++) {
-        const float2 ck = make_float2(snb[t].x * fhr - snb[t].y * fhi, snb[t].x * fhi + snb[t].y * fhr);
-        ax[t] = ck.x - c0.x;
-        ay[t] = ck.y - c0.y;
-        th[t] = t < n_nb ? 0.5f * (ck.x * ck.x + ck.y * ck.y - n0) : 3.0e38f;
+        const float2 ck = make_float2(snb[t].x * hr - snb[t].y * hi, snb[t].x * hi + snb[t].y * hr);
+        const float axx = ck.x - c0.x, ayy = ck.y - c0.y;
+        const float thh = t < n_nb ? 0.5f * (ck.x * ck.x + ck.y * ck.y - n0) : 3.0e38f;
+        if (t & 1) { ax[t / 2].y = axx; ay[t / 2].y = ayy; th[t / 2].y = thh; }
+        else { ax[t / 2].x = axx; ay[t / 2].x = ayy; th[t / 2].x = thh; }
       }
       float cnt = 0.f, sr = 0.f, si = 0.f;
 #pragma unroll
       for (int j = 0; j < SPL; j++) {
-        bool in0 = (j * 32 + lane) < n;
+        bool in0 = true;
 #pragma unroll
-        for (int t = 0; t < MAXNB; t++) in0 = in0 && (fmaf(ax[t], ys[j].x, ay[t] * ys[j].y) <= th[t]);
+        for (int t = 0; t < MAXNB / 2; t++) {
+          const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_mul2(ay[t], make_float2(ys[j].y, ys[j].y)));
+          in0 = in0 && (v.x <= th[t].x) && (v.y <= th[t].y);
+        }
         if (in0) {
           cnt += 1.f;
           sr += ys[j].x;
@@ -381,12 +403,13 @@ __global__ void __launch_bounds__(KMW_WARPS * 32) kmeans_warp_kernel(int B, cons
       prev_r = hr;
       prev_i = hi;
       have_prev = true;
-      const double mr = cum_re / cum_cnt, mi = cum_im / cum_cnt;
-      hr = (mr * s0r + mi * s0i) / s0n;
-      hi = (mi * s0r - mr * s0i) / s0n;
+      const float inv = __fdividef(1.0f, (float)cum_cnt);  // cluster 0 is never empty: the anchor sample sits on c_0
+      const float mr = (float)cum_re * inv, mi = (float)cum_im * inv;
+      hr = mr * is0r - mi * is0i;
+      hi = mr * is0i + mi * is0r;
     }
     if (lane == 0) {
-      hhat_out[f] = make_float2((float)hr, (float)hi);
+      hhat_out[f] = make_float2(hr, hi);
       if (passes_out) passes_out[f] = passes;
     }
   }
