@@ -56,7 +56,8 @@ struct kml_ctx {
   DevBuf<float2> points;
   DevBuf<int32_t> row_ptr, col_idx, km_nb;
   int km_n_nb = 0;
-  DevBuf<uint16_t> vn_addr;
+  DevBuf<uint16_t> vn_addr, col_ell;
+  int ell_width = 0;
   DevBuf<uint8_t> vn_deg, cn_deg;
   DecTables dt{};
   DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
@@ -228,7 +229,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
   d.B = B; d.n_sym = c->n_sym; d.n_tx = c->n_tx; d.bits_per_symbol = c->bits; d.q = c->Q;
   d.m_rows = c->M; d.punct = c->punct; d.y = y; d.inv_var = (float)(1.0 / var);
   for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
-  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p;
+  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p; d.col_ell = c->col_ell.p; d.ell_width = c->ell_width;
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   const int32_t *sel = nullptr;
   int n_cand = 1;
@@ -240,8 +241,9 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
                                c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
-    // hard metric: the four ratio vectors stay in shared memory, only the winner's reaches HBM (if one frame's fit)
-    d.winner_only = (!decode_metric && 16 * (size_t)c->n_tx + c->n_tx + 64 * (size_t)c->Q < 200 * 1024) ? 1 : 0;
+    // hard metric: the four ratio vectors stay in shared memory and only the winner's reaches HBM — as long as that
+    // leaves room for >= 4 CTAs per SM (PEG2304: 39 KB); long frames (PEG8064: 137 KB) write all four instead
+    d.winner_only = (!decode_metric && 16 * (size_t)c->n_tx + c->n_tx + 64 * (size_t)c->Q <= 56 * 1024) ? 1 : 0;
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
     if (d.winner_only) {
       DecParams p = dec_params(c, l, B, l.lr.p, nullptr, 1, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
@@ -356,6 +358,16 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     KML_CUDA(c, cudaMemcpy(c->row_ptr.p, code->row_ptr, sizeof(int32_t) * (c->M + 1), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->col_idx.alloc(c->E));
     KML_CUDA(c, cudaMemcpy(c->col_idx.p, code->col_idx, sizeof(int32_t) * c->E, cudaMemcpyHostToDevice));
+    {  // ELL copy of the graph for the demapper's syndrome pass: [max row degree][M] uint16, padding → an always-zero byte
+      int w = 0;
+      for (int r = 0; r < c->M; r++) w = std::max(w, code->row_ptr[r + 1] - code->row_ptr[r]);
+      std::vector<uint16_t> ell((size_t)w * c->M, (uint16_t)(c->N));
+      for (int r = 0; r < c->M; r++)
+        for (int e = code->row_ptr[r], k = 0; e < code->row_ptr[r + 1]; e++, k++) ell[(size_t)k * c->M + r] = (uint16_t)code->col_idx[e];
+      c->ell_width = w;
+      KML_CUDA(c, c->col_ell.alloc(ell.size()));
+      KML_CUDA(c, cudaMemcpy(c->col_ell.p, ell.data(), ell.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
     KML_CUDA(c, c->counters.alloc(5));
     KML_CUDA(c, cudaMemset(c->counters.p, 0, 5 * sizeof(unsigned long long)));
     KML_CUDA(c, cudaMallocHost(&c->h_counters, 5 * sizeof(unsigned long long)));
@@ -377,7 +389,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
   c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
-  c->vn_addr.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  c->vn_addr.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }
@@ -529,7 +541,7 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   d.hard_metric = hard_metric; d.m_rows = c->M; d.punct = c->punct; d.y = l.y.p; d.h = l.hhat.p;
   d.inv_var = (float)(1.0 / var);
   for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
-  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p;
+  d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p; d.col_ell = c->col_ell.p; d.ell_width = c->ell_width;
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   return d;
 }

@@ -80,7 +80,9 @@ struct DemapParams {
   float inv_var;
   float2 rot[4];         // exp(j (kPi/2) k)
   const float2 *points;  // [q]
-  const int32_t *row_ptr, *col_idx;  // permuted graph (for the hard metric)
+  const int32_t *row_ptr, *col_idx;  // permuted graph
+  const uint16_t *col_ell;           // [ell_width][m_rows] graph columns per row (hard metric), padded with n_tx + punct
+  int ell_width;
   float *lr;             // [B][n_cand][n_tx] likelihood ratios P0/P1 in [1e-12, 1e12]
   float *metric;         // [B][4] (hard metric only)
   int32_t *kstar;        // [B]     (hard metric only; else untouched)

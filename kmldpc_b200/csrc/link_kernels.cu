@@ -426,65 +426,112 @@ constexpr int DM_THREADS = 256;
 // candidates share one byte per variable (bit c = candidate c), so ONE pass over the Tanner graph yields the four
 // syndrome weights.  With `winner_only` the four ratio vectors stay in shared memory and only the chosen candidate's
 // goes to HBM (4x less write traffic, and the decoder needs no per-frame indirection).
-template <int BITS>
+__device__ __forceinline__ float dm_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float dm_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// One symbol against NC candidates: per-point softmax with the reference's clip, bit marginals, ratio P0/P1; returns in
+// rr[j] the candidates' inverted hard decisions of bit j (bit c = candidate c).  lr_base already points at element
+// i * BITS of candidate 0; consecutive candidates are lr_stride floats apart.
+template <int BITS, int NC>
+__device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pts, float scale, float *lr_base,
+                                             size_t lr_stride, unsigned int (&rr)[BITS]) {
+  constexpr int Q = 1 << BITS;
+#pragma unroll
+  for (int j = 0; j < BITS; j++) rr[j] = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    float p[Q];
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+      const float2 s = s_pts[c * Q + k];
+      const float dx = s.x - yy.x, dy = s.y - yy.y;
+      p[k] = -(dx * dx + dy * dy) * scale;
+      mx = fmaxf(mx, p[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+      p[k] = dm_ex2(p[k] - mx);
+      sum += p[k];
+    }
+    const float inv = dm_rcp(sum);
+#pragma unroll
+    for (int k = 0; k < Q; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
+    // (the second normalisation, modem.cc:47-57, cancels in the ratio z0 / z1)
+#pragma unroll
+    for (int j = 0; j < BITS; j++) {
+      float z0 = 0.f, z1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < Q; k++) {
+        if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
+        else z1 += p[k];
+      }
+      lr_base[c * lr_stride + j] = fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax);
+      rr[j] |= (z0 > z1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
+    }
+  }
+}
+
+template <int BITS, int NC>
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
   constexpr int Q = 1 << BITS;
+  constexpr int MAXS = 6;  // symbols a thread keeps in flight (n_sym <= MAXS * DM_THREADS on the fast path)
   extern __shared__ unsigned char dsm[];
-  float2 *s_pts = reinterpret_cast<float2 *>(dsm);                        // [n_cand][Q] s_k * h_cand
-  float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * Q * 4);   // [n_cand][n_tx]   (winner_only)
+  float2 *s_pts = reinterpret_cast<float2 *>(dsm);                        // [NC][Q] s_k * h_cand
+  float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * Q * 4);   // [NC][n_tx]   (winner_only)
   unsigned char *s_rr = dsm + sizeof(float2) * Q * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0);
   __shared__ int s_cnt[4], s_best;
   const int tid = threadIdx.x;
+  const float scale = d.inv_var * 1.4426950408889634f;  // exp(-x / var) = 2^(-x log2(e) / var)
+  const int zero_slot = d.punct + d.n_tx;               // a byte that is always 0 (padding of the ELL column table)
+  const size_t lr_stride = (size_t)d.n_tx;
   for (int f = blockIdx.x; f < d.B; f += gridDim.x) {
     const float2 hb = d.h[f];
     const float2 *yf = d.y + (size_t)f * d.n_sym;
+    float2 yreg[MAXS];
+#pragma unroll
+    for (int u = 0; u < MAXS; u++) {  // all of this thread's symbols are in flight before the first one is used
+      const int i = u * DM_THREADS + tid;
+      yreg[u] = i < d.n_sym ? yf[i] : make_float2(0.f, 0.f);
+    }
     if (tid < 4) s_cnt[tid] = 0;
-    for (int i = tid; i < d.n_cand * Q; i += DM_THREADS) {
-      const float2 r = d.rot[i / Q], s = __ldg(d.points + (i % Q));
+    for (int i = tid; i < NC * Q; i += DM_THREADS) {
+      const int c = i / Q;
+      const float2 r = c == 0 ? d.rot[0] : (c == 1 ? d.rot[1] : (c == 2 ? d.rot[2] : d.rot[3]));
+      const float2 s = __ldg(d.points + (i % Q));
       const float2 hc = make_float2(hb.x * r.x - hb.y * r.y, hb.x * r.y + hb.y * r.x);
       s_pts[i] = make_float2(s.x * hc.x - s.y * hc.y, s.x * hc.y + s.y * hc.x);
     }
-    if (d.hard_metric)
+    if (d.hard_metric) {
       for (int i = tid; i < d.punct; i += DM_THREADS) s_rr[i] = 0;
+      if (tid == 0) s_rr[zero_slot] = 0;
+    }
     __syncthreads();
-    for (int i = tid; i < d.n_sym; i += DM_THREADS) {
-      const float2 yy = yf[i];
-      unsigned int rr[BITS];
+    float *lr0 = d.winner_only ? s_lr : d.lr + (size_t)f * NC * d.n_tx;
 #pragma unroll
-      for (int j = 0; j < BITS; j++) rr[j] = 0;
-      for (int c = 0; c < d.n_cand; c++) {
-        float p[Q];
-        float mx = -3.0e38f;
+    for (int u = 0; u < MAXS; u++) {
+      const int i = u * DM_THREADS + tid;
+      if (i < d.n_sym) {
+        unsigned int rr[BITS];
+        demap_symbol<BITS, NC>(yreg[u], s_pts, scale, lr0 + i * BITS, lr_stride, rr);
+        if (d.hard_metric) {
 #pragma unroll
-        for (int k = 0; k < Q; k++) {
-          const float2 s = s_pts[c * Q + k];
-          const float dx = s.x - yy.x, dy = s.y - yy.y;
-          p[k] = -(dx * dx + dy * dy) * d.inv_var;
-          mx = fmaxf(mx, p[k]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < Q; k++) {
-          p[k] = __expf(p[k] - mx);
-          sum += p[k];
-        }
-        const float inv = __fdividef(1.0f, sum);
-#pragma unroll
-        for (int k = 0; k < Q; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
-        // (the second normalisation, modem.cc:47-57, cancels in the ratio z0 / z1)
-        float *lr_out = d.winner_only ? s_lr + (size_t)c * d.n_tx : d.lr + ((size_t)f * d.n_cand + c) * d.n_tx;
-#pragma unroll
-        for (int j = 0; j < BITS; j++) {
-          float z0 = 0.f, z1 = 0.f;
-#pragma unroll
-          for (int k = 0; k < Q; k++) {
-            if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
-            else z1 += p[k];
-          }
-          lr_out[i * BITS + j] = fminf(fmaxf(__fdividef(z0, z1), kLrMin), kLrMax);
-          rr[j] |= (z0 > z1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
+          for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
         }
       }
+    }
+    for (int i = MAXS * DM_THREADS + tid; i < d.n_sym; i += DM_THREADS) {  // very long frames
+      unsigned int rr[BITS];
+      demap_symbol<BITS, NC>(yf[i], s_pts, scale, lr0 + i * BITS, lr_stride, rr);
       if (d.hard_metric) {
 #pragma unroll
         for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -495,7 +542,8 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
       int bad[4] = {0, 0, 0, 0};
       for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
         unsigned int par = 0;
-        for (int e = __ldg(d.row_ptr + rrow); e < __ldg(d.row_ptr + rrow + 1); e++) par ^= s_rr[__ldg(d.col_idx + e)];
+        for (int k = 0; k < d.ell_width; k++)  // ELL table, transposed: consecutive rows read consecutive 16-bit words
+          par ^= s_rr[__ldg(d.col_ell + (size_t)k * d.m_rows + rrow)];
 #pragma unroll
         for (int c = 0; c < 4; c++) bad[c] += (par >> c) & 1u;
       }
@@ -508,11 +556,11 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
       __syncthreads();
       if (tid == 0) {
         int best = 0;
-        for (int c = 0; c < d.n_cand; c++) {
+        for (int c = 0; c < NC; c++) {
           d.metric[(size_t)f * 4 + c] = (float)s_cnt[c];
           if (s_cnt[c] < s_cnt[best]) best = c;  // std::min_element: first minimum (kmcodec.cc:61-65)
         }
-        for (int c = d.n_cand; c < 4; c++) d.metric[(size_t)f * 4 + c] = 0.f;
+        for (int c = NC; c < 4; c++) d.metric[(size_t)f * 4 + c] = 0.f;
         d.kstar[f] = best;
         s_best = best;
       }
@@ -701,32 +749,35 @@ cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *point
   return cudaGetLastError();
 }
 
+template <int BITS>
+static cudaError_t launch_demap_bits(const DemapParams &d, int grid, int smem, cudaStream_t s) {
+  if (d.n_cand == 4) {
+    if (smem > 48 * 1024) {  // per device: set on every large launch
+      cudaError_t e = cudaFuncSetAttribute(demap_kernel<BITS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+    }
+    demap_kernel<BITS, 4><<<grid, DM_THREADS, smem, s>>>(d);
+  } else if (d.n_cand == 1) {
+    demap_kernel<BITS, 1><<<grid, DM_THREADS, smem, s>>>(d);
+  } else {
+    return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s) {
   const int grid = d.B < num_sms * 8 ? d.B : num_sms * 8;
   if (grid < 1) return cudaSuccess;
-  const int smem = (int)sizeof(float2) * d.q * 4 + (d.winner_only ? (int)sizeof(float) * 4 * d.n_tx : 0) + d.n_tx + d.punct + 16;
-  if (smem > 48 * 1024 && d.bits_per_symbol >= 1 && d.bits_per_symbol <= 6) {  // per device: set on every large launch
-    cudaError_t e = cudaSuccess;
-    switch (d.bits_per_symbol) {
-      case 1: e = cudaFuncSetAttribute(demap_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-      case 2: e = cudaFuncSetAttribute(demap_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-      case 3: e = cudaFuncSetAttribute(demap_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-      case 4: e = cudaFuncSetAttribute(demap_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-      case 5: e = cudaFuncSetAttribute(demap_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-      case 6: e = cudaFuncSetAttribute(demap_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); break;
-    }
-    if (e != cudaSuccess) return e;
-  }
+  const int smem = (int)sizeof(float2) * d.q * 4 + (d.winner_only ? (int)sizeof(float) * 4 * d.n_tx : 0) + d.n_tx + d.punct + 32;
   switch (d.bits_per_symbol) {
-    case 1: demap_kernel<1><<<grid, DM_THREADS, smem, s>>>(d); break;
-    case 2: demap_kernel<2><<<grid, DM_THREADS, smem, s>>>(d); break;
-    case 3: demap_kernel<3><<<grid, DM_THREADS, smem, s>>>(d); break;
-    case 4: demap_kernel<4><<<grid, DM_THREADS, smem, s>>>(d); break;
-    case 5: demap_kernel<5><<<grid, DM_THREADS, smem, s>>>(d); break;
-    case 6: demap_kernel<6><<<grid, DM_THREADS, smem, s>>>(d); break;
+    case 1: return launch_demap_bits<1>(d, grid, smem, s);
+    case 2: return launch_demap_bits<2>(d, grid, smem, s);
+    case 3: return launch_demap_bits<3>(d, grid, smem, s);
+    case 4: return launch_demap_bits<4>(d, grid, smem, s);
+    case 5: return launch_demap_bits<5>(d, grid, smem, s);
+    case 6: return launch_demap_bits<6>(d, grid, smem, s);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
