@@ -226,7 +226,23 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
   o.max_iter = cfg->max_iter; o.known_h = cfg->known_h; o.metric_type = cfg->metric_type; o.metric_iter = cfg->metric_iter;
   o.kmeans_iter = 20; o.early_exit = cfg->early_exit; o.max_batch = cfg->max_batch; o.algorithm = cfg->algorithm;
   std::vector<kml_ctx *> ctx(G, nullptr);
-  for (int g = 0; g < G && rc == KML_OK; g++) rc = kml_create(&ctx[g], g, code, modem, &o);
+  {  // device 0 first (it runs the layout annealing, which the others then take from the cache), the rest in parallel
+    rc = kml_create(&ctx[0], 0, code, modem, &o);
+    std::vector<int> rcs(G, KML_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (int g = 1; g < G && rc == KML_OK; g++)
+      th.emplace_back([&, g] {
+        rcs[g] = kml_create(&ctx[g], g, code, modem, &o);
+        if (rcs[g] != KML_OK) errs[g] = kml_last_error(nullptr);  // thread-local message: carry it over
+      });
+    for (auto &t : th) t.join();
+    for (int g = 1; g < G && rc == KML_OK; g++)
+      if (rcs[g] != KML_OK) {
+        rc = rcs[g];
+        set_global_error(errs[g]);
+      }
+  }
   if (rc == KML_OK) {
     int32_t info[8];
     kml_info(ctx[0], info);
