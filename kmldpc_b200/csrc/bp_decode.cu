@@ -10,9 +10,10 @@
 //     per-step renormalisation, which cancels in the ratio).
 //   * variable→check message: (hard bit h, small probability s <= 0.5): P(bit = h) = 1 - s.  s is computed directly
 //     as min(x,1)/(1+x), so probabilities as small as 1e-36 keep full relative precision — the fp32 analogue of the
-//     reference carrying both members of the pair in fp64.  A word packs s (bit 30 of any float < 2 is 0), the
-//     extrinsic hard bit (bit 31) and the POSTERIOR hard decision of the variable (bit 30), so the check phase can
-//     evaluate the syndrome of the current decisions without a second gather.
+//     reference carrying both members of the pair in fp64.  A word packs s, the extrinsic hard bit in the SIGN bit
+//     (so the check node reads s as |word| — a free operand modifier on FFMA2/FFMA/FMNMX) and the POSTERIOR hard
+//     decision of the variable in the mantissa LSB (a 1-ulp perturbation of s), so the check phase can evaluate the
+//     syndrome of the current decisions without a second gather.
 //   * check node: the reference's 2-state trellis is, in this representation, s_ab = s_a + s_b - 2 s_a s_b on the small
 //     probabilities (all terms positive → no cancellation) and XOR on the hard bits; forward/backward partial
 //     combinations give every extrinsic output in 3(d-2) combines.
@@ -47,20 +48,37 @@ __device__ __forceinline__ float sp_chain(float acc, float s, float t) { return 
 
 // v2c word: s = min(P0, P1) = min(ext, 1) / (1 + ext); bit 31 = extrinsic hard decision (P1 > P0, i.e. ext < 1), taken
 // from the sign of (ext - 1) — one FADD on the FMA pipe instead of FSETP + SEL on the (binding) ALU pipe; `pb` = the
-// variable's posterior decision already shifted to bit 30.
+// variable's posterior decision (0 / 1), which replaces the mantissa LSB of s.  Two LOP3.
+// (inline PTX pins the association: left to itself ptxas emits three LOP3)
+__device__ __forceinline__ uint32_t v2c_pack(float sgn, float s, uint32_t pb) {
+  uint32_t w;
+  asm("{.reg .b32 t; lop3.b32 t, %1, 0x80000000, %3, 0xEA; lop3.b32 %0, %2, 0xfffffffe, t, 0xEA;}"
+      : "=r"(w) : "r"(__float_as_uint(sgn)), "r"(__float_as_uint(s)), "r"(pb));
+  return w;
+}
 __device__ __forceinline__ uint32_t v2c_word(float ext, uint32_t pb) {
   const float s = fminf(ext, 1.0f) * rcp_approx(1.0f + ext);
-  return (__float_as_uint(ext - 1.0f) & 0x80000000u) | __float_as_uint(s) | pb;
+  return v2c_pack(ext - 1.0f, s, pb);
+}
+
+// sign bit of (x ^ w) as a predicate in ONE instruction (LOP3.LUT with a predicate destination) — the C form
+// `(int)(x ^ w) < 0` compiles to LOP3 + ISETP.  LUT of (a ^ b) & c = (0xF0 ^ 0xCC) & 0xAA = 0x28.
+__device__ __forceinline__ bool sign_xor(uint32_t x, uint32_t w) {
+  uint32_t d, r;
+  asm("{.reg .pred pp; lop3.or.b32 %0|pp, %2, %3, 0x80000000, 0x28, 0; selp.u32 %1, 1, 0, pp;}"
+      : "=r"(d), "=r"(r) : "r"(x), "r"(w));
+  (void)d;
+  return r != 0;
 }
 
 // c2v ratio P0/P1 from the small probability s and the output's hard decision (sign bit of xw).  The clip of c2v0 to
 // [1e-12, 1-1e-12] (binaryldpccodec.cc:259-263) acts on the small side only.  q = (1-s)/s is the ratio for hard = 0;
 // hard = 1 takes a second (predicated) reciprocal — cheaper on this ALU-bound kernel than selecting numerator and
 // denominator (2 FSEL): the XU pipe has head-room (profiles/r1b).
-__device__ __forceinline__ float c2v_ratio(float s, uint32_t xw) {
+__device__ __forceinline__ float c2v_ratio(float s, uint32_t x, uint32_t w) {
   s = fmaxf(s, kSmallProbF);
   float q = (1.0f - s) * rcp_approx(s);
-  if ((int)xw < 0) q = rcp_approx(q);
+  if (sign_xor(x, w)) q = rcp_approx(q);
   return q;
 }
 
@@ -97,12 +115,20 @@ __device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
 // (3,6)-regular codes (PEG2304, PEG8064): N = VPT * T variables, M = CPT * T checks, everything unrolled,
 // edge addresses and channel ratios resident in registers.
 // ---------------------------------------------------------------------------------------------------------------
-template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2>
+//
+// Two shared-memory layouts (layout_opt.cpp makes the variable-node gathers conflict free for either):
+//   ROWM = false ("planar")   : edge (row slot, k) at word k * (M + 1) + slot — check nodes issue 6 LDS.32 + 6 STS.32
+//   ROWM = true  ("row-major"): at word 6 * slot + phys(k) — the six words of a check are contiguous and move as
+//                               3 LDS.64 + 3 STS.64 (a half-warp covers 16 distinct even banks: conflict free), which
+//                               takes one issue slot per edge-iteration out of this issue-bound kernel.
+template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false>
 __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
-  extern __shared__ uint32_t msg[];
+  extern __shared__ __align__(16) uint32_t msg[];
   __shared__ int s_frame;
   const int tid = threadIdx.x;
-  constexpr int mpad = CPT * T + 1;  // words between the k planes: bank = (slot + k) mod 32 (see layout_opt.cpp)
+  constexpr int mpad = CPT * T + 1;  // planar: words between the k planes, bank = (slot + k) mod 32
+  constexpr int n_words = ROWM ? 6 * CPT * T : 6 * mpad;
+  static_assert(!ROWM || PACK, "row-major layout is implemented for the packed path");
 
   uint32_t va[VPT][3];
 #pragma unroll
@@ -121,7 +147,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     float ch[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; j++) ch[j] = load_channel_ratio(in, j * T + tid, p.in_is_lr);
-    for (int i = tid; i < 6 * mpad; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
+    for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
     __syncthreads();
 
     uint32_t bits = 0, latched_bits = 0;
@@ -144,19 +170,19 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           const float e2 = ab.x * x1;
           const float post = e2 * x2;
           bit = (post > 1.0f) ? 0u : 1u;
-          const uint32_t pb = bit << 30;
+          const uint32_t pb = bit;
           const float2 den = add2(e10, splat(1.0f)), sgn = add2(e10, splat(-1.0f));
           const float2 s10 = mul2(make_float2(fminf(e10.x, 1.0f), fminf(e10.y, 1.0f)),
                                   make_float2(rcp_approx(den.x), rcp_approx(den.y)));
-          w1 = (__float_as_uint(sgn.x) & 0x80000000u) | __float_as_uint(s10.x) | pb;
-          w0 = (__float_as_uint(sgn.y) & 0x80000000u) | __float_as_uint(s10.y) | pb;
+          w1 = v2c_pack(sgn.x, s10.x, pb);
+          w0 = v2c_pack(sgn.y, s10.y, pb);
           w2 = v2c_word(e2, pb);
         } else {
           const float a = ch[j] * x0, b = ch[j] * x1;
           const float e2 = a * x1, e1 = a * x2, e0 = b * x2;
           const float post = e2 * x2;
           bit = (post > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
-          const uint32_t pb = bit << 30;
+          const uint32_t pb = bit;
           w0 = v2c_word(e0, pb);
           w1 = v2c_word(e1, pb);
           w2 = v2c_word(e2, pb);
@@ -177,13 +203,22 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         uint32_t w[6];
         float s[6];
         uint32_t x = 0;
+        // row-major: the check node is indifferent to the order of its edges, so the physical pairs (0,1) (2,3) (4,5)
+        // are taken as the logical pairs (1,4) (2,3) (5,0) the packed arithmetic produces its outputs in
+        uint2 *row = reinterpret_cast<uint2 *>(msg + 6 * slot);
+        if (ROWM) {
+          const uint2 p0 = row[0], p1 = row[1], p2 = row[2];
+          w[1] = p0.x; w[4] = p0.y; w[2] = p1.x; w[3] = p1.y; w[5] = p2.x; w[0] = p2.y;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; k++) w[k] = msg[k * mpad + slot];
+        }
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-          w[k] = msg[k * mpad + slot];
           x ^= w[k];
-          s[k] = __uint_as_float(w[k] & 0x3fffffffu);
+          s[k] = fabsf(__uint_as_float(w[k]));
         }
-        fail |= (int)((x >> 30) & 1u);
+        fail |= (int)(x & 1u);
         float so[6], sall = 0.0f;
         if (PACK) {
           // prefix and suffix chains advance in lock step in the two halves of one FFMA2:
@@ -207,7 +242,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           for (int i = 0; i < 3; i++) {
             const float2 sc = make_float2(fmaxf(so[ka[i]], kSmallProbF), fmaxf(so[kb[i]], kSmallProbF));
             const float2 big = fma2(sc, splat(-1.0f), splat(1.0f));
-            const bool ha = (int)(x ^ w[ka[i]]) < 0, hb = (int)(x ^ w[kb[i]]) < 0;
+            const bool ha = sign_xor(x, w[ka[i]]), hb = sign_xor(x, w[kb[i]]);
             float2 q;
             if (RATIO == 0) {         // second, predicated reciprocal for hard = 1 (XU pipe)
               q = mul2(big, make_float2(rcp_approx(sc.x), rcp_approx(sc.y)));
@@ -222,8 +257,12 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
               q = mul2(make_float2(big.x, numb), make_float2(rcp_approx(sc.x), rcp_approx(denb)));
               if (ha) q.x = rcp_approx(q.x);
             }
-            msg[ka[i] * mpad + slot] = __float_as_uint(q.x);
-            msg[kb[i] * mpad + slot] = __float_as_uint(q.y);
+            if (ROWM) {
+              row[i] = make_uint2(__float_as_uint(q.x), __float_as_uint(q.y));
+            } else {
+              msg[ka[i] * mpad + slot] = __float_as_uint(q.x);
+              msg[kb[i] * mpad + slot] = __float_as_uint(q.y);
+            }
           }
         } else {
           float tt[6];
@@ -241,7 +280,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 #pragma unroll
           for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
 #pragma unroll
-          for (int k = 0; k < 6; k++) msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x ^ w[k]));
+          for (int k = 0; k < 6; k++) msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x, w[k]));
           if (p.out_soft) sall = sp_chain(pre[5], s[5], tt[5]);
         }
         if (p.out_soft)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
@@ -313,12 +352,12 @@ __device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, f
   for (int k = 0; k < D; k++) {
     float e = pre[k] * suf[k + 1];
     if (kClamp) e = fminf(fmaxf(e, kClampLo), kClampHi);
-    msg[a[k]] = v2c_word(e, bit << 30);
+    msg[a[k]] = v2c_word(e, bit);
   }
   return bit;
 }
 
-// returns the XOR of the row's words (bit 30 = syndrome of the current decisions, bit 31 = parity of the extrinsic hard
+// returns the XOR of the row's words (bit 0 = syndrome of the current decisions, bit 31 = parity of the extrinsic hard
 // bits); *s_all = small probability of the whole row (for syndrom_soft)
 template <int D>
 __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, float *s_all) {
@@ -328,7 +367,7 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, 
   for (int k = 0; k < D; k++) {
     w[k] = msg[k * plane + slot];
     x ^= w[k];
-    s[k] = __uint_as_float(w[k] & 0x3fffffffu);
+    s[k] = fabsf(__uint_as_float(w[k]));
     tt[k] = fmaf(-2.0f, s[k], 1.0f);
   }
   float pre[D + 1], suf[D + 1];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}; 0 is the neutral element
@@ -341,7 +380,7 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, 
 #pragma unroll
   for (int k = 0; k < D; k++) {
     const float so = k == 0 ? suf[1] : (k == D - 1 ? pre[D - 1] : sp_combine(pre[k], suf[k + 1]));
-    msg[k * plane + slot] = __float_as_uint(c2v_ratio(so, x ^ w[k]));
+    msg[k * plane + slot] = __float_as_uint(c2v_ratio(so, x, w[k]));
   }
   *s_all = pre[D];
   return x;
@@ -415,7 +454,7 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
           KML_CN_CASE(16)
           default: continue;  // padding slot
         }
-        fail |= (int)((x >> 30) & 1u);
+        fail |= (int)(x & 1u);
         if (p.out_soft) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
       }
       const int any_fail = __syncthreads_or(fail);
@@ -443,22 +482,31 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
 #undef KML_VN_CASE
 #undef KML_CN_CASE
 
-dec_kernel_t kernel_of(DecKernelKind k, int alg) {
+dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor) {
   if (alg != 0) return minsum_kernel_of(k, alg);
   switch (k) {
     case DEC_REG_6_3: {
       const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
       const int b = e ? atoi(e) : 3;
-      const char *pe = getenv("KML_DEC_NOPACK");  // A/B knob: scalar fp32 instead of FMUL2/FADD2/FFMA2
-      if (pe && atoi(pe)) return bp_regular_kernel<6, 3, 384, 3, false>;
-      const char *re = getenv("KML_DEC_RATIO");
-      if (re && atoi(re) == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0>;
-      if (re && atoi(re) == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1>;
-      if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
-      if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
-      return bp_regular_kernel<6, 3, 384, 3>;
+      const char *re = getenv("KML_DEC_RATIO");  // A/B knob: how check outputs with hard bit 1 are inverted
+      const int r = re ? atoi(re) : 2;
+      if (!rowmajor) {
+        const char *pe = getenv("KML_DEC_NOPACK");  // A/B knob: scalar fp32 instead of FMUL2/FADD2/FFMA2
+        if (pe && atoi(pe)) return bp_regular_kernel<6, 3, 384, 3, false>;
+        if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0>;
+        if (r == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1>;
+        if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
+        if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
+        return bp_regular_kernel<6, 3, 384, 3>;
+      }
+      if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0, true>;
+      if (r == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1, true>;
+      if (b == 2) return bp_regular_kernel<6, 3, 384, 2, true, 2, true>;
+      if (b == 4) return bp_regular_kernel<6, 3, 384, 4, true, 2, true>;
+      return bp_regular_kernel<6, 3, 384, 3, true, 2, true>;
     }
-    case DEC_REG_12_6: return bp_regular_kernel<12, 6, 672, 1>;
+    case DEC_REG_12_6:
+      return rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1>;
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
     case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;
@@ -468,8 +516,14 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg) {
 
 }  // namespace
 
+bool dec_wants_rowmajor(DecKernelKind k, int alg) {
+  if (alg != 0 || (k != DEC_REG_6_3 && k != DEC_REG_12_6)) return false;
+  const char *e = getenv("KML_DEC_PLANAR");  // A/B knob: the planar layout for the regular sum-product kernels too
+  return !(e && atoi(e));
+}
+
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind, l.alg);
+  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -488,7 +542,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  kernel_of(l.kind, l.alg)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  kernel_of(l.kind, l.alg, l.rowmajor)<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -56,17 +56,17 @@ struct kml_ctx {
   DevBuf<float2> points;
   DevBuf<int32_t> row_ptr, col_idx, km_nb;
   int km_n_nb = 0;
-  DevBuf<uint16_t> vn_addr, col_ell;
+  DevBuf<uint16_t> vn_addr, vn_addr_rm, col_ell;
   int ell_width = 0;
   DevBuf<uint8_t> vn_deg, cn_deg;
-  DecTables dt{};
+  DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
   DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
   float alpha = 0.8f;
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
   uint64_t launches = 0;
-  int layout_residual = 0, layout_excess = 0;  // layout_opt.cpp: annealing cost left / wavefronts above the ideal
+  int layout_residual = 0, layout_excess = 0, layout_excess_planar = 0;  // layout_opt.cpp: annealing cost left / wavefronts above the ideal
   std::string err;
 };
 
@@ -176,22 +176,37 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   // every kernel hands 32 consecutive variables to one warp instruction
   std::vector<int> group(N);
   for (int v = 0; v < N; v++) group[v] = v / 32;
-  std::vector<int> slot, pos;
-  std::vector<std::vector<int>> order;
-  c->layout_residual = optimize_decoder_layout(M, N, mpad, plane, code->row_ptr, code->col_idx, group, (N + 31) / 32, dv_tab,
-                                               slot, pos, order, &c->layout_excess);
   std::vector<int> erow(code->n_edges);
   for (int r = 0; r < M; r++)
     for (int e = code->row_ptr[r]; e < code->row_ptr[r + 1]; e++) erow[e] = r;
-  std::vector<uint16_t> vaddr((size_t)N * dv_tab, 0xFFFFu);
   std::vector<uint8_t> vdeg(N, 0), cndeg(mpad, 0);
-  for (int r = 0; r < M; r++) cndeg[slot[r]] = (uint8_t)rdeg[r];
-  for (int v = 0; v < N; v++) {  // compact list in colour order (no holes: the kernels unroll on the exact degree)
-    for (int i = 0; i < dv_tab; i++) {
-      const int e = order[v][i];
-      if (e >= 0) vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(pos[e] * plane + slot[erow[e]]);
-    }
+  // address list of one layout: word = pos * pos_stride + slot * slot_stride, compact and in colour order (no holes:
+  // the kernels unroll on the exact degree)
+  auto build_addr = [&](int pos_stride, int slot_stride, std::vector<uint16_t> &vaddr, int *residual, int *excess) {
+    std::vector<int> slot, pos;
+    std::vector<std::vector<int>> order;
+    *residual = optimize_decoder_layout(M, N, mpad, pos_stride, slot_stride, code->row_ptr, code->col_idx, group,
+                                        (N + 31) / 32, dv_tab, slot, pos, order, excess);
+    vaddr.assign((size_t)N * dv_tab, 0xFFFFu);
+    std::fill(vdeg.begin(), vdeg.end(), 0);
+    std::fill(cndeg.begin(), cndeg.end(), 0);
+    for (int r = 0; r < M; r++) cndeg[slot[r]] = (uint8_t)rdeg[r];
+    for (int v = 0; v < N; v++)
+      for (int i = 0; i < dv_tab; i++) {
+        const int e = order[v][i];
+        if (e >= 0) vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(pos[e] * pos_stride + slot[erow[e]] * slot_stride);
+      }
+  };
+  std::vector<uint16_t> vaddr;
+  const bool rowmajor = dec_wants_rowmajor(dl.kind, 0);
+  if (rowmajor) {  // check nodes of the regular kernels read their six words with LDS.64: 6 * slot + k
+    int res_rm = 0;
+    build_addr(1, 6, vaddr, &res_rm, &c->layout_excess);
+    KML_CUDA(c, c->vn_addr_rm.alloc(vaddr.size()));
+    KML_CUDA(c, cudaMemcpy(c->vn_addr_rm.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   }
+  build_addr(plane, 1, vaddr, &c->layout_residual, &c->layout_excess_planar);
+  if (!rowmajor) c->layout_excess = c->layout_excess_planar;
   KML_CUDA(c, c->vn_addr.alloc(vaddr.size()));
   KML_CUDA(c, cudaMemcpy(c->vn_addr.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   KML_CUDA(c, c->vn_deg.alloc(N));
@@ -201,8 +216,13 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
   c->dt.n = N; c->dt.m_pad = mpad; c->dt.plane = plane; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct;
   c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
+  c->dt_rm = c->dt;
+  c->dt_rm.vn_addr = c->vn_addr_rm.p; c->dt_rm.plane = 1;
   for (int alg = 0; alg < 3; alg++) {
     dl.alg = alg;
+    dl.rowmajor = (alg == 0 && rowmajor) ? 1 : 0;
+    if (dl.rowmajor) dl.smem_bytes = 6 * mpad * 4;
+    else if (dl.kind == DEC_REG_6_3 || dl.kind == DEC_REG_12_6) dl.smem_bytes = 6 * plane * 4;
     KML_CUDA(c, dec_prepare(dl));
     c->dl_alg[alg] = dl;
   }
@@ -213,7 +233,7 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
 DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t *sel, int n_cand, int in_is_lr, int iters,
                      uint32_t *out_bits, int32_t *out_ret, float *out_soft) {
   DecParams p{};
-  p.t = c->dt;
+  p.t = c->dl.rowmajor ? c->dt_rm : c->dt;
   p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
   p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
   p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
@@ -389,7 +409,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
   c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
-  c->vn_addr.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  c->vn_addr.release(); c->vn_addr_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }

@@ -26,7 +26,8 @@ enum : uint32_t { STREAM_BITS = 0x5eed0001u, STREAM_FADE = 0x5eed0002u, STREAM_N
 std::vector<int> voronoi_neighbours_of_first(const double *pts, int q);
 
 // layout_opt.cpp
-int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t *row_ptr, const int32_t *col_idx,
+int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_stride, const int32_t *row_ptr,
+                            const int32_t *col_idx,
                             const std::vector<int> &group_of_var, int n_groups, int slots_per_var,
                             std::vector<int> &slot_of_row, std::vector<int> &pos_of_edge,
                             std::vector<std::vector<int>> &edge_order, int *excess_wavefronts);

@@ -11,6 +11,7 @@ namespace kml {
 // Edge messages live in shared memory as one 32-bit word per edge at word address k * plane + slot(row), k = position
 // of the edge inside its row: check-node threads (one row slot each) touch consecutive words → conflict free, and
 // variable-node threads gather/scatter through per-variable address lists that layout_opt.cpp makes conflict free.
+// (The regular sum-product kernels use a second, row-major table: 6 * slot + k, see bp_decode.cu.)
 struct DecTables {
   const uint16_t *vn_addr;  // [n][dv_max] shared-memory word address of each edge of a variable, 0xFFFF = none
   const uint8_t *vn_deg;    // [n]
@@ -40,11 +41,13 @@ struct DecLaunch {
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
+  int rowmajor;     // regular sum-product kernels: messages at 6 * slot + k (DecTables of that layout) instead of planar
 };
 
 typedef void (*dec_kernel_t)(const DecParams);
 dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
 inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
+bool dec_wants_rowmajor(DecKernelKind k, int alg);
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 

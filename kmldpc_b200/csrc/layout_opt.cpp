@@ -1,6 +1,8 @@
 // Shared-memory layout optimiser for the BP decoder (host side, runs once per code; results are cached in-process).
 //
-// The decoder stores the message of edge e = (row r, position k inside the row) at word  k * plane + slot(r).
+// The decoder stores the message of edge e = (row r, position k inside the row) at word
+// k * plane + slot(r) * slot_stride:  "planar" (slot_stride 1, plane = row slots + 1; any row degree) or "row-major"
+// (slot_stride = row degree, plane 1: a check node's words are contiguous and move with 64-bit LDS/STS).
 // Check-node threads own one slot each, so their accesses are conflict free for ANY assignment.  A warp of
 // variable-node threads gathers 32 arbitrary edges per load: with slot(r) = r and plane % 32 == 0 the PEG graphs give
 // 2.3–3.8-way bank conflicts on every variable-node access (ncu, profiles/r1a_bp_decoder_full.txt).
@@ -60,7 +62,8 @@ uint64_t fnv(uint64_t h, const void *p, size_t n) {
 //          edge_order[v][i] = CSR edge fetched by variable v's i-th gather instruction (-1 = none);
 //          *excess_wavefronts = shared-memory wavefronts above one per warp gather that remain (0 = conflict free).
 // Returns the residual annealing cost.
-int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t *row_ptr, const int32_t *col_idx,
+int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_stride, const int32_t *row_ptr,
+                            const int32_t *col_idx,
                             const std::vector<int> &group_of_var, int n_groups, int slots_per_var,
                             std::vector<int> &slot_of_row, std::vector<int> &pos_of_edge,
                             std::vector<std::vector<int>> &edge_order, int *excess_wavefronts) {
@@ -68,7 +71,7 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t 
   uint64_t key = fnv(1469598103934665603ull, row_ptr, sizeof(int32_t) * (M + 1));
   key = fnv(key, col_idx, sizeof(int32_t) * E);
   key = fnv(key, group_of_var.data(), sizeof(int) * N);
-  const int par[4] = {n_slots, plane, slots_per_var, n_groups};
+  const int par[5] = {n_slots, plane, slots_per_var, n_groups, slot_stride};
   key = fnv(key, par, sizeof par);
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -93,7 +96,7 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t 
   for (int r = 0; r < n_slots; r++) slot[r] = r;
   for (int r = 0; r < M; r++)
     for (int e = row_ptr[r]; e < row_ptr[r + 1]; e++) pos[e] = e - row_ptr[r];
-  auto ebank = [&](int e) { return (slot[erow[e]] + pos[e] * plane) & (B - 1); };
+  auto ebank = [&](int e) { return (slot[erow[e]] * slot_stride + pos[e] * plane) & (B - 1); };
   std::vector<int16_t> load((size_t)n_groups * B, 0);
   auto cell = [&](int g, int b) -> int16_t & { return load[(size_t)g * B + b]; };
   for (int e = 0; e < E; e++) cell(egrp[e], ebank(e))++;
@@ -145,7 +148,7 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, const int32_t 
       }
     } else {  // swap the slots of two rows
       const int r2 = (int)rng.below(n_slots);
-      if (((slot[r1] ^ slot[r2]) & (B - 1)) == 0) continue;
+      if ((((slot[r1] - slot[r2]) * slot_stride) & (B - 1)) == 0) continue;
       d = rem_row(r1) + rem_row(r2);
       std::swap(slot[r1], slot[r2]);
       d += add_row(r1) + add_row(r2);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # static instruction count of the decoder's VN and CN phases (between barriers) for bp_regular_kernel<6,3,384,MINB>
-SO=${1:-kmldpc_b200/lib/libkmldpc_b200.so}; MINB=${2:-3}
-cuobjdump -sass $SO 2>/dev/null | awk -v pat="bp_regular_kernelILi6ELi3ELi384ELi${MINB}E" '/Function : /{p = index($0, pat) > 0} p{print}' | grep -E '^\s+/\*[0-9a-f]{4}\*/' | sed -E 's/^\s+\/\*([0-9a-f]+)\*\/\s+//; s/\s*\/\*.*$//' > /tmp/bp_sass.txt
+SO=${1:-kmldpc_b200/lib/libkmldpc_b200.so}; MINB=${2:-3}; SUF=${3:-ELb1ELi2E}
+cuobjdump -sass $SO 2>/dev/null | awk -v pat="bp_regular_kernelILi6ELi3ELi384ELi${MINB}${SUF}" '/Function : /{p = index($0, pat) > 0} p{print}' | grep -E '^\s+/\*[0-9a-f]{4}\*/' | sed -E 's/^\s+\/\*([0-9a-f]+)\*\/\s+//; s/\s*\/\*.*$//' > /tmp/bp_sass.txt
 python3 - <<'PY'
 import collections
 L=[l.strip() for l in open('/tmp/bp_sass.txt')]
