@@ -116,12 +116,15 @@ __device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
 // edge addresses and channel ratios resident in registers.
 // ---------------------------------------------------------------------------------------------------------------
 //
+// SOFT = the syndrom_soft sum of the soft-syndrome metric ([ldpc] metric_type = true) is produced; a compile-time switch
+// because even the skipped branch costs 7 issue slots per check in this issue-bound loop.
+//
 // Two shared-memory layouts (layout_opt.cpp makes the variable-node gathers conflict free for either):
 //   ROWM = false ("planar")   : edge (row slot, k) at word k * (M + 1) + slot — check nodes issue 6 LDS.32 + 6 STS.32
 //   ROWM = true  ("row-major"): at word 6 * slot + phys(k) — the six words of a check are contiguous and move as
 //                               3 LDS.64 + 3 STS.64 (a half-warp covers 16 distinct even banks: conflict free), which
 //                               takes one issue slot per edge-iteration out of this issue-bound kernel.
-template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false>
+template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false, bool SOFT = false>
 __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
   extern __shared__ __align__(16) uint32_t msg[];
   __shared__ int s_frame;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           const float2 o14 = fma2(mul2(c1, splat(-2.0f)), c4s, add2(c1, c4s));
           const float2 o23 = fma2(mul2(c2, splat(-2.0f)), c3s, add2(c2, c3s));
           so[1] = o14.x; so[4] = o14.y; so[2] = o23.x; so[3] = o23.y; so[5] = c5.x; so[0] = c5.y;
-          if (p.out_soft) sall = sp_chain(c5.x, s[5], fmaf(-2.0f, s[5], 1.0f));
+          if (SOFT) sall = sp_chain(c5.x, s[5], fmaf(-2.0f, s[5], 1.0f));
           // ratios two at a time: clip, 1 - s, reciprocal, product
           const int ka[3] = {1, 2, 5}, kb[3] = {4, 3, 0};
 #pragma unroll
@@ -252,6 +255,11 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
               const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
               const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);
               q = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+            } else if (RATIO == 3) {  // selects + ONE reciprocal for the pair: r = 1 / (den_a den_b), q_a = num_a den_b r
+              const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
+              const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);  // >= 1e-12 each: product is normal
+              const float r = rcp_approx(den.x * den.y);
+              q = mul2(mul2(num, make_float2(den.y, den.x)), splat(r));
             } else {                  // one of each: balances the XU and ALU pipes
               const float numb = hb ? sc.y : big.y, denb = hb ? big.y : sc.y;
               q = mul2(make_float2(big.x, numb), make_float2(rcp_approx(sc.x), rcp_approx(denb)));
@@ -281,9 +289,9 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           for (int k = 1; k < 5; k++) so[k] = sp_combine(pre[k], suf[k + 1]);
 #pragma unroll
           for (int k = 0; k < 6; k++) msg[k * mpad + slot] = __float_as_uint(c2v_ratio(so[k], x, w[k]));
-          if (p.out_soft) sall = sp_chain(pre[5], s[5], tt[5]);
+          if (SOFT) sall = sp_chain(pre[5], s[5], tt[5]);
         }
-        if (p.out_soft)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
+        if (SOFT)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
           soft += __logf((x >> 31) ? sall : 1.0f - sall);
       }
       const int any_fail = __syncthreads_or(fail);
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
       if (lane == 0) p.out_bits[(size_t)f * p.words_n + ((j * T + tid) >> 5)] = word;
     }
     if (tid == 0) p.out_ret[f] = ret;
-    if (p.out_soft) {
+    if (SOFT) {
       // NOTE: when the reference leaves at t = 0 its syndrom_soft_ is stale (left over from the previous call);
       // here that case reports 0.
 #pragma unroll
@@ -482,14 +490,18 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
 #undef KML_VN_CASE
 #undef KML_CN_CASE
 
-dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor) {
+dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
   if (alg != 0) return minsum_kernel_of(k, alg);
+  if (soft && k == DEC_REG_6_3)
+    return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
+  if (soft && k == DEC_REG_12_6)
+    return rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, true, true> : bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>;
   switch (k) {
     case DEC_REG_6_3: {
       const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
       const int b = e ? atoi(e) : 3;
       const char *re = getenv("KML_DEC_RATIO");  // A/B knob: how check outputs with hard bit 1 are inverted
-      const int r = re ? atoi(re) : 2;
+      const int r = re ? atoi(re) : 1;
       if (!rowmajor) {
         const char *pe = getenv("KML_DEC_NOPACK");  // A/B knob: scalar fp32 instead of FMUL2/FADD2/FFMA2
         if (pe && atoi(pe)) return bp_regular_kernel<6, 3, 384, 3, false>;
@@ -500,13 +512,18 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor) {
         return bp_regular_kernel<6, 3, 384, 3>;
       }
       if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0, true>;
-      if (r == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1, true>;
+      if (r == 3) return bp_regular_kernel<6, 3, 384, 3, true, 3, true>;
       if (b == 2) return bp_regular_kernel<6, 3, 384, 2, true, 2, true>;
       if (b == 4) return bp_regular_kernel<6, 3, 384, 4, true, 2, true>;
-      return bp_regular_kernel<6, 3, 384, 3, true, 2, true>;
+      if (r == 2) return bp_regular_kernel<6, 3, 384, 3, true, 2, true>;
+      return bp_regular_kernel<6, 3, 384, 3, true, 1, true>;
     }
-    case DEC_REG_12_6:
-      return rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1>;
+    case DEC_REG_12_6: {
+      const char *re = getenv("KML_DEC_RATIO");
+      const int r8 = re ? atoi(re) : 2;  // one CTA per SM: the predicated reciprocal wins here (measured)
+      return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
+                      : bp_regular_kernel<12, 6, 672, 1>;
+    }
     case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
     case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
     case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;
@@ -516,6 +533,11 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor) {
 
 }  // namespace
 
+int dec_regular_threads(DecKernelKind k) {
+  if (k == DEC_REG_12_6) return 672;
+  return 384;  // (576 threads x (4 variables, 2 checks), 2 CTAs per SM measured 7 % slower)
+}
+
 bool dec_wants_rowmajor(DecKernelKind k, int alg) {
   if (alg != 0 || (k != DEC_REG_6_3 && k != DEC_REG_12_6)) return false;
   const char *e = getenv("KML_DEC_PLANAR");  // A/B knob: the planar layout for the regular sum-product kernels too
@@ -523,10 +545,15 @@ bool dec_wants_rowmajor(DecKernelKind k, int alg) {
 }
 
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor);
+  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
+  dec_kernel_t ks = kernel_of(l.kind, l.alg, l.rowmajor, true);  // the soft-syndrome twin, same launch shape
+  if (ks != k) {
+    e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
+    if (e != cudaSuccess) return e;
+  }
   int n = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.threads, l.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -542,7 +569,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  kernel_of(l.kind, l.alg, l.rowmajor)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  kernel_of(l.kind, l.alg, l.rowmajor, p.out_soft != nullptr)<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -221,6 +221,7 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   for (int alg = 0; alg < 3; alg++) {
     dl.alg = alg;
     dl.rowmajor = (alg == 0 && rowmajor) ? 1 : 0;
+    if (dl.kind == DEC_REG_6_3) dl.threads = alg == 0 ? dec_regular_threads(dl.kind) : 384;
     if (dl.rowmajor) dl.smem_bytes = 6 * mpad * 4;
     else if (dl.kind == DEC_REG_6_3 || dl.kind == DEC_REG_12_6) dl.smem_bytes = 6 * plane * 4;
     KML_CUDA(c, dec_prepare(dl));

@@ -48,6 +48,7 @@ typedef void (*dec_kernel_t)(const DecParams);
 dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
 inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
 bool dec_wants_rowmajor(DecKernelKind k, int alg);
+int dec_regular_threads(DecKernelKind k);
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 

@@ -118,19 +118,20 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_strid
   auto add_row = [&](int r) { int d = 0; if (r < M) for (int e = row_ptr[r]; e < row_ptr[r + 1]; e++) d += add(e); return d; };
   Rng rng{0x9E3779B97F4A7C15ull};
   const long moves = std::min<long>(12000000, 600L * E);
-  const double t0 = 0.3, t1 = 0.05;
+  const double t0 = 0.4, t1 = 0.12;
   float temp = (float)t0;
+  std::vector<int> hot;
   for (long it = 0; it < moves && cost > 0; it++) {
     if ((it & 0x3fff) == 0) temp = (float)(t0 * std::pow(t1 / t0, (double)it / moves));
-    // bias towards rows that currently sit in an overloaded cell
-    int r1 = (int)rng.below(M);
-    for (int tries = 0; tries < 4; tries++) {
-      const int e = (int)rng.below(E);
-      if (cell(egrp[e], ebank(e)) > cap[egrp[e]]) {
-        r1 = erow[e];
-        break;
-      }
+    // pick a row that currently sits in an overloaded cell: the list of edges in overloaded cells is rebuilt every 4096
+    // moves (late in the run only a handful of cells are over capacity, and blind sampling almost never finds them)
+    if ((it & 0xfff) == 0) {
+      hot.clear();
+      for (int e = 0; e < E; e++)
+        if (cell(egrp[e], ebank(e)) > cap[egrp[e]]) hot.push_back(e);
     }
+    int r1 = (int)rng.below(M);
+    if (!hot.empty() && (rng.next() & 3) != 0) r1 = erow[hot[rng.below((uint32_t)hot.size())]];
     int d = 0;
     if (it & 1) {  // swap the positions of two edges inside row r1
       const int deg = row_ptr[r1 + 1] - row_ptr[r1];
