@@ -326,94 +326,136 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 
 // ---------------------------------------------------------------------------------------------------------------
 // Any Tanner graph with column degree <= DV and row degree <= DC (5G BG2, irregular codes, odd sizes).
-// Runtime loops over the thread's variables / row slots; the node update is dispatched on the node's EXACT degree
-// (warp-uniform for quasi-cyclic codes: 32 consecutive variables / rows share a degree), so no work is spent on padding.
-// Address lists come through the read-only path, channel ratios are staged in shared memory.
+// * Work is handed out in WARP ITEMS: 32 consecutive variables (or row slots).  The host balances the items over the
+//   CTA's warps by node degree (longest-processing-time first; kml_api.cu) — a tid-strided loop leaves the warps that
+//   drew the degree-9 columns of BG2 with 2x the work of the others.
+// * The node update is dispatched on the node's EXACT degree (warp-uniform for quasi-cyclic codes: the 32 nodes of an
+//   item share a degree), so no work is spent on padding.
+// * Node arithmetic is packed like the regular kernel's: prefix and suffix products / combinations advance in the two
+//   halves of one FMUL2 / FFMA2, outputs pair up as (k, D-1-k).
+// * Variable nodes above degree 3 rely on fp32 saturation (inf / 0) instead of clamping every partial product: a
+//   saturated extrinsic ratio gives s = 0 exactly like a clamped one gives s < 1e-36, and the one pathological
+//   combination (inf x 0 = NaN: >= 4 saturated messages each way on one variable) is absorbed by the check node's
+//   clip (fmaxf(NaN, 1e-12) = 1e-12) — the clamped product was equally arbitrary there.
+// * Address lists are stored transposed ([edge k][variable]) so a warp's 32 loads are one 64-byte line; channel
+//   ratios are staged in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 swap2(float2 a) { return make_float2(a.y, a.x); }
+
 template <int D>
-__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, float ch) {
+__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, int stride, float ch) {
   uint32_t a[D];
   float x[D];
 #pragma unroll
   for (int k = 0; k < D; k++) {
-    a[k] = __ldg(ad + k);
+    a[k] = __ldg(ad + (size_t)k * stride);
     x[k] = __uint_as_float(msg[a[k]]);
   }
-  // up to 3 edges the products stay inside fp32 (1e12^3); above, partial products are clamped to 1e±36, which only
-  // acts where the ratio is already far beyond the 1e±12 clip of every check message (see the header comment)
-  constexpr bool kClamp = D > 3;
-  float pre[D + 1], suf[D + 1];
-  pre[0] = ch;
+  // P[i] = (pre_i, suf_{D-i}):  pre_i = ch x_0 … x_{i-1},  suf_j = x_j … x_{D-1}
+  float2 P[D + 1];
+  P[0] = make_float2(ch, 1.0f);
 #pragma unroll
-  for (int k = 0; k < D; k++) {
-    pre[k + 1] = pre[k] * x[k];
-    if (kClamp) pre[k + 1] = fminf(fmaxf(pre[k + 1], kClampLo), kClampHi);
-  }
-  suf[D] = 1.0f;
+  for (int i = 0; i < D; i++) P[i + 1] = mul2(P[i], make_float2(x[i], x[D - 1 - i]));
+  const uint32_t bit = (P[D].x > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
+  // extrinsic ratios  ext_k = pre_k suf_{k+1}:  (ext_k, ext_{D-1-k}) = P[k] * swap(P[D-1-k])
 #pragma unroll
-  for (int k = D - 1; k >= 0; k--) {
-    suf[k] = suf[k + 1] * x[k];
-    if (kClamp) suf[k] = fminf(fmaxf(suf[k], kClampLo), kClampHi);
-  }
-  const uint32_t bit = (pre[D] > 1.0f) ? 0u : 1u;  // alpha0 > alpha1 ? 0 : 1 (tie → 1)
-#pragma unroll
-  for (int k = 0; k < D; k++) {
-    float e = pre[k] * suf[k + 1];
-    if (kClamp) e = fminf(fmaxf(e, kClampLo), kClampHi);
-    msg[a[k]] = v2c_word(e, bit);
+  for (int k = 0; 2 * k < D; k++) {
+    const int kk = D - 1 - k;
+    if (k < kk) {
+      const float2 e = mul2(P[k], swap2(P[kk]));
+      const float2 den = add2(e, splat(1.0f)), sgn = add2(e, splat(-1.0f));
+      const float2 s2 = mul2(make_float2(fminf(e.x, 1.0f), fminf(e.y, 1.0f)),
+                             make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+      msg[a[k]] = v2c_pack(sgn.x, s2.x, bit);
+      msg[a[kk]] = v2c_pack(sgn.y, s2.y, bit);
+    } else {
+      msg[a[k]] = v2c_word(P[k].x * P[k].y, bit);
+    }
   }
   return bit;
 }
 
+// c2v ratios of a pair of outputs (select-based inversion, as the regular kernel's RATIO = 1)
+__device__ __forceinline__ float2 c2v_ratio2(float2 so, uint32_t x, uint32_t wa, uint32_t wb) {
+  const float2 sc = make_float2(fmaxf(so.x, kSmallProbF), fmaxf(so.y, kSmallProbF));
+  const float2 big = fma2(sc, splat(-1.0f), splat(1.0f));
+  const bool ha = sign_xor(x, wa), hb = sign_xor(x, wb);
+  const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
+  const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);
+  return mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+}
+
 // returns the XOR of the row's words (bit 0 = syndrome of the current decisions, bit 31 = parity of the extrinsic hard
 // bits); *s_all = small probability of the whole row (for syndrom_soft)
-template <int D>
+template <int D, bool SOFT>
 __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, float *s_all) {
   uint32_t w[D], x = 0;
-  float s[D], tt[D];
+  float s[D];
 #pragma unroll
   for (int k = 0; k < D; k++) {
     w[k] = msg[k * plane + slot];
     x ^= w[k];
     s[k] = fabsf(__uint_as_float(w[k]));
-    tt[k] = fmaf(-2.0f, s[k], 1.0f);
   }
-  float pre[D + 1], suf[D + 1];  // pre[k] = s_0 ⊕ … ⊕ s_{k-1}; 0 is the neutral element
-  pre[0] = 0.0f;
+  if (D < 3) {  // degree 1: the only output is the neutral element (clipped); degree 2: the two inputs swap
 #pragma unroll
-  for (int k = 0; k < D; k++) pre[k + 1] = k == 0 ? s[0] : sp_chain(pre[k], s[k], tt[k]);
-  suf[D] = 0.0f;
-#pragma unroll
-  for (int k = D - 1; k >= 0; k--) suf[k] = k == D - 1 ? s[k] : sp_chain(suf[k + 1], s[k], tt[k]);
-#pragma unroll
-  for (int k = 0; k < D; k++) {
-    const float so = k == 0 ? suf[1] : (k == D - 1 ? pre[D - 1] : sp_combine(pre[k], suf[k + 1]));
-    msg[k * plane + slot] = __float_as_uint(c2v_ratio(so, x, w[k]));
+    for (int k = 0; k < D; k++) msg[k * plane + slot] = __float_as_uint(c2v_ratio(D == 1 ? 0.0f : s[1 - k], x, w[k]));
+    if (SOFT) *s_all = D == 1 ? s[0] : sp_combine(s[0], s[1]);
+    return x;
   }
-  *s_all = pre[D];
+  // C[j] = (pre_j, suf_{D-j}), j = 1 … D-1:  pre_j = s_0 ⊕ … ⊕ s_{j-1},  suf_j = s_j ⊕ … ⊕ s_{D-1};
+  // C[j+1] = C[j] (t_j, t_{D-1-j}) + (s_j, s_{D-1-j})
+  float2 C[D];
+  C[1] = make_float2(s[0], s[D - 1]);
+#pragma unroll
+  for (int j = 1; j < D - 1; j++) {
+    const float2 sj = make_float2(s[j], s[D - 1 - j]);
+    C[j + 1] = fma2(C[j], fma2(sj, splat(-2.0f), splat(1.0f)), sj);
+  }
+  // outputs: (so_{D-1}, so_0) = C[D-1];  (so_k, so_{D-1-k}) = C[k] ⊕ swap(C[D-1-k])
+  {
+    const float2 q = c2v_ratio2(C[D - 1], x, w[D - 1], w[0]);
+    msg[(D - 1) * plane + slot] = __float_as_uint(q.x);
+    msg[slot] = __float_as_uint(q.y);
+  }
+#pragma unroll
+  for (int k = 1; 2 * k < D; k++) {
+    const int kk = D - 1 - k;
+    if (k < kk) {
+      const float2 cs = swap2(C[kk]);
+      const float2 so = fma2(mul2(C[k], splat(-2.0f)), cs, add2(C[k], cs));
+      const float2 q = c2v_ratio2(so, x, w[k], w[kk]);
+      msg[k * plane + slot] = __float_as_uint(q.x);
+      msg[kk * plane + slot] = __float_as_uint(q.y);
+    } else {
+      msg[k * plane + slot] = __float_as_uint(c2v_ratio(sp_combine(C[k].x, C[k].y), x, w[k]));
+    }
+  }
+  if (SOFT) *s_all = sp_chain(C[D - 1].x, s[D - 1], fmaf(-2.0f, s[D - 1], 1.0f));
   return x;
 }
 
 #define KML_VN_CASE(D)                                  \
   case D:                                               \
-    if (D <= DV) bit = vn_node<(D <= DV ? D : 1)>(msg, ad, chan[v]); \
+    if (D <= DV) bit = vn_node<(D <= DV ? D : 1)>(msg, ad, n_pad, chan[v]); \
     break;
 #define KML_CN_CASE(D)                                  \
   case D:                                               \
-    if (D <= DC) x = cn_node<(D <= DC ? D : 1)>(msg, plane, slot, &s_all); \
+    if (D <= DC) x = cn_node<(D <= DC ? D : 1), SOFT>(msg, plane, slot, &s_all); \
     break;
 
-template <int DV, int DC>
-__global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
+constexpr int kGenericThreads = 384;  // 3 CTAs per SM at <= 56 registers
+
+template <int DV, int DC, bool SOFT>
+__global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const DecParams p) {
   static_assert(DV <= 16 && DC <= 16, "add switch cases");
   extern __shared__ uint32_t smem[];
   __shared__ int s_frame;
-  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31;
-  const int mpad = p.t.m_pad, plane = p.t.plane, n = p.t.n, dcm = p.t.dc_max;
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
+  const int plane = p.t.plane, n = p.t.n, dcm = p.t.dc_max, n_pad = p.t.n_pad;
   uint32_t *msg = smem;                                  // [dc_max * plane]
   float *chan = reinterpret_cast<float *>(smem + dcm * plane);  // [n]
   uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);      // [2][words_n] decisions, double buffered
-  const int n_round = (n + 31) & ~31;
 
   while (true) {
     if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
@@ -433,11 +475,14 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
     for (int t = 0; t < p.iters; t++) {
       last_t = t;
       uint32_t *dcur = dec + (t & 1) * p.words_n;
-      for (int v = tid; v < n_round; v += T) {
+      for (int i = warp; i < p.t.vn_items_n; i += W) {
+        const int g = __ldg(p.t.vn_items + i);
+        if (g == 0xFFFF) continue;  // padding of a shorter list (warp-uniform)
+        const int v = g * 32 + lane;
         uint32_t bit = 0;
         if (v < n) {
           // edges in the order the layout optimiser coloured them (= gather instruction index inside the warp)
-          const uint16_t *ad = p.t.vn_addr + (size_t)v * p.t.dv_max;
+          const uint16_t *ad = p.t.vn_addr_t + v;
           switch (__ldg(p.t.vn_deg + v)) {
             case 0: bit = (chan[v] > 1.0f) ? 0u : 1u; break;
             KML_VN_CASE(1) KML_VN_CASE(2) KML_VN_CASE(3) KML_VN_CASE(4) KML_VN_CASE(5) KML_VN_CASE(6) KML_VN_CASE(7) KML_VN_CASE(8)
@@ -447,13 +492,16 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
           }
         }
         const uint32_t word = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0) dcur[v >> 5] = word;
+        if (lane == 0) dcur[g] = word;
       }
       __syncthreads();
       int fail = 0;
       const float soft_before = soft;
       soft = 0.0f;
-      for (int slot = tid; slot < mpad; slot += T) {
+      for (int i = warp; i < p.t.cn_items_n; i += W) {
+        const int g = __ldg(p.t.cn_items + i);
+        if (g == 0xFFFF) continue;
+        const int slot = g * 32 + lane;
         uint32_t x = 0;
         float s_all = 0.0f;
         switch (__ldg(p.t.cn_deg + slot)) {
@@ -463,7 +511,7 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
           default: continue;  // padding slot
         }
         fail |= (int)(x & 1u);
-        if (p.out_soft) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
+        if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
       }
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -480,7 +528,7 @@ __global__ void __launch_bounds__(512) bp_generic_kernel(const DecParams p) {
       for (int w = tid; w < p.words_n; w += T) p.out_bits[(size_t)f * p.words_n + w] = dl[w];
     }
     if (tid == 0) p.out_ret[f] = ret;
-    if (p.out_soft) {
+    if (SOFT) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
       if (lane == 0) atomicAdd(p.out_soft + f, soft_out);
@@ -524,14 +572,16 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
       return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
                       : bp_regular_kernel<12, 6, 672, 1>;
     }
-    case DEC_GEN_4_8: return bp_generic_kernel<4, 8>;
-    case DEC_GEN_9_10: return bp_generic_kernel<9, 10>;
-    case DEC_GEN_16_32: return bp_generic_kernel<16, 16>;
+    case DEC_GEN_4_8: return soft ? bp_generic_kernel<4, 8, true> : bp_generic_kernel<4, 8, false>;
+    case DEC_GEN_9_10: return soft ? bp_generic_kernel<9, 10, true> : bp_generic_kernel<9, 10, false>;
+    case DEC_GEN_16_32: return soft ? bp_generic_kernel<16, 16, true> : bp_generic_kernel<16, 16, false>;
   }
   return nullptr;
 }
 
 }  // namespace
+
+int dec_generic_max_threads() { return kGenericThreads; }
 
 int dec_regular_threads(DecKernelKind k) {
   if (k == DEC_REG_12_6) return 672;

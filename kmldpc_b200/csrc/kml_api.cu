@@ -56,7 +56,7 @@ struct kml_ctx {
   DevBuf<float2> points;
   DevBuf<int32_t> row_ptr, col_idx, km_nb;
   int km_n_nb = 0;
-  DevBuf<uint16_t> vn_addr, vn_addr_rm, col_ell;
+  DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_t, vn_items, cn_items, col_ell;
   int ell_width = 0;
   DevBuf<uint8_t> vn_deg, cn_deg;
   DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
@@ -166,8 +166,9 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     else if (dvm <= 16 && dcm <= 16) { dl.kind = DEC_GEN_16_32; }
     else return fail_arg(c, "row/column degree beyond the compiled decoder kernels (max 16/16)");
     dv_tab = dvm;
-    int t = std::min(512, std::max(128, ((N + 5) / 6 + 31) & ~31));
-    for (int cand = 512; cand >= 256; cand -= 32)  // prefer a block size that tiles the row slots exactly
+    const int tmax = dec_generic_max_threads();
+    int t = std::min(tmax, std::max(128, ((N + 5) / 6 + 31) & ~31));
+    for (int cand = tmax; cand >= 256; cand -= 32)  // prefer a block size that tiles the row slots exactly
       if (mpad % cand == 0 && cand * 8 >= N) { t = cand; break; }
     dl.threads = t;
     dl.smem_bytes = (dcm * plane + N + 2 * c->words_n) * 4;
@@ -216,6 +217,51 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
   c->dt.n = N; c->dt.m_pad = mpad; c->dt.plane = plane; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct;
   c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
+  {
+    // generic sum-product kernel: transposed address lists (a warp's 32 loads = one 64-byte line) and warp work lists
+    // balanced by node degree — longest-processing-time first over the CTA's warps, then laid out [round][warp]
+    const int n_pad = (N + 31) & ~31, W = dl.threads / 32;
+    std::vector<uint16_t> vt((size_t)dv_tab * n_pad, 0xFFFFu);
+    for (int v = 0; v < N; v++)
+      for (int k = 0; k < dv_tab; k++) vt[(size_t)k * n_pad + v] = vaddr[(size_t)v * dv_tab + k];
+    auto balance = [&](int n_groups, auto group_cost, std::vector<uint16_t> &items) {
+      std::vector<int> ord(n_groups);
+      for (int g = 0; g < n_groups; g++) ord[g] = g;
+      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return group_cost(a) > group_cost(b); });
+      std::vector<std::vector<int>> mine(W);
+      std::vector<long> load(W, 0);
+      for (int g : ord) {
+        if (group_cost(g) == 0) continue;  // nothing to do in this group
+        const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+        mine[w].push_back(g);
+        load[w] += group_cost(g) + 2;  // + loop / dispatch overhead of an item
+      }
+      size_t rounds = 0;
+      for (auto &m : mine) rounds = std::max(rounds, m.size());
+      items.assign(rounds * W, 0xFFFFu);
+      for (int w = 0; w < W; w++)
+        for (size_t i = 0; i < mine[w].size(); i++) items[i * W + w] = (uint16_t)mine[w][i];
+    };
+    std::vector<uint16_t> vi, ci;
+    balance(n_pad / 32, [&](int g) {
+      int d = 1;  // degree-0 variables still report a decision
+      for (int v = g * 32; v < std::min(N, g * 32 + 32); v++) d = std::max<int>(d, vdeg[v]);
+      return d;
+    }, vi);
+    balance(mpad / 32, [&](int g) {
+      int d = 0;
+      for (int sl = g * 32; sl < g * 32 + 32; sl++) d = std::max<int>(d, cndeg[sl]);
+      return d;
+    }, ci);
+    KML_CUDA(c, c->vn_addr_t.alloc(vt.size()));
+    KML_CUDA(c, cudaMemcpy(c->vn_addr_t.p, vt.data(), vt.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->vn_items.alloc(vi.size()));
+    KML_CUDA(c, cudaMemcpy(c->vn_items.p, vi.data(), vi.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->cn_items.alloc(ci.size()));
+    KML_CUDA(c, cudaMemcpy(c->cn_items.p, ci.data(), ci.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    c->dt.vn_addr_t = c->vn_addr_t.p; c->dt.vn_items = c->vn_items.p; c->dt.cn_items = c->cn_items.p;
+    c->dt.n_pad = n_pad; c->dt.vn_items_n = (int)vi.size(); c->dt.cn_items_n = (int)ci.size();
+  }
   c->dt_rm = c->dt;
   c->dt_rm.vn_addr = c->vn_addr_rm.p; c->dt_rm.plane = 1;
   for (int alg = 0; alg < 3; alg++) {
@@ -410,7 +456,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
   c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
-  c->vn_addr.release(); c->vn_addr_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_t.release(); c->vn_items.release(); c->cn_items.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }

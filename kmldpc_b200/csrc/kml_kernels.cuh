@@ -17,6 +17,11 @@ struct DecTables {
   const uint8_t *vn_deg;    // [n]
   const uint8_t *cn_deg;    // [m_pad] degree of the row held by a slot (0 = padding)
   int n, m_pad, plane, n_tx, punct, dv_max, dc_max;  // m_pad = row slots (multiple of 32), plane = m_pad + 1
+  // generic sum-product kernel: transposed address lists and degree-balanced warp work lists
+  const uint16_t *vn_addr_t;  // [dv_max][n_pad]
+  const uint16_t *vn_items;   // [vn_items_n] groups of 32 variables, laid out [round][warp]; 0xFFFF = none
+  const uint16_t *cn_items;   // [cn_items_n] groups of 32 row slots, same layout
+  int n_pad, vn_items_n, cn_items_n;
 };
 
 struct DecParams {
@@ -49,6 +54,7 @@ dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
 inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
 bool dec_wants_rowmajor(DecKernelKind k, int alg);
 int dec_regular_threads(DecKernelKind k);
+int dec_generic_max_threads();
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 
