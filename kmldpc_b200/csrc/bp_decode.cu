@@ -337,18 +337,20 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 //   saturated extrinsic ratio gives s = 0 exactly like a clamped one gives s < 1e-36, and the one pathological
 //   combination (inf x 0 = NaN: >= 4 saturated messages each way on one variable) is absorbed by the check node's
 //   clip (fmaxf(NaN, 1e-12) = 1e-12) — the clamped product was equally arbitrary there.
-// * Address lists are stored transposed ([edge k][variable]) so a warp's 32 loads are one 64-byte line; channel
-//   ratios are staged in shared memory.
+// * Messages are row-major with an odd compile-time row stride RS (word 'slot * RS + k': conflict free for the check
+//   nodes, every access an immediate offset from one base register); variable-node address lists are stored per item as
+//   [edge k][lane] so a warp's 32 loads are one 64-byte line at an immediate offset.  Channel ratios are staged in
+//   shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 swap2(float2 a) { return make_float2(a.y, a.x); }
 
 template <int D>
-__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, int stride, float ch) {
+__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, float ch) {
   uint32_t a[D];
   float x[D];
 #pragma unroll
   for (int k = 0; k < D; k++) {
-    a[k] = __ldg(ad + (size_t)k * stride);
+    a[k] = __ldg(ad + k * 32);
     x[k] = __uint_as_float(msg[a[k]]);
   }
   // P[i] = (pre_i, suf_{D-i}):  pre_i = ch x_0 … x_{i-1},  suf_j = x_j … x_{D-1}
@@ -388,18 +390,18 @@ __device__ __forceinline__ float2 c2v_ratio2(float2 so, uint32_t x, uint32_t wa,
 // returns the XOR of the row's words (bit 0 = syndrome of the current decisions, bit 31 = parity of the extrinsic hard
 // bits); *s_all = small probability of the whole row (for syndrom_soft)
 template <int D, bool SOFT>
-__device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, float *s_all) {
+__device__ __forceinline__ uint32_t cn_node(uint32_t *row, float *s_all) {
   uint32_t w[D], x = 0;
   float s[D];
 #pragma unroll
   for (int k = 0; k < D; k++) {
-    w[k] = msg[k * plane + slot];
+    w[k] = row[k];
     x ^= w[k];
     s[k] = fabsf(__uint_as_float(w[k]));
   }
   if (D < 3) {  // degree 1: the only output is the neutral element (clipped); degree 2: the two inputs swap
 #pragma unroll
-    for (int k = 0; k < D; k++) msg[k * plane + slot] = __float_as_uint(c2v_ratio(D == 1 ? 0.0f : s[1 - k], x, w[k]));
+    for (int k = 0; k < D; k++) row[k] = __float_as_uint(c2v_ratio(D == 1 ? 0.0f : s[1 - k], x, w[k]));
     if (SOFT) *s_all = D == 1 ? s[0] : sp_combine(s[0], s[1]);
     return x;
   }
@@ -415,8 +417,8 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, 
   // outputs: (so_{D-1}, so_0) = C[D-1];  (so_k, so_{D-1-k}) = C[k] ⊕ swap(C[D-1-k])
   {
     const float2 q = c2v_ratio2(C[D - 1], x, w[D - 1], w[0]);
-    msg[(D - 1) * plane + slot] = __float_as_uint(q.x);
-    msg[slot] = __float_as_uint(q.y);
+    row[D - 1] = __float_as_uint(q.x);
+    row[0] = __float_as_uint(q.y);
   }
 #pragma unroll
   for (int k = 1; 2 * k < D; k++) {
@@ -425,24 +427,73 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *msg, int plane, int slot, 
       const float2 cs = swap2(C[kk]);
       const float2 so = fma2(mul2(C[k], splat(-2.0f)), cs, add2(C[k], cs));
       const float2 q = c2v_ratio2(so, x, w[k], w[kk]);
-      msg[k * plane + slot] = __float_as_uint(q.x);
-      msg[kk * plane + slot] = __float_as_uint(q.y);
+      row[k] = __float_as_uint(q.x);
+      row[kk] = __float_as_uint(q.y);
     } else {
-      msg[k * plane + slot] = __float_as_uint(c2v_ratio(sp_combine(C[k].x, C[k].y), x, w[k]));
+      row[k] = __float_as_uint(c2v_ratio(sp_combine(C[k].x, C[k].y), x, w[k]));
     }
   }
   if (SOFT) *s_all = sp_chain(C[D - 1].x, s[D - 1], fmaf(-2.0f, s[D - 1], 1.0f));
   return x;
 }
 
-#define KML_VN_CASE(D)                                  \
-  case D:                                               \
-    if (D <= DV) bit = vn_node<(D <= DV ? D : 1)>(msg, ad, n_pad, chan[v]); \
+// one case of the per-item dispatch: the whole run of `cnt` groups is processed inside the case, so the compare chain
+// of the switch is paid once per item
+#define KML_VN_CASE(D)                                                                      \
+  case D:                                                                                   \
+    if (D <= DV) {                                                                          \
+      for (int r = 0; r < cnt; r++, v += 32, ad += 32 * dvm) {                              \
+        const uint32_t bit = vn_node<(D <= DV ? D : 1)>(msg, ad, chan[v]);                  \
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);                              \
+        if (lane == 0) dcur[g0 + r] = word;                                                 \
+      }                                                                                     \
+    }                                                                                       \
     break;
-#define KML_CN_CASE(D)                                  \
-  case D:                                               \
-    if (D <= DC) x = cn_node<(D <= DC ? D : 1), SOFT>(msg, plane, slot, &s_all); \
+#define KML_CN_CASE(D)                                                                      \
+  case D:                                                                                   \
+    if (D <= DC) {                                                                          \
+      for (int r = 0; r < cnt; r++, slot += 32) {                                           \
+        float s_all = 0.0f;                                                                 \
+        const uint32_t x = cn_node<(D <= DC ? D : 1), SOFT>(msg + slot * RS, &s_all);       \
+        fail |= (int)(x & 1u);                                                              \
+        if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);                         \
+      }                                                                                     \
+    }                                                                                       \
     break;
+#define KML_VN_LANE_CASE(D)                                                                 \
+  case D:                                                                                   \
+    if (D <= DV) bit = vn_node<(D <= DV ? D : 1)>(msg, ad, ch);                             \
+    break;
+#define KML_CN_LANE_CASE(D)                                                                 \
+  case D:                                                                                   \
+    if (D <= DC) x = cn_node<(D <= DC ? D : 1), SOFT>(row, s_all);                          \
+    break;
+
+// groups whose 32 nodes do not share a degree (irregular non-quasi-cyclic graphs, the ragged last group): per-lane
+// dispatch, kept out of line so the common path stays small
+template <int DV>
+__device__ __noinline__ uint32_t vn_lane_dispatch(uint32_t *msg, const uint16_t *ad, float ch, int deg) {
+  uint32_t bit = 0;
+  switch (deg) {
+    case 0: bit = (ch > 1.0f) ? 0u : 1u; break;
+    KML_VN_LANE_CASE(1) KML_VN_LANE_CASE(2) KML_VN_LANE_CASE(3) KML_VN_LANE_CASE(4) KML_VN_LANE_CASE(5) KML_VN_LANE_CASE(6)
+    KML_VN_LANE_CASE(7) KML_VN_LANE_CASE(8) KML_VN_LANE_CASE(9) KML_VN_LANE_CASE(10) KML_VN_LANE_CASE(11)
+    KML_VN_LANE_CASE(12) KML_VN_LANE_CASE(13) KML_VN_LANE_CASE(14) KML_VN_LANE_CASE(15) KML_VN_LANE_CASE(16)
+    default: break;
+  }
+  return bit;
+}
+template <int DC, bool SOFT>
+__device__ __noinline__ uint32_t cn_lane_dispatch(uint32_t *row, float *s_all, int deg) {
+  uint32_t x = 0;
+  switch (deg) {
+    KML_CN_LANE_CASE(1) KML_CN_LANE_CASE(2) KML_CN_LANE_CASE(3) KML_CN_LANE_CASE(4) KML_CN_LANE_CASE(5) KML_CN_LANE_CASE(6)
+    KML_CN_LANE_CASE(7) KML_CN_LANE_CASE(8) KML_CN_LANE_CASE(9) KML_CN_LANE_CASE(10) KML_CN_LANE_CASE(11)
+    KML_CN_LANE_CASE(12) KML_CN_LANE_CASE(13) KML_CN_LANE_CASE(14) KML_CN_LANE_CASE(15) KML_CN_LANE_CASE(16)
+    default: break;  // padding slot
+  }
+  return x;
+}
 
 constexpr int kGenericThreads = 384;  // 3 CTAs per SM at <= 56 registers
 
@@ -452,9 +503,10 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
   extern __shared__ uint32_t smem[];
   __shared__ int s_frame;
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, W = T >> 5;
-  const int plane = p.t.plane, n = p.t.n, dcm = p.t.dc_max, n_pad = p.t.n_pad;
-  uint32_t *msg = smem;                                  // [dc_max * plane]
-  float *chan = reinterpret_cast<float *>(smem + dcm * plane);  // [n]
+  constexpr int RS = DC | 1;  // odd row stride: lanes 0..31 of a check-node access hit 32 distinct banks
+  const int n = p.t.n, n_words = p.t.m_pad * RS;
+  uint32_t *msg = smem;                                  // [m_pad][RS]
+  float *chan = reinterpret_cast<float *>(smem + n_words);  // [n]
   uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);      // [2][words_n] decisions, double buffered
 
   while (true) {
@@ -465,7 +517,7 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     for (int v = tid; v < n; v += T)  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
       chan[v] = v < p.t.punct ? 1.0f : load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
-    for (int i = tid; i < dcm * plane; i += T) msg[i] = 0x3f800000u;
+    for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;
     __syncthreads();
 
     int ret = p.iters + (p.iters < p.max_iter);
@@ -476,42 +528,51 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
       last_t = t;
       uint32_t *dcur = dec + (t & 1) * p.words_n;
       for (int i = warp; i < p.t.vn_items_n; i += W) {
-        const int g = __ldg(p.t.vn_items + i);
-        if (g == 0xFFFF) continue;  // padding of a shorter list (warp-uniform)
-        const int v = g * 32 + lane;
-        uint32_t bit = 0;
-        if (v < n) {
-          // edges in the order the layout optimiser coloured them (= gather instruction index inside the warp)
-          const uint16_t *ad = p.t.vn_addr_t + v;
-          switch (__ldg(p.t.vn_deg + v)) {
-            case 0: bit = (chan[v] > 1.0f) ? 0u : 1u; break;
-            KML_VN_CASE(1) KML_VN_CASE(2) KML_VN_CASE(3) KML_VN_CASE(4) KML_VN_CASE(5) KML_VN_CASE(6) KML_VN_CASE(7) KML_VN_CASE(8)
-            KML_VN_CASE(9) KML_VN_CASE(10) KML_VN_CASE(11) KML_VN_CASE(12) KML_VN_CASE(13) KML_VN_CASE(14) KML_VN_CASE(15)
-            KML_VN_CASE(16)
-            default: break;
-          }
+        // item = first group | degree << 16 (0xFF = mixed degrees or ragged: per-lane dispatch) | number of groups << 24
+        const uint32_t item = __ldg(p.t.vn_items + i);
+        if (item == 0xFFFFFFFFu) continue;  // padding of a shorter list (warp-uniform)
+        const int g0 = item & 0xFFFF, cnt = (int)(item >> 24), dvm = p.t.dv_max;
+        // edges in the order the layout optimiser coloured them (= gather instruction index inside the warp)
+        const uint16_t *ad = p.t.vn_addr_g + (size_t)g0 * (32 * dvm) + lane;
+        int v = g0 * 32 + lane;
+        switch ((item >> 16) & 0xFF) {
+          KML_VN_CASE(1) KML_VN_CASE(2) KML_VN_CASE(3) KML_VN_CASE(4) KML_VN_CASE(5) KML_VN_CASE(6) KML_VN_CASE(7) KML_VN_CASE(8)
+          KML_VN_CASE(9) KML_VN_CASE(10) KML_VN_CASE(11) KML_VN_CASE(12) KML_VN_CASE(13) KML_VN_CASE(14) KML_VN_CASE(15)
+          KML_VN_CASE(16)
+          default:
+            for (int r = 0; r < cnt; r++, v += 32, ad += 32 * dvm) {
+              uint32_t bit = 0;
+              if (v < n) bit = vn_lane_dispatch<DV>(msg, ad, chan[v], (int)__ldg(p.t.vn_deg + v));
+              const uint32_t word = __ballot_sync(0xffffffffu, bit);
+              if (lane == 0) dcur[g0 + r] = word;
+            }
+            break;
         }
-        const uint32_t word = __ballot_sync(0xffffffffu, bit);
-        if (lane == 0) dcur[g] = word;
       }
       __syncthreads();
       int fail = 0;
       const float soft_before = soft;
       soft = 0.0f;
       for (int i = warp; i < p.t.cn_items_n; i += W) {
-        const int g = __ldg(p.t.cn_items + i);
-        if (g == 0xFFFF) continue;
-        const int slot = g * 32 + lane;
-        uint32_t x = 0;
-        float s_all = 0.0f;
-        switch (__ldg(p.t.cn_deg + slot)) {
+        const uint32_t item = __ldg(p.t.cn_items + i);
+        if (item == 0xFFFFFFFFu) continue;
+        const int cnt = (int)(item >> 24);
+        int slot = (item & 0xFFFF) * 32 + lane;
+        switch ((item >> 16) & 0xFF) {
           KML_CN_CASE(1) KML_CN_CASE(2) KML_CN_CASE(3) KML_CN_CASE(4) KML_CN_CASE(5) KML_CN_CASE(6) KML_CN_CASE(7) KML_CN_CASE(8)
           KML_CN_CASE(9) KML_CN_CASE(10) KML_CN_CASE(11) KML_CN_CASE(12) KML_CN_CASE(13) KML_CN_CASE(14) KML_CN_CASE(15)
           KML_CN_CASE(16)
-          default: continue;  // padding slot
+          default:
+            for (int r = 0; r < cnt; r++, slot += 32) {
+              float s_all = 0.0f;
+              const int deg = (int)__ldg(p.t.cn_deg + slot);
+              if (deg == 0) continue;  // padding slot
+              const uint32_t x = cn_lane_dispatch<DC, SOFT>(msg + slot * RS, &s_all, deg);
+              fail |= (int)(x & 1u);
+              if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
+            }
+            break;
         }
-        fail |= (int)(x & 1u);
-        if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
       }
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -537,6 +598,8 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
 }
 #undef KML_VN_CASE
 #undef KML_CN_CASE
+#undef KML_VN_LANE_CASE
+#undef KML_CN_LANE_CASE
 
 dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
   if (alg != 0) return minsum_kernel_of(k, alg);
@@ -582,6 +645,7 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
 }  // namespace
 
 int dec_generic_max_threads() { return kGenericThreads; }
+int dec_generic_row_stride(DecKernelKind k) { return k == DEC_GEN_4_8 ? 9 : k == DEC_GEN_9_10 ? 11 : 17; }
 
 int dec_regular_threads(DecKernelKind k) {
   if (k == DEC_REG_12_6) return 672;
@@ -589,7 +653,8 @@ int dec_regular_threads(DecKernelKind k) {
 }
 
 bool dec_wants_rowmajor(DecKernelKind k, int alg) {
-  if (alg != 0 || (k != DEC_REG_6_3 && k != DEC_REG_12_6)) return false;
+  if (alg != 0) return false;
+  if (k != DEC_REG_6_3 && k != DEC_REG_12_6) return true;  // generic sum-product kernel: always its own row-major tables
   const char *e = getenv("KML_DEC_PLANAR");  // A/B knob: the planar layout for the regular sum-product kernels too
   return !(e && atoi(e));
 }

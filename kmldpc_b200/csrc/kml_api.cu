@@ -56,9 +56,10 @@ struct kml_ctx {
   DevBuf<float2> points;
   DevBuf<int32_t> row_ptr, col_idx, km_nb;
   int km_n_nb = 0;
-  DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_t, vn_items, cn_items, col_ell;
+  DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
+  DevBuf<uint32_t> vn_items, cn_items;
   int ell_width = 0;
-  DevBuf<uint8_t> vn_deg, cn_deg;
+  DevBuf<uint8_t> vn_deg, cn_deg, cn_deg_rm;
   DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
   DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
   float alpha = 0.8f;
@@ -198,16 +199,12 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
         if (e >= 0) vaddr[(size_t)v * dv_tab + vdeg[v]++] = (uint16_t)(pos[e] * pos_stride + slot[erow[e]] * slot_stride);
       }
   };
+  const bool regular_kind = dl.kind == DEC_REG_6_3 || dl.kind == DEC_REG_12_6;
+  const int planar_smem = regular_kind ? 6 * plane * 4 : dl.smem_bytes;
   std::vector<uint16_t> vaddr;
-  const bool rowmajor = dec_wants_rowmajor(dl.kind, 0);
-  if (rowmajor) {  // check nodes of the regular kernels read their six words with LDS.64: 6 * slot + k
-    int res_rm = 0;
-    build_addr(1, 6, vaddr, &res_rm, &c->layout_excess);
-    KML_CUDA(c, c->vn_addr_rm.alloc(vaddr.size()));
-    KML_CUDA(c, cudaMemcpy(c->vn_addr_rm.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  }
+  // ---- planar tables: the min-sum kernels (and the sum-product kernels under KML_DEC_PLANAR=1)
   build_addr(plane, 1, vaddr, &c->layout_residual, &c->layout_excess_planar);
-  if (!rowmajor) c->layout_excess = c->layout_excess_planar;
+  c->layout_excess = c->layout_excess_planar;
   KML_CUDA(c, c->vn_addr.alloc(vaddr.size()));
   KML_CUDA(c, cudaMemcpy(c->vn_addr.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   KML_CUDA(c, c->vn_deg.alloc(N));
@@ -217,59 +214,102 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   c->dt.vn_addr = c->vn_addr.p; c->dt.vn_deg = c->vn_deg.p; c->dt.cn_deg = c->cn_deg.p;
   c->dt.n = N; c->dt.m_pad = mpad; c->dt.plane = plane; c->dt.n_tx = c->n_tx; c->dt.punct = c->punct;
   c->dt.dv_max = dv_tab; c->dt.dc_max = dcm;
-  {
-    // generic sum-product kernel: transposed address lists (a warp's 32 loads = one 64-byte line) and warp work lists
-    // balanced by node degree — longest-processing-time first over the CTA's warps, then laid out [round][warp]
-    const int n_pad = (N + 31) & ~31, W = dl.threads / 32;
-    std::vector<uint16_t> vt((size_t)dv_tab * n_pad, 0xFFFFu);
+  c->dt.n_pad = (N + 31) & ~31;
+  c->dt_rm = c->dt;
+  // ---- row-major tables of the sum-product kernels: word = row_stride * slot + k
+  const bool rowmajor = dec_wants_rowmajor(dl.kind, 0);
+  int rm_smem = planar_smem;
+  if (rowmajor && regular_kind) {  // check nodes read their six words with LDS.64
+    int res_rm = 0;
+    build_addr(1, 6, vaddr, &res_rm, &c->layout_excess);
+    KML_CUDA(c, c->vn_addr_rm.alloc(vaddr.size()));
+    KML_CUDA(c, cudaMemcpy(c->vn_addr_rm.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    c->dt_rm.vn_addr = c->vn_addr_rm.p; c->dt_rm.plane = 1;
+    rm_smem = 6 * mpad * 4;
+  } else if (rowmajor) {
+    // generic kernel: odd row stride; address lists per warp item as [edge k][lane] (a warp's 32 loads = one 64-byte
+    // line at an immediate offset); warp work lists balanced by node degree — longest-processing-time first over the
+    // CTA's warps, then laid out [round][warp]
+    const int rs = dec_generic_row_stride(dl.kind), n_pad = c->dt.n_pad, W = dl.threads / 32;
+    if ((size_t)mpad * rs >= 0xFFFFu) return fail_arg(c, "code too large for 16-bit shared-memory edge addresses");
+    int res_rm = 0;
+    build_addr(1, rs, vaddr, &res_rm, &c->layout_excess);  // also refills vdeg / cndeg for THIS slot assignment
+    std::vector<uint16_t> vg((size_t)n_pad * dv_tab, 0xFFFFu);
     for (int v = 0; v < N; v++)
-      for (int k = 0; k < dv_tab; k++) vt[(size_t)k * n_pad + v] = vaddr[(size_t)v * dv_tab + k];
-    auto balance = [&](int n_groups, auto group_cost, std::vector<uint16_t> &items) {
-      std::vector<int> ord(n_groups);
-      for (int g = 0; g < n_groups; g++) ord[g] = g;
-      std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return group_cost(a) > group_cost(b); });
-      std::vector<std::vector<int>> mine(W);
+      for (int k = 0; k < dv_tab; k++) vg[((size_t)(v / 32) * dv_tab + k) * 32 + (v & 31)] = vaddr[(size_t)v * dv_tab + k];
+    // Work lists: a warp item is a RUN of consecutive groups with one degree (quasi-cyclic codes: Z / 32 groups per block
+    // column), so the per-item dispatch overhead is paid once per run.  Runs are cut into chunks of at most half a
+    // warp's share, and the chunks are placed longest-processing-time first.  Cost model (issue slots, from the SASS):
+    // 30 per item + 17 per group + 22 per edge of a lane.
+    auto balance = [&](int n_groups, auto group_deg, std::vector<uint32_t> &items) {
+      struct Run { int g, deg, cnt; long cost; };
+      auto gcost = [](int deg) { return 17L + 22L * std::max(deg == 0xFF ? 16 : deg, 1); };
+      std::vector<Run> runs;
+      long total = 0;
+      for (int g = 0; g < n_groups; g++) {
+        int lo, hi;
+        group_deg(g, &lo, &hi);
+        if (hi < 0) continue;  // nothing to do in this group
+        const int deg = lo == hi ? hi : 0xFF;  // mixed degrees: looked up per lane
+        total += gcost(deg);
+        if (!runs.empty() && deg != 0xFF && runs.back().deg == deg && runs.back().g + runs.back().cnt == g) runs.back().cnt++;
+        else runs.push_back({g, deg, 1, 0});
+      }
+      const long target = std::max<long>(total / W, 1);
+      std::vector<Run> chunks;
+      for (const Run &r : runs) {
+        const int mc = (int)std::min<long>(255, std::max<long>(1, target / (2 * gcost(r.deg))));
+        for (int g = r.g, left = r.cnt; left > 0;) {
+          const int k = std::min(left, mc);
+          chunks.push_back({g, r.deg, k, 30 + k * gcost(r.deg)});
+          g += k;
+          left -= k;
+        }
+      }
+      std::stable_sort(chunks.begin(), chunks.end(), [](const Run &a, const Run &b) { return a.cost > b.cost; });
+      std::vector<std::vector<uint32_t>> mine(W);
       std::vector<long> load(W, 0);
-      for (int g : ord) {
-        if (group_cost(g) == 0) continue;  // nothing to do in this group
+      for (const Run &ch : chunks) {
         const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-        mine[w].push_back(g);
-        load[w] += group_cost(g) + 2;  // + loop / dispatch overhead of an item
+        mine[w].push_back((uint32_t)ch.g | ((uint32_t)ch.deg << 16) | ((uint32_t)ch.cnt << 24));
+        load[w] += ch.cost;
       }
       size_t rounds = 0;
       for (auto &m : mine) rounds = std::max(rounds, m.size());
-      items.assign(rounds * W, 0xFFFFu);
-      for (int w = 0; w < W; w++)
-        for (size_t i = 0; i < mine[w].size(); i++) items[i * W + w] = (uint16_t)mine[w][i];
+      items.assign(rounds * W, 0xFFFFFFFFu);
+      for (int ww = 0; ww < W; ww++)
+        for (size_t i = 0; i < mine[ww].size(); i++) items[i * W + ww] = mine[ww][i];
     };
-    std::vector<uint16_t> vi, ci;
-    balance(n_pad / 32, [&](int g) {
-      int d = 1;  // degree-0 variables still report a decision
-      for (int v = g * 32; v < std::min(N, g * 32 + 32); v++) d = std::max<int>(d, vdeg[v]);
-      return d;
+    std::vector<uint32_t> vi, ci;
+    balance(n_pad / 32, [&](int g, int *lo, int *hi) {
+      *lo = 255; *hi = 0;
+      for (int v = g * 32; v < std::min(N, g * 32 + 32); v++) { *lo = std::min<int>(*lo, vdeg[v]); *hi = std::max<int>(*hi, vdeg[v]); }
+      // ragged last group and degree-0 variables (they still report a decision): per-lane dispatch
+      if (g * 32 + 32 > N || *lo == 0) { *lo = 0; *hi = std::max(*hi, 1); }
     }, vi);
-    balance(mpad / 32, [&](int g) {
-      int d = 0;
-      for (int sl = g * 32; sl < g * 32 + 32; sl++) d = std::max<int>(d, cndeg[sl]);
-      return d;
+    balance(mpad / 32, [&](int g, int *lo, int *hi) {
+      *lo = 255; *hi = 0;
+      for (int sl = g * 32; sl < g * 32 + 32; sl++) { *lo = std::min<int>(*lo, cndeg[sl]); *hi = std::max<int>(*hi, cndeg[sl]); }
+      if (*hi == 0) *hi = -1;  // padding slots only
     }, ci);
-    KML_CUDA(c, c->vn_addr_t.alloc(vt.size()));
-    KML_CUDA(c, cudaMemcpy(c->vn_addr_t.p, vt.data(), vt.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->vn_addr_g.alloc(vg.size()));
+    KML_CUDA(c, cudaMemcpy(c->vn_addr_g.p, vg.data(), vg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    KML_CUDA(c, c->cn_deg_rm.alloc(mpad));
+    KML_CUDA(c, cudaMemcpy(c->cn_deg_rm.p, cndeg.data(), mpad, cudaMemcpyHostToDevice));
     KML_CUDA(c, c->vn_items.alloc(vi.size()));
-    KML_CUDA(c, cudaMemcpy(c->vn_items.p, vi.data(), vi.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    KML_CUDA(c, cudaMemcpy(c->vn_items.p, vi.data(), vi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->cn_items.alloc(ci.size()));
-    KML_CUDA(c, cudaMemcpy(c->cn_items.p, ci.data(), ci.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    c->dt.vn_addr_t = c->vn_addr_t.p; c->dt.vn_items = c->vn_items.p; c->dt.cn_items = c->cn_items.p;
-    c->dt.n_pad = n_pad; c->dt.vn_items_n = (int)vi.size(); c->dt.cn_items_n = (int)ci.size();
+    KML_CUDA(c, cudaMemcpy(c->cn_items.p, ci.data(), ci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->dt_rm.vn_addr = nullptr; c->dt_rm.plane = 1; c->dt_rm.cn_deg = c->cn_deg_rm.p;
+    c->dt_rm.vn_addr_g = c->vn_addr_g.p; c->dt_rm.vn_items = c->vn_items.p; c->dt_rm.cn_items = c->cn_items.p;
+    c->dt_rm.vn_items_n = (int)vi.size(); c->dt_rm.cn_items_n = (int)ci.size();
+    rm_smem = (mpad * rs + N + 2 * c->words_n) * 4;
+    if (rm_smem > 227 * 1024) return fail_arg(c, "code too large for one frame per SM in shared memory");
   }
-  c->dt_rm = c->dt;
-  c->dt_rm.vn_addr = c->vn_addr_rm.p; c->dt_rm.plane = 1;
   for (int alg = 0; alg < 3; alg++) {
     dl.alg = alg;
     dl.rowmajor = (alg == 0 && rowmajor) ? 1 : 0;
-    if (dl.kind == DEC_REG_6_3) dl.threads = alg == 0 ? dec_regular_threads(dl.kind) : 384;
-    if (dl.rowmajor) dl.smem_bytes = 6 * mpad * 4;
-    else if (dl.kind == DEC_REG_6_3 || dl.kind == DEC_REG_12_6) dl.smem_bytes = 6 * plane * 4;
+    dl.smem_bytes = dl.rowmajor ? rm_smem : planar_smem;
     KML_CUDA(c, dec_prepare(dl));
     c->dl_alg[alg] = dl;
   }
@@ -456,7 +496,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
   c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
-  c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_t.release(); c->vn_items.release(); c->cn_items.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_g.release(); c->vn_items.release(); c->cn_items.release(); c->cn_deg_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }

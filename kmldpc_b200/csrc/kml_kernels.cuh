@@ -17,10 +17,11 @@ struct DecTables {
   const uint8_t *vn_deg;    // [n]
   const uint8_t *cn_deg;    // [m_pad] degree of the row held by a slot (0 = padding)
   int n, m_pad, plane, n_tx, punct, dv_max, dc_max;  // m_pad = row slots (multiple of 32), plane = m_pad + 1
-  // generic sum-product kernel: transposed address lists and degree-balanced warp work lists
-  const uint16_t *vn_addr_t;  // [dv_max][n_pad]
-  const uint16_t *vn_items;   // [vn_items_n] groups of 32 variables, laid out [round][warp]; 0xFFFF = none
-  const uint16_t *cn_items;   // [cn_items_n] groups of 32 row slots, same layout
+  // generic sum-product kernel: per-item address lists and degree-balanced warp work lists
+  const uint16_t *vn_addr_g;  // [n_pad / 32][dv_max][32]
+  const uint32_t *vn_items;   // [vn_items_n] run of groups of 32 variables: first group | degree << 16 (0xFF = mixed) |
+                              // number of groups << 24, laid out [round][warp]; 0xFFFFFFFF = none
+  const uint32_t *cn_items;   // [cn_items_n] groups of 32 row slots, same layout
   int n_pad, vn_items_n, cn_items_n;
 };
 
@@ -46,7 +47,7 @@ struct DecLaunch {
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
-  int rowmajor;     // regular sum-product kernels: messages at 6 * slot + k (DecTables of that layout) instead of planar
+  int rowmajor;     // sum-product kernels: messages at row_stride * slot + k (their own DecTables) instead of planar
 };
 
 typedef void (*dec_kernel_t)(const DecParams);
@@ -55,6 +56,7 @@ inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 &
 bool dec_wants_rowmajor(DecKernelKind k, int alg);
 int dec_regular_threads(DecKernelKind k);
 int dec_generic_max_threads();
+int dec_generic_row_stride(DecKernelKind k);
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 
