@@ -472,3 +472,55 @@ def test_parity_statistics_at_scale(name, frames, kb):
     assert stats["converged_bits_same"] >= 0.9999, stats
     assert stats["frame_error_same"] >= 0.999, stats
     link.close()
+
+
+def _write_irregular_code(path, m, n, col_degs, seed):
+    """A random irregular parity-check matrix in the reference's file format: [A | staircase], full row rank, column
+    degrees of A drawn from col_degs WITHOUT any 32-wide regularity (so warp groups mix degrees), one all-zero column."""
+    rng = np.random.default_rng(seed)
+    rows = [set() for _ in range(m)]
+    for c in range(n - m):
+        d = 0 if c == 5 else int(rng.choice(col_degs))
+        load = np.array([len(r) for r in rows], dtype=np.float64)
+        for r in rng.choice(m, size=d, replace=False, p=(1.0 / (1.0 + load) ** 2) / (1.0 / (1.0 + load) ** 2).sum()):
+            rows[int(r)].add(c)
+    for r in range(m):  # staircase: rank m
+        rows[r].add(n - m + r)
+        if r > 0:
+            rows[r].add(n - m + r - 1)
+    with open(path, "w") as f:
+        f.write("num_of_row--num_of_col--rank_of_H\n%d\t%d\t%d\nno_of_row--degree_of_row--no_of_col\n" % (m, n, m))
+        for r in range(m):
+            cs = sorted(rows[r])
+            f.write("%d %d %s \n" % (r, len(cs), " ".join(map(str, cs))))
+    return max(len(r) for r in rows)
+
+
+@pytest.mark.parametrize("m,n,col_degs,seed,snr", [(150, 334, (1, 2, 3, 4), 1, 3.0), (120, 300, (2, 3, 3, 3, 12), 2, 12.0)])
+def test_generic_decoder_on_irregular_ragged_graph(tmp_path, m, n, col_degs, seed, snr):
+    """The run-time-graph kernel away from the quasi-cyclic case: mixed degrees inside every 32-node group (per-lane
+    dispatch), N not a multiple of 32, a degree-0 variable, degree-1 staircase end — against the oracle's decoder."""
+    path = str(tmp_path / "irregular.txt")
+    dc = _write_irregular_code(path, m, n, col_degs, seed)
+    assert dc <= 16
+    name = "irregular_%d" % seed
+    util.CASES[name] = (path, "2bits_4PSK.txt", snr, {})
+    try:
+        olink, rs = util.oracle_frames(name, 150)
+        link = util.gpu_link(name)
+        llr = np.stack([util.llr_of_p0(r.p0) for r in rs]).astype(np.float32)
+        cc, uu, ret = link.decode(llr)
+        ref_ret = np.array([r.ret for r in rs])
+        assert np.array_equal(ret, ref_ret), np.where(ret != ref_ret)[0][:5]
+        conv = np.array([olink.code.parity_check(r.cc_hat) for r in rs]) == 0
+        assert 10 < conv.sum()
+        assert np.array_equal(cc[conv], np.stack([r.cc_hat for r in rs])[conv])
+        assert np.array_equal(uu[conv], np.stack([r.uu_hat for r in rs])[conv])
+        # the chained receiver on the same frames
+        y = np.stack([r.y for r in rs])
+        uu_p, hhat, kstar, ret2 = link.receive(y, 10 ** (-snr / 10))
+        assert np.array_equal(kstar, [r.kstar for r in rs]) and np.array_equal(ret2, ref_ret)
+        link.close()
+    finally:
+        util.CASES.pop(name, None)
+        util.oracle_frames.cache_clear()
