@@ -23,6 +23,7 @@
 // coalesced) and the packed decisions (1 bit/variable) touches HBM.
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 
 #include "kml_internal.h"
 #include "kml_kernels.cuh"
@@ -344,15 +345,12 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float2 swap2(float2 a) { return make_float2(a.y, a.x); }
 
+// a[k] = shared-memory word address of the variable's k-th edge
 template <int D>
-__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, float ch) {
-  uint32_t a[D];
+__device__ __forceinline__ uint32_t vn_core(uint32_t *msg, const uint32_t *a, float ch) {
   float x[D];
 #pragma unroll
-  for (int k = 0; k < D; k++) {
-    a[k] = __ldg(ad + k * 32);
-    x[k] = __uint_as_float(msg[a[k]]);
-  }
+  for (int k = 0; k < D; k++) x[k] = __uint_as_float(msg[a[k]]);
   // P[i] = (pre_i, suf_{D-i}):  pre_i = ch x_0 … x_{i-1},  suf_j = x_j … x_{D-1}
   float2 P[D + 1];
   P[0] = make_float2(ch, 1.0f);
@@ -375,6 +373,14 @@ __device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, f
     }
   }
   return bit;
+}
+
+template <int D>
+__device__ __forceinline__ uint32_t vn_node(uint32_t *msg, const uint16_t *ad, float ch) {
+  uint32_t a[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) a[k] = __ldg(ad + k * 32);
+  return vn_core<D>(msg, a, ch);
 }
 
 // c2v ratios of a pair of outputs (select-based inversion, as the regular kernel's RATIO = 1)
@@ -601,8 +607,130 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
 #undef KML_VN_LANE_CASE
 #undef KML_CN_LANE_CASE
 
-dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
+// ---------------------------------------------------------------------------------------------------------------
+// Quasi-cyclic codes with a compile-time plan: the block structure (which block columns / block rows a thread serves,
+// and their degrees) is a template argument, so the node updates are fully unrolled, the edge addresses and channel
+// ratios live in registers and nothing is dispatched at run time — the regular kernel's organisation for an
+// irregular graph.  The CTA's 4 * Z threads form 4 "quarters" of Z threads; thread z of quarter q serves node z of
+// every block in the quarter's list.  The lists balance the edges per thread (19/19/19/20 for BG2).
+// The host (kml_api.cu) checks that the loaded graph has exactly this block structure before choosing the kernel;
+// any other graph runs bp_generic_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct QcPlanBg2R12 {  // 5G NR BG2 truncated to 12 block rows x 22 block columns (rate 1/2 after puncturing 2 Z), Z = 96:
+                       // config/5GLDPCBG2a3_R12_K960.txt in the column order the reference's elimination leaves
+  static constexpr int Z = 96, MAXV = 6, MAXC = 3, DVM = 9, RS = 11;
+  static constexpr int vblk[4][6] = {{0, 5, 3, 14, 15, -1}, {1, 9, 4, 16, 17, -1}, {7, 6, 8, 2, 18, 19}, {11, 10, 13, 12, 20, 21}};
+  static constexpr int vdeg[4][6] = {{9, 5, 3, 1, 1, 0}, {9, 5, 3, 1, 1, 0}, {7, 4, 4, 2, 1, 1}, {7, 4, 4, 3, 1, 1}};
+  static constexpr int cblk[4][3] = {{1, 9, 4}, {3, 10, 8}, {0, 5, 11}, {2, 6, 7}};
+  static constexpr int cdeg[4][3] = {{10, 5, 4}, {10, 5, 4}, {8, 6, 5}, {8, 6, 6}};
+};
+
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
+  (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+  static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
+}
+
+template <class P, int Q>
+__device__ __forceinline__ constexpr int qc_voff(int i) {  // edges of the quarter's variables before variable i
+  int o = 0;
+  for (int j = 0; j < i; j++) o += P::vdeg[Q][j];
+  return o;
+}
+
+// One quarter's whole decoding loop.  All quarters execute the same sequence of barriers (frame queue, iteration count
+// and exit decisions are CTA-uniform), so the BAR instructions of the four instances pair up.
+template <class P, int Q>
+__device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, volatile int *s_frame, int z) {
+  constexpr int NE = qc_voff<P, Q>(P::MAXV);
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t va[NE];
+  static_for<P::MAXV>([&](auto ic) {
+    constexpr int i = decltype(ic)::value, D = P::vdeg[Q][i], O = qc_voff<P, Q>(i);
+    if constexpr (D > 0) {
+      const int v = P::vblk[Q][i] * P::Z + z;
+#pragma unroll
+      for (int k = 0; k < D; k++) va[O + k] = __ldg(p.t.vn_addr + (size_t)v * P::DVM + k);
+    }
+  });
+  const int n_words = p.t.m_pad * P::RS;
+  while (true) {
+    if (tid == 0) *s_frame = (int)atomicAdd(p.work_counter, 1u);
+    __syncthreads();
+    const int f = *s_frame;
+    if (f >= p.B) break;
+    const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
+    float ch[P::MAXV];
+    static_for<P::MAXV>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      ch[i] = 1.0f;
+      if constexpr (P::vdeg[Q][i] > 0) {
+        const int v = P::vblk[Q][i] * P::Z + z;  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
+        if (v >= p.t.punct) ch[i] = load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
+      }
+    });
+    for (int i = tid; i < n_words; i += blockDim.x) msg[i] = 0x3f800000u;
+    __syncthreads();
+
+    uint32_t bits = 0, latched_bits = 0;
+    int ret = p.iters + (p.iters < p.max_iter);
+    bool latched = false;
+    for (int t = 0; t < p.iters; t++) {
+      bits = 0;
+      static_for<P::MAXV>([&](auto ic) {
+        constexpr int i = decltype(ic)::value, D = P::vdeg[Q][i], O = qc_voff<P, Q>(i);
+        if constexpr (D > 0) bits |= vn_core<D>(msg, va + O, ch[i]) << i;
+      });
+      __syncthreads();
+      int fail = 0;
+      static_for<P::MAXC>([&](auto jc) {
+        constexpr int j = decltype(jc)::value, D = P::cdeg[Q][j];
+        float unused;
+        fail |= (int)(cn_node<D, false>(msg + (P::cblk[Q][j] * P::Z + z) * P::RS, &unused) & 1u);
+      });
+      const int any_fail = __syncthreads_or(fail);
+      if (!any_fail && !latched) {
+        latched = true;
+        latched_bits = bits;
+        ret = t + (t < p.max_iter);
+        if (p.early_exit) break;  // the reference leaves BEFORE the check phase; its c2v are never read again
+      }
+    }
+    if (!latched) latched_bits = bits;
+    static_for<P::MAXV>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      if constexpr (P::vdeg[Q][i] > 0) {
+        const uint32_t word = __ballot_sync(0xffffffffu, (latched_bits >> i) & 1u);
+        if (lane == 0) p.out_bits[(size_t)f * p.words_n + ((P::vblk[Q][i] * P::Z + z) >> 5)] = word;
+      }
+    });
+    if (tid == 0) p.out_ret[f] = ret;
+  }
+}
+
+template <class P, int MINB>
+__global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p) {
+  static_assert(P::Z % 32 == 0, "a warp must not straddle two quarters");
+  extern __shared__ uint32_t msg[];  // [m_pad][RS]
+  __shared__ int s_frame;
+  const int q = threadIdx.x / P::Z, z = threadIdx.x % P::Z;
+  switch (q) {  // warp-uniform
+    case 0: qc_quarter<P, 0>(p, msg, &s_frame, z); break;
+    case 1: qc_quarter<P, 1>(p, msg, &s_frame, z); break;
+    case 2: qc_quarter<P, 2>(p, msg, &s_frame, z); break;
+    default: qc_quarter<P, 3>(p, msg, &s_frame, z); break;
+  }
+}
+
+dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan = 0) {
   if (alg != 0) return minsum_kernel_of(k, alg);
+  if (qc_plan == 1 && !soft) {
+    const char *e = getenv("KML_DEC_QC_MINB");  // A/B knob
+    return (e && atoi(e) == 2) ? bp_qc_kernel<QcPlanBg2R12, 2> : bp_qc_kernel<QcPlanBg2R12, 3>;
+  }
   if (soft && k == DEC_REG_6_3)
     return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
   if (soft && k == DEC_REG_12_6)
@@ -645,6 +773,34 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft) {
 }  // namespace
 
 int dec_generic_max_threads() { return kGenericThreads; }
+
+// Does the graph (degrees per variable / per row slot of the row-major layout) have the block structure of a compiled
+// quasi-cyclic plan?  Returns the plan id (1 = QcPlanBg2R12) or 0.
+int dec_match_qc_plan(int n, int m_pad, const uint8_t *vdeg, const uint8_t *cndeg, int dv_max, int row_stride) {
+  using P = QcPlanBg2R12;
+  const char *e = getenv("KML_DEC_NO_QC");  // A/B knob: run the generic kernel instead
+  if (e && atoi(e)) return 0;
+  if (n != 22 * P::Z || m_pad != 12 * P::Z || dv_max != P::DVM || row_stride != P::RS) return 0;
+  int seen_v[22] = {0}, seen_c[12] = {0};
+  for (int q = 0; q < 4; q++) {
+    for (int i = 0; i < P::MAXV; i++) {
+      if (P::vdeg[q][i] == 0) continue;
+      const int b = P::vblk[q][i];
+      seen_v[b]++;
+      for (int zz = 0; zz < P::Z; zz++)
+        if (vdeg[b * P::Z + zz] != P::vdeg[q][i]) return 0;
+    }
+    for (int j = 0; j < P::MAXC; j++) {
+      const int b = P::cblk[q][j];
+      seen_c[b]++;
+      for (int zz = 0; zz < P::Z; zz++)
+        if (cndeg[b * P::Z + zz] != P::cdeg[q][j]) return 0;
+    }
+  }
+  for (int b = 0; b < 22; b++) if (seen_v[b] != 1) return 0;
+  for (int b = 0; b < 12; b++) if (seen_c[b] != 1) return 0;
+  return 1;
+}
 int dec_generic_row_stride(DecKernelKind k) { return k == DEC_GEN_4_8 ? 9 : k == DEC_GEN_9_10 ? 11 : 17; }
 
 int dec_regular_threads(DecKernelKind k) {
@@ -660,7 +816,7 @@ bool dec_wants_rowmajor(DecKernelKind k, int alg) {
 }
 
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false);
+  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false, l.qc_plan);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -684,7 +840,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  kernel_of(l.kind, l.alg, l.rowmajor, p.out_soft != nullptr)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  kernel_of(l.kind, l.alg, l.rowmajor, p.out_soft != nullptr, l.qc_plan)<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

@@ -218,7 +218,7 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   c->dt_rm = c->dt;
   // ---- row-major tables of the sum-product kernels: word = row_stride * slot + k
   const bool rowmajor = dec_wants_rowmajor(dl.kind, 0);
-  int rm_smem = planar_smem;
+  int rm_smem = planar_smem, qc_plan = 0;
   if (rowmajor && regular_kind) {  // check nodes read their six words with LDS.64
     int res_rm = 0;
     build_addr(1, 6, vaddr, &res_rm, &c->layout_excess);
@@ -300,7 +300,10 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     KML_CUDA(c, cudaMemcpy(c->vn_items.p, vi.data(), vi.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->cn_items.alloc(ci.size()));
     KML_CUDA(c, cudaMemcpy(c->cn_items.p, ci.data(), ci.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    c->dt_rm.vn_addr = nullptr; c->dt_rm.plane = 1; c->dt_rm.cn_deg = c->cn_deg_rm.p;
+    KML_CUDA(c, c->vn_addr_rm.alloc(vaddr.size()));  // [v][dv_max] in the same layout: the quasi-cyclic kernel's lists
+    KML_CUDA(c, cudaMemcpy(c->vn_addr_rm.p, vaddr.data(), vaddr.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    qc_plan = dec_match_qc_plan(N, mpad, vdeg.data(), cndeg.data(), dv_tab, rs);
+    c->dt_rm.vn_addr = c->vn_addr_rm.p; c->dt_rm.plane = 1; c->dt_rm.cn_deg = c->cn_deg_rm.p;
     c->dt_rm.vn_addr_g = c->vn_addr_g.p; c->dt_rm.vn_items = c->vn_items.p; c->dt_rm.cn_items = c->cn_items.p;
     c->dt_rm.vn_items_n = (int)vi.size(); c->dt_rm.cn_items_n = (int)ci.size();
     rm_smem = (mpad * rs + N + 2 * c->words_n) * 4;
@@ -309,6 +312,7 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   for (int alg = 0; alg < 3; alg++) {
     dl.alg = alg;
     dl.rowmajor = (alg == 0 && rowmajor) ? 1 : 0;
+    dl.qc_plan = alg == 0 ? qc_plan : 0;
     dl.smem_bytes = dl.rowmajor ? rm_smem : planar_smem;
     KML_CUDA(c, dec_prepare(dl));
     c->dl_alg[alg] = dl;

@@ -47,6 +47,7 @@ struct DecLaunch {
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
+  int qc_plan;      // != 0: the graph matches a compiled quasi-cyclic plan (bp_qc_kernel); sum-product, no soft output
   int rowmajor;     // sum-product kernels: messages at row_stride * slot + k (their own DecTables) instead of planar
 };
 
@@ -57,6 +58,7 @@ bool dec_wants_rowmajor(DecKernelKind k, int alg);
 int dec_regular_threads(DecKernelKind k);
 int dec_generic_max_threads();
 int dec_generic_row_stride(DecKernelKind k);
+int dec_match_qc_plan(int n, int m_pad, const uint8_t *vdeg, const uint8_t *cndeg, int dv_max, int row_stride);
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 
