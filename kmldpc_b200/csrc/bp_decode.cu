@@ -734,7 +734,9 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
   if (soft && k == DEC_REG_6_3)
     return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
   if (soft && k == DEC_REG_12_6)
-    return rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, true, true> : bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>;
+    return !rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>
+                     : dec_regular_threads(k) == 1008 ? bp_regular_kernel<8, 4, 1008, 1, true, 2, true, true>
+                                                      : bp_regular_kernel<12, 6, 672, 1, true, 2, true, true>;
   switch (k) {
     case DEC_REG_6_3: {
       const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
@@ -759,7 +761,9 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
     }
     case DEC_REG_12_6: {
       const char *re = getenv("KML_DEC_RATIO");
-      const int r8 = re ? atoi(re) : 2;  // one CTA per SM: the predicated reciprocal wins here (measured)
+      const int r8 = re ? atoi(re) : 1;
+      if (rowmajor && dec_regular_threads(k) == 1008)
+        return r8 == 2 ? bp_regular_kernel<8, 4, 1008, 1, true, 2, true> : bp_regular_kernel<8, 4, 1008, 1, true, 1, true>;
       return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
                       : bp_regular_kernel<12, 6, 672, 1>;
     }
@@ -804,7 +808,12 @@ int dec_match_qc_plan(int n, int m_pad, const uint8_t *vdeg, const uint8_t *cnde
 int dec_generic_row_stride(DecKernelKind k) { return k == DEC_GEN_4_8 ? 9 : k == DEC_GEN_9_10 ? 11 : 17; }
 
 int dec_regular_threads(DecKernelKind k) {
-  if (k == DEC_REG_12_6) return 672;
+  if (k == DEC_REG_12_6) {
+    // 1008 threads x (8 variables, 4 checks): 32 warps on the SM's single CTA instead of 21 (4.60 -> 4.19 ms per 4096
+    // frames); KML_DEC_T8064=672 is the A/B knob for the 672 x (12, 6) shape, which the planar layout also uses
+    const char *e = getenv("KML_DEC_T8064");
+    return (!(e && atoi(e) == 672) && dec_wants_rowmajor(k, 0)) ? 1008 : 672;
+  }
   return 384;  // (576 threads x (4 variables, 2 checks), 2 CTAs per SM measured 7 % slower)
 }
 
