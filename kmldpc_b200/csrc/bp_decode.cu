@@ -113,7 +113,8 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
 
 // ---------------------------------------------------------------------------------------------------------------
-// (3,6)-regular codes (PEG2304, PEG8064): N = VPT * T variables, M = CPT * T checks, everything unrolled,
+// (3,6)-regular codes (PEG2304, PEG8064): NV <= VPT * T variables, NV / 2 <= CPT * T checks (the last round of a
+// thread may be empty when the tiling is not exact), everything unrolled,
 // edge addresses and channel ratios resident in registers.
 // ---------------------------------------------------------------------------------------------------------------
 //
@@ -125,13 +126,17 @@ __device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
 //   ROWM = true  ("row-major"): at word 6 * slot + phys(k) — the six words of a check are contiguous and move as
 //                               3 LDS.64 + 3 STS.64 (a half-warp covers 16 distinct even banks: conflict free), which
 //                               takes one issue slot per edge-iteration out of this issue-bound kernel.
-template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false, bool SOFT = false>
+template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false, bool SOFT = false,
+          int NV = VPT * T>
 __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
+  static_assert(T % 32 == 0 && NV % 64 == 0 && NV <= VPT * T && NV / 2 <= CPT * T, "warps must line up with the 32-node groups");
+  constexpr int NC = NV / 2;
+  constexpr bool kExact = NV == VPT * T && NC == CPT * T;
   extern __shared__ __align__(16) uint32_t msg[];
   __shared__ int s_frame;
   const int tid = threadIdx.x;
-  constexpr int mpad = CPT * T + 1;  // planar: words between the k planes, bank = (slot + k) mod 32
-  constexpr int n_words = ROWM ? 6 * CPT * T : 6 * mpad;
+  constexpr int mpad = NC + 1;  // planar: words between the k planes, bank = (slot + k) mod 32
+  constexpr int n_words = ROWM ? 6 * NC : 6 * mpad;
   static_assert(!ROWM || PACK, "row-major layout is implemented for the packed path");
 
   uint32_t va[VPT][3];
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
   for (int j = 0; j < VPT; j++) {
     const int v = j * T + tid;
 #pragma unroll
-    for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[v * 3 + k];
+    for (int k = 0; k < 3; k++) va[j][k] = (kExact || v < NV) ? p.t.vn_addr[v * 3 + k] : 0;
   }
 
   while (true) {
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     float ch[VPT];
 #pragma unroll
-    for (int j = 0; j < VPT; j++) ch[j] = load_channel_ratio(in, j * T + tid, p.in_is_lr);
+    for (int j = 0; j < VPT; j++) ch[j] = (kExact || j * T + tid < NV) ? load_channel_ratio(in, j * T + tid, p.in_is_lr) : 1.0f;
     for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
     __syncthreads();
 
@@ -163,6 +168,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
       bits = 0;
 #pragma unroll
       for (int j = 0; j < VPT; j++) {
+        if (!kExact && j * T + tid >= NV) continue;  // empty last round (warp-uniform: NV is a multiple of 32)
         const float x0 = __uint_as_float(msg[va[j][0]]);
         const float x1 = __uint_as_float(msg[va[j][1]]);
         const float x2 = __uint_as_float(msg[va[j][2]]);
@@ -204,6 +210,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 #pragma unroll
       for (int j = 0; j < CPT; j++) {
         const int slot = j * T + tid;
+        if (!kExact && slot >= NC) continue;
         uint32_t w[6];
         float s[6];
         uint32_t x = 0;
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
 #pragma unroll
     for (int j = 0; j < VPT; j++) {
       const uint32_t word = __ballot_sync(0xffffffffu, (latched_bits >> j) & 1u);
-      if (lane == 0) p.out_bits[(size_t)f * p.words_n + ((j * T + tid) >> 5)] = word;
+      if (lane == 0 && (kExact || j * T + tid < NV)) p.out_bits[(size_t)f * p.words_n + ((j * T + tid) >> 5)] = word;
     }
     if (tid == 0) p.out_ret[f] = ret;
     if (SOFT) {
@@ -735,7 +742,7 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
     return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
   if (soft && k == DEC_REG_12_6)
     return !rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>
-                     : dec_regular_threads(k) == 1008 ? bp_regular_kernel<8, 4, 1008, 1, true, 2, true, true>
+                     : dec_regular_threads(k) == 1024 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, true, 8064>
                                                       : bp_regular_kernel<12, 6, 672, 1, true, 2, true, true>;
   switch (k) {
     case DEC_REG_6_3: {
@@ -762,8 +769,9 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
     case DEC_REG_12_6: {
       const char *re = getenv("KML_DEC_RATIO");
       const int r8 = re ? atoi(re) : 1;
-      if (rowmajor && dec_regular_threads(k) == 1008)
-        return r8 == 2 ? bp_regular_kernel<8, 4, 1008, 1, true, 2, true> : bp_regular_kernel<8, 4, 1008, 1, true, 1, true>;
+      if (rowmajor && dec_regular_threads(k) == 1024)
+        return r8 == 2 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, false, 8064>
+                       : bp_regular_kernel<8, 4, 1024, 1, true, 1, true, false, 8064>;
       return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
                       : bp_regular_kernel<12, 6, 672, 1>;
     }
@@ -809,10 +817,11 @@ int dec_generic_row_stride(DecKernelKind k) { return k == DEC_GEN_4_8 ? 9 : k ==
 
 int dec_regular_threads(DecKernelKind k) {
   if (k == DEC_REG_12_6) {
-    // 1008 threads x (8 variables, 4 checks): 32 warps on the SM's single CTA instead of 21 (4.60 -> 4.19 ms per 4096
-    // frames); KML_DEC_T8064=672 is the A/B knob for the 672 x (12, 6) shape, which the planar layout also uses
+    // 1024 threads x (8 variables, 4 checks; the last round is empty for the top 128 threads): 32 warps on the SM's
+    // single CTA instead of 21; KML_DEC_T8064=672 is the A/B knob for the exact 672 x (12, 6) tiling, which the planar
+    // layout also uses
     const char *e = getenv("KML_DEC_T8064");
-    return (!(e && atoi(e) == 672) && dec_wants_rowmajor(k, 0)) ? 1008 : 672;
+    return (!(e && atoi(e) == 672) && dec_wants_rowmajor(k, 0)) ? 1024 : 672;
   }
   return 384;  // (576 threads x (4 variables, 2 checks), 2 CTAs per SM measured 7 % slower)
 }
