@@ -59,6 +59,7 @@ SYMBOLS = {
     "kml_set_algorithm": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "kml_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_decoder_info": (C.c_int, [C.c_void_p, c_i32p]),
+    "kml_measure_smem_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "kml_launch_count": (C.c_uint64, [C.c_void_p]),
     "kml_encode": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_i32p]),
     "kml_generate": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, c_i32p, c_i32p, c_f32p, c_f32p]),

@@ -533,6 +533,14 @@ extern "C" int kml_info(const kml_ctx *c, int32_t info[8]) {
   return KML_OK;
 }
 
+extern "C" int kml_measure_smem_bandwidth(kml_ctx *c, double *gb_per_s) {
+  if (!c || !gb_per_s) return KML_ERR_ARG;
+  KML_CUDA(c, cudaSetDevice(c->device));
+  KML_CUDA(c, measure_smem_bandwidth(c->num_sms, gb_per_s, c->lane[0].stream));
+  c->launches += 6;
+  return KML_OK;
+}
+
 extern "C" int kml_decoder_info(const kml_ctx *c, int32_t info[8]) {
   if (!c || !info) return KML_ERR_ARG;
   info[0] = (int)c->dl.kind; info[1] = c->dl.threads; info[2] = c->dl.smem_bytes; info[3] = c->dl.ctas_per_sm;

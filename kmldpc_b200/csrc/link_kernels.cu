@@ -838,4 +838,56 @@ cudaError_t launch_count_errors(int B, int k, int k_words, const uint32_t *u_pac
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ roofline probe
+// What the SMs of THIS device sustain for conflict-free shared-memory loads (LDS.128, every lane its own 16 bytes, no
+// two loads of the loop at one address): the denominator of the decoder's roofline.frac, measured instead of derived
+// from 128 B/clk/SM x clock (tools/microbench.cu is the stand-alone version with the other pipes).
+namespace {
+constexpr int PROBE_T = 1024, PROBE_ITERS = 2048;
+__global__ void __launch_bounds__(PROBE_T, 2) smem_probe_kernel(float *out) {
+  extern __shared__ __align__(16) float psm[];
+  for (int i = threadIdx.x; i < 8192; i += PROBE_T) psm[i] = (float)i;
+  __syncthreads();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int base = (threadIdx.x * 4) & 8191;
+  for (int it = 0; it < PROBE_ITERS; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int a = (base + (it * 8 + u) * 1056) & (8191 & ~3);
+      float v, w, x, y;
+      asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v), "=f"(w), "=f"(x), "=f"(y)
+                   : "r"((unsigned)__cvta_generic_to_shared(psm + a)));
+      a0 += v; a1 += w; a2 += x; a3 += y;
+    }
+  }
+  out[blockIdx.x * PROBE_T + threadIdx.x] = a0 + a1 + a2 + a3;
+}
+}  // namespace
+
+cudaError_t measure_smem_bandwidth(int num_sms, double *gbs, cudaStream_t s) {
+  const int grid = num_sms * 2;
+  float *out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(float) * grid * PROBE_T);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 6 && e == cudaSuccess; r++) {  // first launch = warm-up
+    cudaEventRecord(e0, s);
+    smem_probe_kernel<<<grid, PROBE_T, 32768, s>>>(out);
+    cudaEventRecord(e1, s);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e == cudaSuccess) *gbs = (double)grid * PROBE_T * PROBE_ITERS * 8 * 16 / (best * 1e-3) * 1e-9;
+  return e;
+}
+
 }  // namespace kml

@@ -246,6 +246,12 @@ class Link:
                                            _ptr(cnt, C.c_uint64), C.byref(it)), "kml_simulate")
         return cnt, int(it.value)
 
+    def measure_smem_bandwidth(self) -> float:
+        """GB/s of conflict-free LDS.128 over all SMs of this device (the decoder's roofline denominator)."""
+        v = C.c_double(0.0)
+        self._check(self._lib.kml_measure_smem_bandwidth(self._h, C.byref(v)), "kml_measure_smem_bandwidth")
+        return float(v.value)
+
     def histogram(self, snr_db: float, frames: int, *, seed: int = 17, frame_begin: int = 0):
         """Histogram mode (simulator.cc:154-162): the four candidate metrics per frame + the counters the reference
         accumulates in that mode."""
