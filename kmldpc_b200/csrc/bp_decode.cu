@@ -27,6 +27,7 @@
 
 #include "kml_internal.h"
 #include "kml_kernels.cuh"
+#include "bp_minsum_nodes.cuh"
 
 namespace kml {
 namespace {
@@ -650,7 +651,8 @@ __device__ __forceinline__ constexpr int qc_voff(int i) {  // edges of the quart
 
 // One quarter's whole decoding loop.  All quarters execute the same sequence of barriers (frame queue, iteration count
 // and exit decisions are CTA-uniform), so the BAR instructions of the four instances pair up.
-template <class P, int Q>
+// ALG = 0: the reference's sum-product; ALG = 1: normalised min-sum (bp_minsum.cu; messages are LLRs, not ratios).
+template <class P, int Q, int ALG>
 __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, volatile int *s_frame, int z) {
   constexpr int NE = qc_voff<P, Q>(P::MAXV);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -673,13 +675,14 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
     float ch[P::MAXV];
     static_for<P::MAXV>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
-      ch[i] = 1.0f;
+      ch[i] = ALG == 0 ? 1.0f : 0.0f;
       if constexpr (P::vdeg[Q][i] > 0) {
         const int v = P::vblk[Q][i] * P::Z + z;  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
-        if (v >= p.t.punct) ch[i] = load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
+        if (v >= p.t.punct)
+          ch[i] = ALG == 0 ? load_channel_ratio(in, v - p.t.punct, p.in_is_lr) : msn::load_channel_llr(in, v - p.t.punct, p.in_is_lr);
       }
     });
-    for (int i = tid; i < n_words; i += blockDim.x) msg[i] = 0x3f800000u;
+    for (int i = tid; i < n_words; i += blockDim.x) msg[i] = ALG == 0 ? 0x3f800000u : 0u;  // c2v = (0.5, 0.5)
     __syncthreads();
 
     uint32_t bits = 0, latched_bits = 0;
@@ -689,14 +692,15 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
       bits = 0;
       static_for<P::MAXV>([&](auto ic) {
         constexpr int i = decltype(ic)::value, D = P::vdeg[Q][i], O = qc_voff<P, Q>(i);
-        if constexpr (D > 0) bits |= vn_core<D>(msg, va + O, ch[i]) << i;
+        if constexpr (D > 0) bits |= (ALG == 0 ? vn_core<D>(msg, va + O, ch[i]) : msn::ms_vn<D>(msg, va + O, ch[i])) << i;
       });
       __syncthreads();
       int fail = 0;
       static_for<P::MAXC>([&](auto jc) {
         constexpr int j = decltype(jc)::value, D = P::cdeg[Q][j];
         float unused;
-        fail |= (int)(cn_node<D, false>(msg + (P::cblk[Q][j] * P::Z + z) * P::RS, &unused) & 1u);
+        uint32_t *row = msg + (P::cblk[Q][j] * P::Z + z) * P::RS;
+        fail |= (int)((ALG == 0 ? cn_node<D, false>(row, &unused) : msn::ms_cn<D>(row, 1, 0, p.alpha)) & 1u);
       });
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -718,25 +722,26 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
   }
 }
 
-template <class P, int MINB>
+template <class P, int MINB, int ALG>
 __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p) {
   static_assert(P::Z % 32 == 0, "a warp must not straddle two quarters");
   extern __shared__ uint32_t msg[];  // [m_pad][RS]
   __shared__ int s_frame;
   const int q = threadIdx.x / P::Z, z = threadIdx.x % P::Z;
   switch (q) {  // warp-uniform
-    case 0: qc_quarter<P, 0>(p, msg, &s_frame, z); break;
-    case 1: qc_quarter<P, 1>(p, msg, &s_frame, z); break;
-    case 2: qc_quarter<P, 2>(p, msg, &s_frame, z); break;
-    default: qc_quarter<P, 3>(p, msg, &s_frame, z); break;
+    case 0: qc_quarter<P, 0, ALG>(p, msg, &s_frame, z); break;
+    case 1: qc_quarter<P, 1, ALG>(p, msg, &s_frame, z); break;
+    case 2: qc_quarter<P, 2, ALG>(p, msg, &s_frame, z); break;
+    default: qc_quarter<P, 3, ALG>(p, msg, &s_frame, z); break;
   }
 }
 
 dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan = 0) {
+  if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;  // (fp16 x 2 frames exists for regular codes only)
   if (alg != 0) return minsum_kernel_of(k, alg);
   if (qc_plan == 1 && !soft) {
     const char *e = getenv("KML_DEC_QC_MINB");  // A/B knob
-    return (e && atoi(e) == 2) ? bp_qc_kernel<QcPlanBg2R12, 2> : bp_qc_kernel<QcPlanBg2R12, 3>;
+    return (e && atoi(e) == 2) ? bp_qc_kernel<QcPlanBg2R12, 2, 0> : bp_qc_kernel<QcPlanBg2R12, 3, 0>;
   }
   if (soft && k == DEC_REG_6_3)
     return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;

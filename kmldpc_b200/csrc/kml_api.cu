@@ -311,8 +311,8 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
   }
   for (int alg = 0; alg < 3; alg++) {
     dl.alg = alg;
-    dl.rowmajor = (alg == 0 && rowmajor) ? 1 : 0;
-    dl.qc_plan = alg == 0 ? qc_plan : 0;
+    dl.qc_plan = qc_plan;  // the quasi-cyclic plan kernel has a sum-product and a min-sum variant, both on the row-major tables
+    dl.rowmajor = ((alg == 0 && rowmajor) || qc_plan) ? 1 : 0;
     if (dl.kind == DEC_REG_12_6) dl.threads = dl.rowmajor ? dec_regular_threads(dl.kind) : 672;
     dl.smem_bytes = dl.rowmajor ? rm_smem : planar_smem;
     KML_CUDA(c, dec_prepare(dl));
