@@ -469,7 +469,7 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *row, float *s_all) {
       for (int r = 0; r < cnt; r++, slot += 32) {                                           \
         float s_all = 0.0f;                                                                 \
         const uint32_t x = cn_node<(D <= DC ? D : 1), SOFT>(msg + slot * RS, &s_all);       \
-        fail |= (int)(x & 1u);                                                              \
+        fail += (int)(x & 1u);                                                              \
         if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);                         \
       }                                                                                     \
     }                                                                                       \
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
     for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;
     __syncthreads();
 
-    int ret = p.iters + (p.iters < p.max_iter);
+    int ret = p.iters + (p.iters < p.max_iter), nfail = 0;
     bool latched = false;
     int last_t = 0;
     float soft = 0.0f, soft_out = 0.0f;
@@ -582,12 +582,13 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
               const int deg = (int)__ldg(p.t.cn_deg + slot);
               if (deg == 0) continue;  // padding slot
               const uint32_t x = cn_lane_dispatch<DC, SOFT>(msg + slot * RS, &s_all, deg);
-              fail |= (int)(x & 1u);
+              fail += (int)(x & 1u);
               if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
             }
             break;
         }
       }
+      nfail = fail;  // this thread's unsatisfied checks of the decisions just made
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
         latched = true;
@@ -603,6 +604,12 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
       for (int w = tid; w < p.words_n; w += T) p.out_bits[(size_t)f * p.words_n + w] = dl[w];
     }
     if (tid == 0) p.out_ret[f] = ret;
+    if (p.out_synd) {  // ParityCheck(cc_hat) of the final decisions (kmcodec.cc:157-160), summed over the CTA bit by bit
+      int total = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) total += __syncthreads_count((nfail >> b) & 1) << b;
+      if (tid == 0) p.out_synd[f] = latched ? 0.0f : (float)total;
+    }
     if (SOFT) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
@@ -686,7 +693,7 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
     __syncthreads();
 
     uint32_t bits = 0, latched_bits = 0;
-    int ret = p.iters + (p.iters < p.max_iter);
+    int ret = p.iters + (p.iters < p.max_iter), nfail = 0;
     bool latched = false;
     for (int t = 0; t < p.iters; t++) {
       bits = 0;
@@ -695,13 +702,14 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
         if constexpr (D > 0) bits |= (ALG == 0 ? vn_core<D>(msg, va + O, ch[i]) : msn::ms_vn<D>(msg, va + O, ch[i])) << i;
       });
       __syncthreads();
-      int fail = 0;
+      int fail = 0;  // this thread's unsatisfied checks (of the decisions just made)
       static_for<P::MAXC>([&](auto jc) {
         constexpr int j = decltype(jc)::value, D = P::cdeg[Q][j];
         float unused;
         uint32_t *row = msg + (P::cblk[Q][j] * P::Z + z) * P::RS;
-        fail |= (int)((ALG == 0 ? cn_node<D, false>(row, &unused) : msn::ms_cn<D>(row, 1, 0, p.alpha)) & 1u);
+        fail += (int)((ALG == 0 ? cn_node<D, false>(row, &unused) : msn::ms_cn<D>(row, 1, 0, p.alpha)) & 1u);
       });
+      nfail = fail;
       const int any_fail = __syncthreads_or(fail);
       if (!any_fail && !latched) {
         latched = true;
@@ -719,6 +727,11 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
       }
     });
     if (tid == 0) p.out_ret[f] = ret;
+    if (p.out_synd) {  // ParityCheck(cc_hat) of the final decisions (kmcodec.cc:157-160): 0 when latched, else the count
+      static_assert(P::MAXC <= 3, "two count bits");  // of the last check phase, summed over the CTA bit by bit
+      const int total = __syncthreads_count(nfail & 1) + 2 * __syncthreads_count(nfail & 2);
+      if (tid == 0) p.out_synd[f] = latched ? 0.0f : (float)total;
+    }
   }
 }
 
@@ -836,6 +849,11 @@ bool dec_wants_rowmajor(DecKernelKind k, int alg) {
   if (k != DEC_REG_6_3 && k != DEC_REG_12_6) return true;  // generic sum-product kernel: always its own row-major tables
   const char *e = getenv("KML_DEC_PLANAR");  // A/B knob: the planar layout for the regular sum-product kernels too
   return !(e && atoi(e));
+}
+
+bool dec_has_synd_output(const DecLaunch &l, bool soft) {
+  if (l.qc_plan && !soft) return true;                                  // bp_qc_kernel, both algorithms
+  return l.alg == 0 && l.kind != DEC_REG_6_3 && l.kind != DEC_REG_12_6;  // bp_generic_kernel
 }
 
 cudaError_t dec_prepare(DecLaunch &l) {

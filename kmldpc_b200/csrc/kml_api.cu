@@ -368,11 +368,12 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
       if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * B, s));
       DecParams p = dec_params(c, l, 4 * B, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
       p.early_exit = 1;
+      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
       KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
       if (soft) {
         KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * B, cudaMemcpyDeviceToDevice, s));
         KML_LAUNCH(c, launch_abs_inplace(4 * B, l.metric.p, s));
-      } else {
+      } else if (!p.out_synd) {
         KML_LAUNCH(c, launch_syndrome_weight(4 * B, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p,
                                             l.metric.p, s));
       }
@@ -703,11 +704,12 @@ extern "C" int kml_resolve(kml_ctx *c, int B, const float *y, const float *hhat,
       if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
       DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
       p.early_exit = 1;
+      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
       KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
       if (soft) {
         KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
         KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
-      } else {
+      } else if (!p.out_synd) {
         KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
       }
       KML_LAUNCH(c, launch_argmin4(nb, l.metric.p, l.kstar.p, s));
@@ -879,11 +881,12 @@ extern "C" int kml_histogram(kml_ctx *c, double snr_db, uint64_t seed, uint64_t 
       if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
       DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
       p.early_exit = 1;
+      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
       KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
       if (soft) {
         KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
         KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
-      } else {
+      } else if (!p.out_synd) {
         KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
       }
       // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)

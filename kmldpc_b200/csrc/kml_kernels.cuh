@@ -34,6 +34,8 @@ struct DecParams {
   uint32_t *out_bits;       // [B][words_n] hard decisions of all graph variables, bit-packed
   int32_t *out_ret;         // [B] reference return value: iter + (iter < max_iter)
   float *out_soft;          // optional [B]: sum over rows of ln(syndrom_soft) after the LAST check-node phase executed
+  float *out_synd;          // optional [B]: unsatisfied checks of the final decisions (= ParityCheck(cc_hat)); only the
+                            // kernels dec_has_synd_output() names fill it
   unsigned int *work_counter;  // dynamic frame scheduler (zeroed by the launcher)
   int words_n;
   float alpha;              // min-sum normalisation (algorithm = 1 only)
@@ -59,6 +61,8 @@ int dec_regular_threads(DecKernelKind k);
 int dec_generic_max_threads();
 int dec_generic_row_stride(DecKernelKind k);
 int dec_match_qc_plan(int n, int m_pad, const uint8_t *vdeg, const uint8_t *cndeg, int dv_max, int row_stride);
+// does the kernel behind `l` write DecParams::out_synd itself (else: launch_syndrome_weight on its packed decisions)
+bool dec_has_synd_output(const DecLaunch &l, bool soft);
 cudaError_t dec_prepare(DecLaunch &l);
 cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cudaStream_t s);
 
