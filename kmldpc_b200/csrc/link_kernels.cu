@@ -437,13 +437,22 @@ __device__ __forceinline__ float dm_rcp(float x) {
   return r;
 }
 
+// (dx, dy) = s - y as one packed FADD2 (sm_100 add.rn.f32x2); s arrives from shared memory as a register pair
+__device__ __forceinline__ float dm_dist2(const float2 s, const float2 ny) {
+  float dx, dy;
+  asm("{.reg .b64 a, b, d; mov.b64 a, {%2,%3}; mov.b64 b, {%4,%5}; add.rn.f32x2 d, a, b; mov.b64 {%0,%1}, d;}"
+      : "=f"(dx), "=f"(dy) : "f"(s.x), "f"(s.y), "f"(ny.x), "f"(ny.y));
+  return fmaf(dy, dy, dx * dx);
+}
+
 // One symbol against NC candidates: per-point softmax with the reference's clip, bit marginals, ratio P0/P1; returns in
 // rr[j] the candidates' inverted hard decisions of bit j (bit c = candidate c).  lr_base already points at element
 // i * BITS of candidate 0; consecutive candidates are lr_stride floats apart.
 template <int BITS, int NC>
-__device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pts, float scale, float *lr_base,
+__device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pts, float rscale, float *lr_base,
                                              size_t lr_stride, unsigned int (&rr)[BITS]) {
   constexpr int Q = 1 << BITS;
+  const float2 ny = make_float2(-yy.x * rscale, -yy.y * rscale);
 #pragma unroll
   for (int j = 0; j < BITS; j++) rr[j] = 0;
 #pragma unroll
@@ -452,9 +461,7 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
     float mx = -3.0e38f;
 #pragma unroll
     for (int k = 0; k < Q; k++) {
-      const float2 s = s_pts[c * Q + k];
-      const float dx = s.x - yy.x, dy = s.y - yy.y;
-      p[k] = -(dx * dx + dy * dy) * scale;
+      p[k] = -dm_dist2(s_pts[c * Q + k], ny);  // points and symbol are pre-scaled by sqrt(log2(e) / var)
       mx = fmaxf(mx, p[k]);
     }
     float sum = 0.f;
@@ -481,17 +488,102 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
   }
 }
 
+// 64-point constellations: FOUR lanes share a symbol, 16 points each (lane t of the quad owns the points whose two
+// top label bits are t).  One thread per symbol needs all 64 probabilities live (126 registers → 16 warps per SM, the
+// kernel then runs at half its own instruction bound); a quad keeps 16, exchanges minimum / sum / the bit marginals
+// with 24 shuffles per candidate, and lets 4x more warps be resident.  Same arithmetic as demap_symbol (the sums of a
+// marginal are taken pairwise instead of sequentially).  Lane t finalises the bits j with j mod 4 == t.
+template <int NC>
+__device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float2 *s_pts, float rscale, float *lr_base,
+                                                    size_t lr_stride, int t, bool valid, unsigned int &rr_a,
+                                                    unsigned int &rr_b) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const float2 ny = make_float2(-yy.x * rscale, -yy.y * rscale);
+  rr_a = rr_b = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    float p[16];
+    float mn = 3.0e38f;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      p[m] = dm_dist2(s_pts[c * 68 + 17 * t + m], ny);  // chunks padded to 17: the quad's four addresses hit distinct banks
+      mn = fminf(mn, p[m]);
+    }
+    mn = fminf(mn, __shfl_xor_sync(FULL, mn, 1));
+    mn = fminf(mn, __shfl_xor_sync(FULL, mn, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      p[m] = dm_ex2(mn - p[m]);
+      sum += p[m];
+    }
+    sum += __shfl_xor_sync(FULL, sum, 1);
+    sum += __shfl_xor_sync(FULL, sum, 2);
+    const float inv = dm_rcp(sum);
+#pragma unroll
+    for (int m = 0; m < 16; m++) p[m] = fmaxf(p[m] * inv, kSmallProbF);
+    // label bit j of point k = (k >> (5 - j)) & 1 with k = 16 t + m: bits 0, 1 come from t, bits 2..5 from m (MSB first)
+    float z0[6], z1[6];
+    float q8[8], q4[4], q2[2];
+    {  // bit 5 = m & 1
+      float e = p[0], o = p[1];
+#pragma unroll
+      for (int i = 1; i < 8; i++) { e += p[2 * i]; o += p[2 * i + 1]; }
+      z0[5] = e; z1[5] = o;
+#pragma unroll
+      for (int i = 0; i < 8; i++) q8[i] = p[2 * i] + p[2 * i + 1];
+    }
+    {  // bit 4 = (m >> 1) & 1
+      float e = q8[0], o = q8[1];
+#pragma unroll
+      for (int i = 1; i < 4; i++) { e += q8[2 * i]; o += q8[2 * i + 1]; }
+      z0[4] = e; z1[4] = o;
+#pragma unroll
+      for (int i = 0; i < 4; i++) q4[i] = q8[2 * i] + q8[2 * i + 1];
+    }
+    z0[3] = q4[0] + q4[2]; z1[3] = q4[1] + q4[3];  // bit 3 = (m >> 2) & 1
+    q2[0] = q4[0] + q4[1]; q2[1] = q4[2] + q4[3];
+    z0[2] = q2[0]; z1[2] = q2[1];                  // bit 2 = (m >> 3) & 1
+    const float mine = q2[0] + q2[1];              // this lane's 16 points
+#pragma unroll
+    for (int j = 2; j < 6; j++) {
+      z0[j] += __shfl_xor_sync(FULL, z0[j], 1); z0[j] += __shfl_xor_sync(FULL, z0[j], 2);
+      z1[j] += __shfl_xor_sync(FULL, z1[j], 1); z1[j] += __shfl_xor_sync(FULL, z1[j], 2);
+    }
+    {  // bit 0 = t >> 1: lanes {0,1} against {2,3};  bit 1 = t & 1: lanes {0,2} against {1,3}
+      const float pair01 = mine + __shfl_xor_sync(FULL, mine, 1), other01 = __shfl_xor_sync(FULL, pair01, 2);
+      z0[0] = (t & 2) ? other01 : pair01; z1[0] = (t & 2) ? pair01 : other01;
+      const float pair02 = mine + __shfl_xor_sync(FULL, mine, 2), other02 = __shfl_xor_sync(FULL, pair02, 1);
+      z0[1] = (t & 1) ? other02 : pair02; z1[1] = (t & 1) ? pair02 : other02;
+    }
+    // lane t writes bits t and t + 4 (the latter for t < 2)
+    float a0 = z0[0], a1 = z1[0], b0 = z0[4], b1 = z1[4];
+    if (t == 1) { a0 = z0[1]; a1 = z1[1]; b0 = z0[5]; b1 = z1[5]; }
+    if (t == 2) { a0 = z0[2]; a1 = z1[2]; }
+    if (t == 3) { a0 = z0[3]; a1 = z1[3]; }
+    if (valid) {
+      lr_base[c * lr_stride + t] = fminf(fmaxf(a0 * dm_rcp(a1), kLrMin), kLrMax);
+      if (t < 2) lr_base[c * lr_stride + t + 4] = fminf(fmaxf(b0 * dm_rcp(b1), kLrMin), kLrMax);
+    }
+    rr_a |= (a0 > a1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
+    rr_b |= (b0 > b1 ? 1u : 0u) << c;
+  }
+}
+
 template <int BITS, int NC>
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
   constexpr int Q = 1 << BITS;
   constexpr int MAXS = 6;  // symbols a thread keeps in flight (n_sym <= MAXS * DM_THREADS on the fast path)
   extern __shared__ unsigned char dsm[];
-  float2 *s_pts = reinterpret_cast<float2 *>(dsm);                        // [NC][Q] s_k * h_cand
-  float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * Q * 4);   // [NC][n_tx]   (winner_only)
-  unsigned char *s_rr = dsm + sizeof(float2) * Q * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0);
+  constexpr int PTS = BITS == 6 ? 68 : Q;  // 64 points: four chunks of 16 padded to 17 (see demap_symbol_quad64)
+  float2 *s_pts = reinterpret_cast<float2 *>(dsm);                          // [NC][PTS] s_k * h_cand
+  float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * PTS * 4);   // [NC][n_tx]   (winner_only)
+  unsigned char *s_rr = dsm + sizeof(float2) * PTS * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0);
   __shared__ int s_cnt[4], s_best;
   const int tid = threadIdx.x;
-  const float scale = d.inv_var * 1.4426950408889634f;  // exp(-x / var) = 2^(-x log2(e) / var)
+  // exp(-|s - y|^2 / var) = 2^(-|r s - r y|^2) with r = sqrt(log2(e) / var): the candidate tables and the symbols are
+  // pre-scaled, which leaves FADD2 + FMUL + FFMA per point
+  const float rscale = sqrtf(d.inv_var * 1.4426950408889634f);
   const int zero_slot = d.punct + d.n_tx;               // a byte that is always 0 (padding of the ELL column table)
   const size_t lr_stride = (size_t)d.n_tx;
   for (int f = blockIdx.x; f < d.B; f += gridDim.x) {
@@ -501,7 +593,7 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
 #pragma unroll
     for (int u = 0; u < MAXS; u++) {  // all of this thread's symbols are in flight before the first one is used
       const int i = u * DM_THREADS + tid;
-      yreg[u] = i < d.n_sym ? yf[i] : make_float2(0.f, 0.f);
+      yreg[u] = (BITS != 6 && i < d.n_sym) ? yf[i] : make_float2(0.f, 0.f);
     }
     if (tid < 4) s_cnt[tid] = 0;
     for (int i = tid; i < NC * Q; i += DM_THREADS) {
@@ -509,7 +601,9 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
       const float2 r = c == 0 ? d.rot[0] : (c == 1 ? d.rot[1] : (c == 2 ? d.rot[2] : d.rot[3]));
       const float2 s = __ldg(d.points + (i % Q));
       const float2 hc = make_float2(hb.x * r.x - hb.y * r.y, hb.x * r.y + hb.y * r.x);
-      s_pts[i] = make_float2(s.x * hc.x - s.y * hc.y, s.x * hc.y + s.y * hc.x);
+      const int k = i % Q;
+      s_pts[BITS == 6 ? c * PTS + k + (k >> 4) : i] =
+          make_float2((s.x * hc.x - s.y * hc.y) * rscale, (s.x * hc.y + s.y * hc.x) * rscale);
     }
     if (d.hard_metric) {
       for (int i = tid; i < d.punct; i += DM_THREADS) s_rr[i] = 0;
@@ -517,21 +611,35 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
     }
     __syncthreads();
     float *lr0 = d.winner_only ? s_lr : d.lr + (size_t)f * NC * d.n_tx;
+    if constexpr (BITS == 6) {  // a quad of lanes per symbol
+      const int t = tid & 3;
+      for (int i0 = 0; i0 < d.n_sym; i0 += DM_THREADS / 4) {
+        const int i = i0 + (tid >> 2);
+        const bool valid = i < d.n_sym;
+        const float2 yy = yf[valid ? i : d.n_sym - 1];
+        unsigned int rr_a, rr_b;
+        demap_symbol_quad64<NC>(yy, s_pts, rscale, lr0 + i * BITS, lr_stride, t, valid, rr_a, rr_b);
+        if (d.hard_metric && valid) {
+          s_rr[d.punct + i * BITS + t] = (unsigned char)rr_a;
+          if (t < 2) s_rr[d.punct + i * BITS + t + 4] = (unsigned char)rr_b;
+        }
+      }
+    } else
 #pragma unroll
     for (int u = 0; u < MAXS; u++) {
       const int i = u * DM_THREADS + tid;
       if (i < d.n_sym) {
         unsigned int rr[BITS];
-        demap_symbol<BITS, NC>(yreg[u], s_pts, scale, lr0 + i * BITS, lr_stride, rr);
+        demap_symbol<BITS, NC>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
         if (d.hard_metric) {
 #pragma unroll
           for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
         }
       }
     }
-    for (int i = MAXS * DM_THREADS + tid; i < d.n_sym; i += DM_THREADS) {  // very long frames
+    for (int i = MAXS * DM_THREADS + tid; BITS != 6 && i < d.n_sym; i += DM_THREADS) {  // very long frames
       unsigned int rr[BITS];
-      demap_symbol<BITS, NC>(yf[i], s_pts, scale, lr0 + i * BITS, lr_stride, rr);
+      demap_symbol<BITS, NC>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
       if (d.hard_metric) {
 #pragma unroll
         for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -768,7 +876,7 @@ static cudaError_t launch_demap_bits(const DemapParams &d, int grid, int smem, c
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s) {
   const int grid = d.B < num_sms * 8 ? d.B : num_sms * 8;
   if (grid < 1) return cudaSuccess;
-  const int smem = (int)sizeof(float2) * d.q * 4 + (d.winner_only ? (int)sizeof(float) * 4 * d.n_tx : 0) + d.n_tx + d.punct + 32;
+  const int smem = (int)sizeof(float2) * (d.q == 64 ? 68 : d.q) * 4 + (d.winner_only ? (int)sizeof(float) * 4 * d.n_tx : 0) + d.n_tx + d.punct + 32;
   switch (d.bits_per_symbol) {
     case 1: return launch_demap_bits<1>(d, grid, smem, s);
     case 2: return launch_demap_bits<2>(d, grid, smem, s);
