@@ -99,7 +99,8 @@ int kml_set_early_exit(kml_ctx *ctx, int early_exit);
 int kml_set_algorithm(kml_ctx *ctx, int algorithm, double alpha);
 /* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
 int kml_info(const kml_ctx *ctx, int32_t info[8]);
-/* Decoder launch facts: info[0..7] = kernel kind, threads per CTA, dynamic shared memory bytes, CTAs per SM,
+/* Decoder launch facts: info[0..7] = kernel kind (bits 0-7: 0/1 = (3,6)-regular PEG2304 / PEG8064 shapes, 2-4 = run-time
+ * graph; bits 8-15: id of the compile-time quasi-cyclic plan in use, 0 = none; bit 16: row-major messages), threads per CTA, dynamic shared memory bytes, CTAs per SM,
  * layout annealing residual, shared-memory wavefronts above one per variable-node gather (0 = conflict free),
  * variable-node gather instructions per iteration (the ideal wavefront count), row slots. */
 int kml_decoder_info(const kml_ctx *ctx, int32_t info[8]);

@@ -167,6 +167,30 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     for (int t = 0; t < p.iters; t++) {
       // ---- variable nodes (binaryldpccodec.cc:177-212)
       bits = 0;
+      if (PACK && kExact && VPT % 2 == 0) {
+        // Two variables per step, so that EVERY operation is packed.  With post = ch x0 x1 x2 the extrinsic ratio is
+        // e_k = post / x_k, hence  s_k = min(e_k, 1) / (1 + e_k) = min(post, x_k) / (x_k + post)  and the hard bit is
+        // the sign of post - x_k: the three e_k are never formed.  fp32 range: post overflows / underflows only when
+        // every e_k is beyond 1e±26, where s_k = 0 is the right limit.
+#pragma unroll
+        for (int j = 0; j < VPT; j += 2) {
+          float2 x[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++)
+            x[k] = make_float2(__uint_as_float(msg[va[j][k]]), __uint_as_float(msg[va[j + 1][k]]));
+          const float2 post = mul2(mul2(make_float2(ch[j], ch[j + 1]), x[0]), mul2(x[1], x[2]));
+          const uint32_t ba = (post.x > 1.0f) ? 0u : 1u, bb = (post.y > 1.0f) ? 0u : 1u;  // tie → 1
+          bits |= (ba << j) | (bb << (j + 1));
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            const float2 den = add2(x[k], post), sgn = fma2(x[k], splat(-1.0f), post);
+            const float2 s2 = mul2(make_float2(fminf(post.x, x[k].x), fminf(post.y, x[k].y)),
+                                   make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+            msg[va[j][k]] = v2c_pack(sgn.x, s2.x, ba);
+            msg[va[j + 1][k]] = v2c_pack(sgn.y, s2.y, bb);
+          }
+        }
+      } else
 #pragma unroll
       for (int j = 0; j < VPT; j++) {
         if (!kExact && j * T + tid >= NV) continue;  // empty last round (warp-uniform: NV is a multiple of 32)
@@ -175,19 +199,22 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         const float x2 = __uint_as_float(msg[va[j][2]]);
         uint32_t w0, w1, w2, bit;
         if (PACK) {
-          // (a, b) = ch (x0, x1);  (e1, e0) = (a, b) x2;  e2 = a x1;  post = e2 x2  — 2 FMUL2 + 2 FMUL instead of 6 FMUL
-          const float2 ab = mul2(splat(ch[j]), make_float2(x0, x1));
-          const float2 e10 = mul2(ab, splat(x2));
-          const float e2 = ab.x * x1;
-          const float post = e2 * x2;
+          // With post = ch x0 x1 x2 the extrinsic ratio is e_k = post / x_k, so  s_k = min(e_k, 1) / (1 + e_k)
+          // = min(post, x_k) / (x_k + post)  and the hard bit is the sign of post - x_k: the three e_k are never
+          // formed (3 issue slots for the products instead of 4, and the edge-2 add / subtract are one FFMA2).  fp32 range: post overflows / underflows only when
+          // every e_k is beyond 1e±26, where s_k = 0 is the right limit.
+          const float post = (ch[j] * x0) * (x1 * x2);  // scalar: pairing ch with a loaded value would cost a move
           bit = (post > 1.0f) ? 0u : 1u;
           const uint32_t pb = bit;
-          const float2 den = add2(e10, splat(1.0f)), sgn = add2(e10, splat(-1.0f));
-          const float2 s10 = mul2(make_float2(fminf(e10.x, 1.0f), fminf(e10.y, 1.0f)),
-                                  make_float2(rcp_approx(den.x), rcp_approx(den.y)));
-          w1 = v2c_pack(sgn.x, s10.x, pb);
-          w0 = v2c_pack(sgn.y, s10.y, pb);
-          w2 = v2c_word(e2, pb);
+          const float2 x01 = make_float2(x0, x1);
+          const float2 den01 = add2(x01, splat(post)), sgn01 = fma2(x01, splat(-1.0f), splat(post));
+          const float2 ds2 = fma2(splat(x2), make_float2(1.0f, -1.0f), splat(post));  // (x2 + post, post - x2)
+          const float2 s01 = mul2(make_float2(fminf(post, x0), fminf(post, x1)),
+                                  make_float2(rcp_approx(den01.x), rcp_approx(den01.y)));
+          const float s2 = fminf(post, x2) * rcp_approx(ds2.x);
+          w0 = v2c_pack(sgn01.x, s01.x, pb);
+          w1 = v2c_pack(sgn01.y, s01.y, pb);
+          w2 = v2c_pack(ds2.y, s2, pb);
         } else {
           const float a = ch[j] * x0, b = ch[j] * x1;
           const float e2 = a * x1, e1 = a * x2, e0 = b * x2;

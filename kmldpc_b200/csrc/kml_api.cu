@@ -544,7 +544,7 @@ extern "C" int kml_measure_smem_bandwidth(kml_ctx *c, double *gb_per_s) {
 
 extern "C" int kml_decoder_info(const kml_ctx *c, int32_t info[8]) {
   if (!c || !info) return KML_ERR_ARG;
-  info[0] = (int)c->dl.kind; info[1] = c->dl.threads; info[2] = c->dl.smem_bytes; info[3] = c->dl.ctas_per_sm;
+  info[0] = (int)c->dl.kind | (c->dl.qc_plan << 8) | (c->dl.rowmajor << 16); info[1] = c->dl.threads; info[2] = c->dl.smem_bytes; info[3] = c->dl.ctas_per_sm;
   info[4] = c->layout_residual; info[5] = c->layout_excess; info[6] = ((c->N + 31) / 32) * c->dt.dv_max; info[7] = c->dt.m_pad;
   return KML_OK;
 }

@@ -126,7 +126,10 @@ class Link:
         self._check(self._lib.kml_decoder_info(self._h, info), "kml_decoder_info")
         keys = ("kernel_kind", "threads", "smem_bytes", "ctas_per_sm", "layout_residual", "excess_wavefronts",
                 "gather_instructions", "row_slots")
-        return dict(zip(keys, list(info)))
+        d = dict(zip(keys, list(info)))
+        d["qc_plan"], d["row_major"] = (d["kernel_kind"] >> 8) & 0xFF, (d["kernel_kind"] >> 16) & 1
+        d["kernel_kind"] &= 0xFF
+        return d
 
     @property
     def launches(self) -> int:

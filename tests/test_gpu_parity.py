@@ -524,3 +524,16 @@ def test_generic_decoder_on_irregular_ragged_graph(tmp_path, m, n, col_degs, see
     finally:
         util.CASES.pop(name, None)
         util.oracle_frames.cache_clear()
+
+
+def test_decoder_kernel_selection():
+    """The fast kernels are the ones that run: PEG2304 / PEG8064 on the unrolled regular kernel (row-major layout),
+    the reference's 5G matrix on the compile-time quasi-cyclic plan, anything else on the run-time-graph kernel — a
+    silent fallback to the generic kernel would halve the 5G throughput without failing any parity test."""
+    for name, kind, plan, threads in (("peg2304_4psk_6db", 0, 0, 384), ("peg8064_64qam_20db", 1, 0, 1024),
+                                      ("5g_16qam_gray_10db", 3, 1, 384)):
+        link = util.gpu_link(name)
+        info = link.decoder_info()
+        assert (info["kernel_kind"], info["qc_plan"], info["threads"], info["row_major"]) == (kind, plan, threads, 1), info
+        assert info["ctas_per_sm"] == (1 if kind == 1 else 3), info
+        link.close()
