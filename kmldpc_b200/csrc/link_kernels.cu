@@ -81,19 +81,24 @@ __global__ void gen_bits_kernel(GenParams g, uint32_t *u_packed) {
 // BinaryLDPCCodec::Encoder (binaryldpccodec.cc:144-162): cc = [p | u], p_t = XOR_j u_j & enc_h[t][chk + j]
 // Binary5GLDPCCodec::Encoder (binary5gldpccodec.cc:86-109): cc_np = [u | p], transmitted = cc_np[2Z:]
 // One CTA encodes ENC_FT frames: thread t owns parity row t (rows strided by the block), reads its row of the
-// transposed matrix once per word and applies it to all ENC_FT frames (u words are warp-broadcast from shared memory).
-constexpr int ENC_FT = 8;
+// transposed matrix once per word and applies it to all ENC_FT frames; the information words are also kept word-major
+// ([word][frame]) so that one warp-broadcast LDS.128 delivers the same word of four frames (per matrix word:
+// 1 LDG + 4 LDS.128 + 16 LOP3 for 16 frames).
+constexpr int ENC_FT = 16;
 constexpr int ENC_THREADS = 256;
 __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const uint32_t *u_packed, uint32_t *c_packed) {
-  extern __shared__ uint32_t sm[];
+  extern __shared__ __align__(16) uint32_t sm[];
   const int chk_words = (g.n_chk + 31) / 32;
   uint32_t *su = sm;                                   // [ENC_FT][k_words + 1]
   uint32_t *sp = su + ENC_FT * (g.k_words + 1);        // [ENC_FT][chk_words + 1]
+  uint4 *sut = reinterpret_cast<uint4 *>(sm + (((ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) + 3) & ~3));  // [k_words][ENC_FT]
   const int f0 = blockIdx.x * ENC_FT;
   const int nf = min(ENC_FT, g.B - f0);
   for (int i = threadIdx.x; i < ENC_FT * (g.k_words + 1); i += blockDim.x) {
     const int f = i / (g.k_words + 1), w = i % (g.k_words + 1);
-    su[i] = (f < nf && w < g.k_words) ? u_packed[(size_t)(f0 + f) * g.k_words + w] : 0u;
+    const uint32_t v = (f < nf && w < g.k_words) ? u_packed[(size_t)(f0 + f) * g.k_words + w] : 0u;
+    su[i] = v;
+    if (w < g.k_words) reinterpret_cast<uint32_t *>(sut)[w * ENC_FT + f] = v;
   }
   for (int i = threadIdx.x; i < ENC_FT * (chk_words + 1); i += blockDim.x) sp[i] = 0u;
   __syncthreads();
@@ -106,7 +111,13 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const 
       for (int w = 0; w < g.k_words; w++) {
         const uint32_t e = __ldg(g.enc_t + (size_t)w * g.n_chk + t);
 #pragma unroll
-        for (int f = 0; f < ENC_FT; f++) acc[f] ^= e & su[f * (g.k_words + 1) + w];
+        for (int f4 = 0; f4 < ENC_FT / 4; f4++) {
+          const uint4 u4 = sut[w * (ENC_FT / 4) + f4];
+          acc[4 * f4 + 0] ^= e & u4.x;
+          acc[4 * f4 + 1] ^= e & u4.y;
+          acc[4 * f4 + 2] ^= e & u4.z;
+          acc[4 * f4 + 3] ^= e & u4.w;
+        }
       }
     }
 #pragma unroll
@@ -817,7 +828,11 @@ cudaError_t launch_gen_bits(const GenParams &g, uint32_t *u_packed, cudaStream_t
 
 cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s) {
   const int chk_words = (g.n_chk + 31) / 32;
-  const int smem = (ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) * (int)sizeof(uint32_t);
+  const int smem = ((((ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) + 3) & ~3) + ENC_FT * g.k_words) * (int)sizeof(uint32_t);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+  }
   encode_kernel<<<(g.B + ENC_FT - 1) / ENC_FT, ENC_THREADS, smem, s>>>(g, u_packed, c_packed);
   return cudaGetLastError();
 }
