@@ -659,13 +659,34 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
     if (d.hard_metric) {
       __syncthreads();
       int bad[4] = {0, 0, 0, 0};
-      for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
-        unsigned int par = 0;
-        for (int k = 0; k < d.ell_width; k++)  // ELL table, transposed: consecutive rows read consecutive 16-bit words
-          par ^= s_rr[__ldg(d.col_ell + (size_t)k * d.m_rows + rrow)];
+      // ELL table, transposed: consecutive rows read consecutive 16-bit words.  Per-candidate counts are kept packed,
+      // one byte each (a thread sees at most m_rows / DM_THREADS <= 255 rows), and split once at the end.
+      unsigned int bad4 = 0;
+      if (d.ell_width == 6) {  // (3,6)-regular codes: unrolled, all six table words in flight
+        const uint16_t *ce = d.col_ell;
+        const int mr = d.m_rows;
+        for (int rrow = tid; rrow < mr; rrow += DM_THREADS) {
+          unsigned int idx[6], par = 0;
 #pragma unroll
-        for (int c = 0; c < 4; c++) bad[c] += (par >> c) & 1u;
+          for (int k = 0; k < 6; k++) idx[k] = __ldg(ce + k * mr + rrow);
+#pragma unroll
+          for (int k = 0; k < 6; k++) par ^= s_rr[idx[k]];
+          bad4 += (par & 1u) | ((par & 2u) << 7) | ((par & 4u) << 14) | ((par & 8u) << 21);
+        }
+      } else {
+        for (int rrow = tid; rrow < d.m_rows; rrow += DM_THREADS) {
+          unsigned int par = 0;
+          for (int k = 0; k < d.ell_width; k++) par ^= s_rr[__ldg(d.col_ell + (size_t)k * d.m_rows + rrow)];
+          bad4 += (par & 1u) | ((par & 2u) << 7) | ((par & 4u) << 14) | ((par & 8u) << 21);
+          if ((bad4 & 0x80808080u) != 0) {  // a byte is about to overflow (very long codes): spill into the wide counters
+#pragma unroll
+            for (int c = 0; c < 4; c++) bad[c] += (bad4 >> (8 * c)) & 0xFFu;
+            bad4 = 0;
+          }
+        }
       }
+#pragma unroll
+      for (int c = 0; c < 4; c++) bad[c] += (bad4 >> (8 * c)) & 0xFFu;
 #pragma unroll
       for (int c = 0; c < 4; c++) {
 #pragma unroll
