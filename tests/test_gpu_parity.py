@@ -537,3 +537,24 @@ def test_decoder_kernel_selection():
         assert (info["kernel_kind"], info["qc_plan"], info["threads"], info["row_major"]) == (kind, plan, threads, 1), info
         assert info["ctas_per_sm"] == (1 if kind == 1 else 3), info
         link.close()
+
+
+@pytest.mark.parametrize("knob,name,frames", [("KML_DEC_PLANAR", "peg2304_4psk_6db", 80), ("KML_DEC_NO_QC", "5g_16qam_gray_10db", 60),
+                                              ("KML_DEC_T8064=672", "peg8064_64qam_20db", 12),
+                                              ("KML_DEC_RATIO=2", "peg2304_16qam_gray_12db", 80)])
+def test_decoder_fallback_paths_stay_correct(monkeypatch, knob, name, frames):
+    """The A/B knobs select kernels that are still shipped (planar layout, run-time-graph kernel on the 5G matrix, the
+    exact 672-thread PEG8064 tiling, the predicated-reciprocal ratio): each must reproduce the reference as well."""
+    key, _, val = knob.partition("=")
+    monkeypatch.setenv(key, val or "1")
+    olink, rs = util.oracle_frames(name, frames)
+    link = util.gpu_link(name)
+    llr = np.stack([util.llr_of_p0(r.p0) for r in rs]).astype(np.float32)
+    cc, uu, ret = link.decode(llr)
+    assert np.array_equal(ret, np.array([r.ret for r in rs]))
+    conv = np.array([olink.code.parity_check(r.cc_hat) for r in rs]) == 0
+    assert np.array_equal(cc[conv], np.stack([r.cc_hat for r in rs])[conv])
+    y = np.stack([r.y for r in rs])
+    _, _, kstar, ret2 = link.receive(y, 10 ** (-util.CASES[name][2] / 10))
+    assert np.array_equal(kstar, [r.kstar for r in rs]) and np.array_equal(ret2, ret)
+    link.close()
