@@ -171,6 +171,15 @@ def gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "unset"
+    try:  # host buffers and the copy-issuing thread on the CPUs next to this rank's GPU (matters for e2e at N = 8:
+        import pynvml  # eight ranks move 8 x 151 MB per step through host memory)
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        numa = f"{len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:  # affinity is an optimisation, not a requirement
+        numa = f"unavailable ({type(e).__name__})"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -376,6 +385,7 @@ def gpu_arm(args):
                 "e2e": {"value": e2e, "unit": "Mbit/s", "h2d_bytes_per_step": B * N_SYM * 8,
                         "d2h_bytes_per_step": B * kw * 4 + B * 4, "ms_per_step": e2e_ms / args.steps,
                         "timer": "host wall clock around the blocking C-ABI call kml_receive (pinned buffers)",
+                        "cpu_affinity": numa,
                         "matches_device_path": same},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "smem", "kernel": "bp_regular_kernel<6,3> (BP decoder)", "achieved": achieved,

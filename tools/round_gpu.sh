@@ -8,6 +8,7 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --quick > gpurun_out/ncu_launch_$TAG.log 2>&1
 python tools/prof_decode.py 16384 5 -5 > gpurun_out/prof_$TAG.log 2>&1 && \
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke_$TAG.log
 ncu --set full --clock-control none --import-source on -k regex:bp_regular -c 1 -o gpurun_out/bp_$TAG \
     python tools/prof_decode.py 16384 1 -5 > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -c 600 gpurun_out/bench_$TAG.json; cat gpurun_out/prof_$TAG.log
