@@ -390,7 +390,7 @@ def gpu_arm(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "smem", "kernel": "bp_regular_kernel<6,3> (BP decoder)", "achieved": achieved,
                              "peak": smem_peak, "unit": "GB/s", "frac": achieved / smem_peak, "traffic": traffic,
-                             "peak_source": (f"measured live on this GPU: conflict-free LDS.128 on all SMs, best of 3 "
+                             "peak_source": (f"measured live on this GPU: conflict-free LDS.128 on all SMs, best of 2 "
                                              f"(kml_measure_smem_bandwidth); derived {n_sm} SMs x 128 B/clk x {sm_max:.0f} MHz "
                                              f"= {smem_derived:.0f} GB/s; shared memory is not in MEASURED_PEAKS.json")
                              if smem_measured > 0 else

@@ -104,7 +104,7 @@ int kml_info(const kml_ctx *ctx, int32_t info[8]);
  * layout annealing residual, shared-memory wavefronts above one per variable-node gather (0 = conflict free),
  * variable-node gather instructions per iteration (the ideal wavefront count), row slots. */
 int kml_decoder_info(const kml_ctx *ctx, int32_t info[8]);
-/* Shared-memory load bandwidth this device sustains (GB/s; conflict-free LDS.128 on every SM, best of 3 launches):
+/* Shared-memory load bandwidth this device sustains (GB/s; conflict-free LDS.128 on every SM, best of 2 launches):
  * the measured denominator of the decoder's roofline.  No reference counterpart — diagnostics. */
 int kml_measure_smem_bandwidth(kml_ctx *ctx, double *gb_per_s);
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */

@@ -538,7 +538,7 @@ extern "C" int kml_measure_smem_bandwidth(kml_ctx *c, double *gb_per_s) {
   if (!c || !gb_per_s) return KML_ERR_ARG;
   KML_CUDA(c, cudaSetDevice(c->device));
   KML_CUDA(c, measure_smem_bandwidth(c->num_sms, gb_per_s, c->lane[0].stream));
-  c->launches += 4;
+  c->launches += 3;
   return KML_OK;
 }
 

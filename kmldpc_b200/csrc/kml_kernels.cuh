@@ -124,7 +124,7 @@ cudaError_t launch_lr_to_llr(size_t n, const float *lr, float *llr, cudaStream_t
 cudaError_t launch_count_errors(int B, int k, int k_words, const uint32_t *u_packed, const uint32_t *uu_hat_packed,
                                 const int32_t *ret, int max_iter, unsigned long long *counters, cudaStream_t s);
 
-// best-of-3 LDS.128 bandwidth of the device in GB/s (roofline denominator of the decoder)
+// best-of-2 LDS.128 bandwidth of the device in GB/s (roofline denominator of the decoder)
 cudaError_t measure_smem_bandwidth(int num_sms, double *gbs, cudaStream_t s);
 
 }  // namespace kml

@@ -987,7 +987,7 @@ cudaError_t launch_count_errors(int B, int k, int k_words, const uint32_t *u_pac
 // two loads of the loop at one address): the denominator of the decoder's roofline.frac, measured instead of derived
 // from 128 B/clk/SM x clock (tools/microbench.cu is the stand-alone version with the other pipes).
 namespace {
-constexpr int PROBE_T = 1024, PROBE_ITERS = 512;
+constexpr int PROBE_T = 1024, PROBE_ITERS = 2048;  // ~2 ms per launch: the launch ramp is < 1 % of it
 __global__ void __launch_bounds__(PROBE_T, 2) smem_probe_kernel(float *out) {
   extern __shared__ __align__(16) float psm[];
   for (int i = threadIdx.x; i < 8192; i += PROBE_T) psm[i] = (float)i;
@@ -1017,7 +1017,7 @@ cudaError_t measure_smem_bandwidth(int num_sms, double *gbs, cudaStream_t s) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   float best = 1e30f;
-  for (int r = 0; r < 4 && e == cudaSuccess; r++) {  // first launch = warm-up
+  for (int r = 0; r < 3 && e == cudaSuccess; r++) {  // first launch = warm-up
     cudaEventRecord(e0, s);
     smem_probe_kernel<<<grid, PROBE_T, 32768, s>>>(out);
     cudaEventRecord(e1, s);
