@@ -776,7 +776,9 @@ __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p
   }
 }
 
-dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan = 0) {
+// Resolved once per context (dec_prepare): the A/B knobs below are read when a context is created, never on the launch
+// path.  `threads` = the CTA size the tables were built for.
+dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan, int threads) {
   if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;  // (fp16 x 2 frames exists for regular codes only)
   if (alg != 0) return minsum_kernel_of(k, alg);
   if (qc_plan == 1 && !soft) {
@@ -787,7 +789,7 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
     return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
   if (soft && k == DEC_REG_12_6)
     return !rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>
-                     : dec_regular_threads(k) == 1024 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, true, 8064>
+                     : threads == 1024 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, true, 8064>
                                                       : bp_regular_kernel<12, 6, 672, 1, true, 2, true, true>;
   switch (k) {
     case DEC_REG_6_3: {
@@ -814,7 +816,7 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
     case DEC_REG_12_6: {
       const char *re = getenv("KML_DEC_RATIO");
       const int r8 = re ? atoi(re) : 1;
-      if (rowmajor && dec_regular_threads(k) == 1024)
+      if (rowmajor && threads == 1024)
         return r8 == 2 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, false, 8064>
                        : bp_regular_kernel<8, 4, 1024, 1, true, 1, true, false, 8064>;
       return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
@@ -884,11 +886,14 @@ bool dec_has_synd_output(const DecLaunch &l, bool soft) {
 }
 
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false, l.qc_plan);
+  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false, l.qc_plan, l.threads);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
-  dec_kernel_t ks = kernel_of(l.kind, l.alg, l.rowmajor, true);  // the soft-syndrome twin, same launch shape
+  // the soft-syndrome twin (sum-product only; a plan kernel hands over to the run-time-graph kernel), same launch shape
+  dec_kernel_t ks = l.alg == 0 ? kernel_of(l.kind, l.alg, l.rowmajor, true, 0, l.threads) : k;
+  l.fn = k;
+  l.fn_soft = ks;
   if (ks != k) {
     e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -908,7 +913,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  kernel_of(l.kind, l.alg, l.rowmajor, p.out_soft != nullptr, l.qc_plan)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  (p.out_soft ? l.fn_soft : l.fn)<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

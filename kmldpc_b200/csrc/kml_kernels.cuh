@@ -43,17 +43,19 @@ struct DecParams {
 
 enum DecKernelKind { DEC_REG_6_3 = 0, DEC_REG_12_6 = 1, DEC_GEN_4_8 = 2, DEC_GEN_9_10 = 3, DEC_GEN_16_32 = 4 };
 
+typedef void (*dec_kernel_t)(const DecParams);
+
 struct DecLaunch {
   DecKernelKind kind;
   int alg;  // 0 = sum-product (reference semantics, bp_decode.cu), 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
+  dec_kernel_t fn, fn_soft;  // filled by dec_prepare: the kernel, and its twin that also produces DecParams::out_soft
   int qc_plan;      // != 0: the graph matches a compiled quasi-cyclic plan (bp_qc_kernel); sum-product, no soft output
   int rowmajor;     // sum-product kernels: messages at row_stride * slot + k (their own DecTables) instead of planar
 };
 
-typedef void (*dec_kernel_t)(const DecParams);
 dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
 inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
 bool dec_wants_rowmajor(DecKernelKind k, int alg);
