@@ -40,6 +40,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+template <int DIAG>
+__device__ __forceinline__ float rcp_d(float x) { return (DIAG & 2) ? 2.0f - x : rcp_approx(x); }
 
 // s_ab = s_a + s_b - 2 s_a s_b
 // (measured: the 3-instruction form with two independent operands beats fmaf(a, fmaf(-2, b, 1), b) — the kernel is
@@ -127,8 +129,11 @@ __device__ __forceinline__ float2 splat(float c) { return make_float2(c, c); }
 //   ROWM = true  ("row-major"): at word 6 * slot + phys(k) — the six words of a check are contiguous and move as
 //                               3 LDS.64 + 3 STS.64 (a half-warp covers 16 distinct even banks: conflict free), which
 //                               takes one issue slot per edge-iteration out of this issue-bound kernel.
+// DIAG (KML_DEC_DIAG, timing experiments only — the RESULTS ARE WRONG): bit 0 drops the two barriers of an iteration,
+// bit 1 replaces every MUFU.RCP of the loop by an FADD; what the launch time loses says what the barrier / the XU pipe
+// cost (profiles/r1_decoder_ablation.txt).
 template <int VPT, int CPT, int T, int MINB, bool PACK = true, int RATIO = 2, bool ROWM = false, bool SOFT = false,
-          int NV = VPT * T>
+          int NV = VPT * T, int DIAG = 0>
 __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) {
   static_assert(T % 32 == 0 && NV % 64 == 0 && NV <= VPT * T && NV / 2 <= CPT * T, "warps must line up with the 32-node groups");
   constexpr int NC = NV / 2;
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           for (int k = 0; k < 3; k++) {
             const float2 den = add2(x[k], post), sgn = fma2(x[k], splat(-1.0f), post);
             const float2 s2 = mul2(make_float2(fminf(post.x, x[k].x), fminf(post.y, x[k].y)),
-                                   make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+                                   make_float2(rcp_d<DIAG>(den.x), rcp_d<DIAG>(den.y)));
             msg[va[j][k]] = v2c_pack(sgn.x, s2.x, ba);
             msg[va[j + 1][k]] = v2c_pack(sgn.y, s2.y, bb);
           }
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         msg[va[j][1]] = w1;
         msg[va[j][2]] = w2;
       }
-      __syncthreads();
+      if (!(DIAG & 1)) __syncthreads();
       // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
       int fail = 0;
       const float soft_before = soft;  // syndrom_soft_ as the reference holds it when it leaves at this iteration
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
             } else if (RATIO == 1) {  // select numerator / denominator (ALU pipe)
               const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
               const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);
-              q = mul2(num, make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+              q = mul2(num, make_float2(rcp_d<DIAG>(den.x), rcp_d<DIAG>(den.y)));
             } else if (RATIO == 3) {  // selects + ONE reciprocal for the pair: r = 1 / (den_a den_b), q_a = num_a den_b r
               const float2 num = make_float2(ha ? sc.x : big.x, hb ? sc.y : big.y);
               const float2 den = make_float2(ha ? big.x : sc.x, hb ? big.y : sc.y);  // >= 1e-12 each: product is normal
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         if (SOFT)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
           soft += __logf((x >> 31) ? sall : 1.0f - sall);
       }
-      const int any_fail = __syncthreads_or(fail);
+      const int any_fail = (DIAG & 1) ? 1 : __syncthreads_or(fail);
       if (!any_fail && !latched) {
         latched = true;
         latched_bits = bits;
@@ -805,6 +810,12 @@ dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc
         if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
         if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
         return bp_regular_kernel<6, 3, 384, 3>;
+      }
+      if (const char *de = getenv("KML_DEC_DIAG")) {  // timing ablations, wrong results (see the kernel's header)
+        const int dg = atoi(de);
+        if (dg == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 1>;
+        if (dg == 2) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 2>;
+        if (dg == 3) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 3>;
       }
       if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0, true>;
       if (r == 3) return bp_regular_kernel<6, 3, 384, 3, true, 3, true>;
