@@ -760,12 +760,13 @@ extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_
   int step = c->max_batch;
   if (B > 2 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, std::min(2048, (B + 1) / 2)));
   if (const char *e = getenv("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));  // tuning knob
-  int li = 0, chunk_no = 0;
+  int li = 0, chunk_no = 0, slow = 2;
+  if (const char *e = getenv("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));  // tuning knob
   for (int b0 = 0, nb = 0; b0 < B; b0 += nb, li ^= 1, chunk_no++) {
     Lane &l = c->lane[li];
     cudaStream_t s = l.stream;
     // slow start: the first copy is the only one nothing can hide, so the first two sub-batches are a quarter / a half
-    const int want = (B > 4 * step && chunk_no < 2) ? std::max(c->num_sms * 2, step >> (2 - chunk_no)) : step;
+    const int want = (B > 4 * step && chunk_no < slow) ? std::max(c->num_sms, step >> (slow - chunk_no)) : step;
     nb = std::min(want, B - b0);
     KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
     if (c->opts.known_h)

@@ -443,7 +443,8 @@ def test_multi_gpu_sweep_counters_identical(tmp_path, kb):
 
 
 @pytest.mark.parametrize("name,frames", [("peg2304_4psk_6db", 12000), ("peg2304_16qam_gray_12db", 8000),
-                                         ("peg2304_qpsk_10db", 6000), ("5g_16qam_gray_10db", 3000)])
+                                         ("peg2304_qpsk_10db", 6000), ("5g_16qam_gray_10db", 3000),
+                                         ("peg8064_64qam_20db", 1200)])
 def test_parity_statistics_at_scale(name, frames, kb):
     """north_star's acceptance numbers on thousands of reference frames (oracle ≡ reference bit for bit, run on all host
     cores): centroids within 1e-4 relative, rotation choice / decoder return value / frame-error flag identical,
