@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     for (int t = 0; t < p.iters; t++) {
       // ---- variable nodes (binaryldpccodec.cc:177-212)
       bits = 0;
+      uint32_t nbits = 0;  // complemented decisions (two-variable path)
       if (PACK && kExact && VPT % 2 == 0) {
         // Two variables per step, so that EVERY operation is packed.  With post = ch x0 x1 x2 the extrinsic ratio is
         // e_k = post / x_k, hence  s_k = min(e_k, 1) / (1 + e_k) = min(post, x_k) / (x_k + post)  and the hard bit is
@@ -184,8 +185,12 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           for (int k = 0; k < 3; k++)
             x[k] = make_float2(__uint_as_float(msg[va[j][k]]), __uint_as_float(msg[va[j + 1][k]]));
           const float2 post = mul2(mul2(make_float2(ch[j], ch[j + 1]), x[0]), mul2(x[1], x[2]));
-          const uint32_t ba = (post.x > 1.0f) ? 0u : 1u, bb = (post.y > 1.0f) ? 0u : 1u;  // tie → 1
-          bits |= (ba << j) | (bb << (j + 1));
+          // The messages carry the COMPLEMENT of the posterior decision: it is the sign bit of 1 - post (set iff
+          // post > 1, a tie gives +0 → decision 1 like the reference), one shift instead of FSETP + SEL on the
+          // half-rate ALU pipe; a row has six edges, so the XOR of the complements is the XOR of the decisions.
+          const float2 om = fma2(post, splat(-1.0f), splat(1.0f));
+          const uint32_t ba = __float_as_uint(om.x) >> 31, bb = __float_as_uint(om.y) >> 31;
+          nbits += (ba << j) + (bb << (j + 1));
 #pragma unroll
           for (int k = 0; k < 3; k++) {
             const float2 den = add2(x[k], post), sgn = fma2(x[k], splat(-1.0f), post);
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         msg[va[j][1]] = w1;
         msg[va[j][2]] = w2;
       }
+      if (PACK && kExact && VPT % 2 == 0) bits = ~nbits;
       if (!(DIAG & 1)) __syncthreads();
       // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
       int fail = 0;
