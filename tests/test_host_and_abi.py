@@ -96,3 +96,27 @@ def test_bit_packing_helpers_roundtrip():
     p = kb.pack_bits(b)
     assert p.shape == (5, 36) and np.array_equal(kb.unpack_bits(p, 1152), b)
     assert p[0, 0] & 1 == b[0, 0] and (p[0, 1] >> 3) & 1 == b[0, 35]
+
+
+@pytest.mark.parametrize("m,n,col_degs,seed,dup", [(150, 334, (1, 2, 3, 4), 1, False), (120, 300, (2, 3, 3, 3, 12), 2, False),
+                                                   (64, 200, (2, 3), 7, True)])
+def test_code_construction_on_random_irregular_matrices(tmp_path, m, n, col_degs, seed, dup):
+    """The bit-packed elimination against the oracle's byte-matrix restatement away from the three shipped matrices:
+    irregular degrees, an all-zero column, N not a multiple of 32, and (dup) a rank-deficient H with a repeated row."""
+    from tests.test_gpu_parity import _write_irregular_code
+    path = str(tmp_path / "irr.txt")
+    _write_irregular_code(path, m, n, col_degs, seed)
+    if dup:  # repeat row 3 as a new last row: rank stays m, the file declares m + 1 rows
+        lines = open(path).read().splitlines()
+        row3 = lines[3 + 3].split()
+        lines[1] = "%d\t%d\t%d" % (m + 1, n, m)
+        lines.append(" ".join([str(m)] + row3[1:]) + " ")
+        open(path, "w").write("\n".join(lines) + "\n")
+    code, oc = kb.LdpcCode(path), ko.Code(path, False, True)
+    ex = oc.export()
+    assert (code.M, code.N, code.K, code.n_chk) == (oc.M, oc.N, oc.K, oc.chk)
+    assert np.array_equal(code.perm, ex["perm"])
+    rp, ci = ex["row_ptr"], ex["col_idx"]
+    for r in range(code.M):
+        assert sorted(ci[rp[r]:rp[r + 1]]) == list(code.col_idx[code.row_ptr[r]:code.row_ptr[r + 1]])
+    assert np.array_equal(kb.unpack_bits(code.enc_rows, code.K), ex["enc_h"][:code.n_chk, code.n_chk:])
