@@ -216,8 +216,10 @@ typedef struct kml_sweep_cfg {
 
 /* Minimal TOML reader for exactly the keys above (the reference parses the same file with toml11, kmldpc.cpp:29-31). */
 int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg);
-/* Runs the sweep on n_gpus devices (one host thread per GPU, SNR points x frame ranges sharded, counters summed on the
- * host) and fills ber[n_points], fer[n_points], counters[n_points][4].  data_dir is prepended to relative file names.
+/* Runs the sweep on n_gpus devices (one host thread per GPU, frame ranges of every SNR point sharded; with n_gpus > 1 the
+ * per-GPU counters of a point are summed by one ncclAllReduce of 4 x uint64 over NVLink — libnccl.so.2 is opened at run
+ * time, a process without it sums on the host and says so on stderr) and fills ber[n_points], fer[n_points],
+ * counters[n_points][4].  data_dir is prepended to relative file names.
  * log_cb (may be NULL) receives the reference-format lines ("SNR = … Total blk = …", "BER Result", …). */
 int kml_sweep_points(const kml_sweep_cfg *cfg);
 int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,

@@ -1,8 +1,10 @@
 // Host-side sweep driver: what Simulator::Simulator + Simulator::Simulate + Simulator::run do around the per-frame loop
 // (src/simulator.cc:3-109), on top of kml_simulate.  One host thread per GPU; frames of an SNR point are handed out in
-// chunks from a shared cursor; the 64-bit counters are summed on the host; lines are formatted exactly like
-// SourceSink::PrintResult (lib/lab/src/sourcesink.cc:50-65) and the result tables of simulator.cc:48-66.
+// chunks from a shared cursor; with more than one GPU the per-GPU 64-bit counters of a point are summed by ONE
+// ncclAllReduce over NVLink (single process, ncclCommInitAll — the path's only collective); lines are
+// formatted exactly like SourceSink::PrintResult (lib/lab/src/sourcesink.cc:50-65) and the tables of simulator.cc:48-66.
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cctype>
 #include <cmath>
@@ -18,9 +20,119 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "kml_internal.h"
 
 namespace {
+
+// ---- the counter reduction over NCCL.  libnccl is opened at run time (dlopen), not linked: a host process that already
+// carries an NCCL (torch bundles its own) keeps exactly one copy, and a single-GPU run never touches it.
+class CounterReducer {
+ public:
+  // returns false (with `why`) when NCCL cannot be used; the caller then sums on the host and says so on stderr
+  bool init(int n_gpus, std::string &why) {
+    G_ = n_gpus;
+    for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+      lib_ = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+      if (lib_) break;
+    }
+    if (!lib_) {
+      why = std::string("dlopen(libnccl.so.2): ") + dlerror();
+      return false;
+    }
+#define KML_SYM(f)                                         \
+  f##_ = reinterpret_cast<decltype(&f)>(dlsym(lib_, #f)); \
+  if (!f##_) {                                             \
+    why = "libnccl lacks " #f;                             \
+    return false;                                          \
+  }
+    KML_SYM(ncclCommInitAll) KML_SYM(ncclCommDestroy) KML_SYM(ncclAllReduce) KML_SYM(ncclGroupStart) KML_SYM(ncclGroupEnd)
+    KML_SYM(ncclGetErrorString)
+#undef KML_SYM
+    comms_.assign(G_, nullptr);
+    std::vector<int> devs(G_);
+    for (int g = 0; g < G_; g++) devs[g] = g;
+    ncclResult_t r = ncclCommInitAll_(comms_.data(), G_, devs.data());
+    if (r != ncclSuccess) {
+      why = std::string("ncclCommInitAll: ") + ncclGetErrorString_(r);
+      comms_.clear();
+      return false;
+    }
+    dbuf_.assign(G_, nullptr);
+    st_.assign(G_, nullptr);
+    for (int g = 0; g < G_; g++) {
+      if (cudaSetDevice(g) != cudaSuccess || cudaMalloc(&dbuf_[g], 4 * sizeof(unsigned long long)) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&st_[g], cudaStreamNonBlocking) != cudaSuccess) {
+        why = "device buffers for the counter reduction";
+        return false;
+      }
+    }
+    ok_ = true;
+    return true;
+  }
+  bool ok() const { return ok_; }
+  // mine[g][0..3] = counters GPU g accumulated for this point; tot = their sum (read back from GPU 0)
+  bool reduce(const std::vector<std::array<uint64_t, 4>> &mine, uint64_t tot[4], std::string &why) {
+    for (int g = 0; g < G_; g++) {
+      cudaSetDevice(g);
+      if (cudaMemcpyAsync(dbuf_[g], mine[g].data(), 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st_[g]) != cudaSuccess) {
+        why = "cudaMemcpyAsync (counters)";
+        return false;
+      }
+    }
+    ncclGroupStart_();
+    for (int g = 0; g < G_; g++) {
+      ncclResult_t r = ncclAllReduce_(dbuf_[g], dbuf_[g], 4, ncclUint64, ncclSum, comms_[g], st_[g]);
+      if (r != ncclSuccess) {
+        ncclGroupEnd_();
+        why = std::string("ncclAllReduce: ") + ncclGetErrorString_(r);
+        return false;
+      }
+    }
+    ncclResult_t r = ncclGroupEnd_();
+    if (r != ncclSuccess) {
+      why = std::string("ncclGroupEnd: ") + ncclGetErrorString_(r);
+      return false;
+    }
+    for (int g = 0; g < G_; g++) {
+      cudaSetDevice(g);
+      if (g == 0) cudaMemcpyAsync(tot, dbuf_[0], 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_[0]);
+      if (cudaStreamSynchronize(st_[g]) != cudaSuccess) {
+        why = "stream sync after the counter reduction";
+        return false;
+      }
+    }
+    return true;
+  }
+  ~CounterReducer() {
+    for (int g = 0; g < (int)st_.size(); g++) {
+      cudaSetDevice(g);
+      if (st_[g]) cudaStreamDestroy(st_[g]);
+      if (dbuf_[g]) cudaFree(dbuf_[g]);
+    }
+    if (ncclCommDestroy_)
+      for (ncclComm_t c : comms_)
+        if (c) ncclCommDestroy_(c);
+    // the library stays open: other users of the process (torch) may share it
+  }
+
+ private:
+  int G_ = 0;
+  bool ok_ = false;
+  void *lib_ = nullptr;
+  decltype(&ncclCommInitAll) ncclCommInitAll_ = nullptr;
+  decltype(&ncclCommDestroy) ncclCommDestroy_ = nullptr;
+  decltype(&ncclAllReduce) ncclAllReduce_ = nullptr;
+  decltype(&ncclGroupStart) ncclGroupStart_ = nullptr;
+  decltype(&ncclGroupEnd) ncclGroupEnd_ = nullptr;
+  decltype(&ncclGetErrorString) ncclGetErrorString_ = nullptr;
+  std::vector<ncclComm_t> comms_;
+  std::vector<void *> dbuf_;
+  std::vector<cudaStream_t> st_;
+};
 
 using kml::set_global_error;
 
@@ -243,6 +355,13 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
         set_global_error(errs[g]);
       }
   }
+  CounterReducer reducer;
+  if (rc == KML_OK && G > 1) {
+    const char *force = getenv("KML_SWEEP_REDUCE");  // "host": sum on the host (A/B and test knob)
+    std::string why = "KML_SWEEP_REDUCE=host";
+    if ((force && std::string(force) == "host") || !reducer.init(G, why))
+      fprintf(stderr, "kmldpc_b200: counters of the %d GPUs are summed on the host (%s)\n", G, why.c_str());
+  }
   if (rc == KML_OK) {
     int32_t info[8];
     kml_info(ctx[0], info);
@@ -250,8 +369,8 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     for (int i = 0; i < n_pts && rc == KML_OK; i++) {
       const double snr = cfg->min_snr + cfg->step_snr * i;
       std::atomic<uint64_t> cursor{0}, err_blk{0};
-      std::mutex mu;
       uint64_t tot[4] = {0, 0, 0, 0};
+      std::vector<std::array<uint64_t, 4>> mine(G, std::array<uint64_t, 4>{0, 0, 0, 0});  // per GPU, this point
       std::atomic<int> failed{KML_OK};
       // histogram mode (simulator.cc:81-84,154-162): "histogram_<snr>.txt" in the working directory, one line per frame
       // with the four metrics rotated to start at the (first) minimum; frames in index order on GPU 0.
@@ -288,15 +407,26 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
             set_global_error(kml_last_error(ctx[g]));
             break;
           }
-          err_blk.fetch_add(cnt[1]);
-          std::lock_guard<std::mutex> lk(mu);
-          for (int k = 0; k < 4; k++) tot[k] += cnt[k];
+          err_blk.fetch_add(cnt[1]);  // (the stop rule polls this host-side total while frames are in flight)
+          for (int k = 0; k < 4; k++) mine[g][k] += cnt[k];
         }
       };
       std::vector<std::thread> th;
       for (int g = 0; g < G; g++) th.emplace_back(worker, g);
       for (auto &t : th) t.join();
       if (rc == KML_OK) rc = failed.load();
+      if (!cfg->histogram_enable) {
+        std::string why;
+        if (reducer.ok() && rc == KML_OK) {  // the path's one collective: 4 x uint64 per point over NCCL / NVLink
+          if (!reducer.reduce(mine, tot, why)) {
+            set_global_error("counter reduction: " + why);
+            rc = KML_ERR_CUDA;
+          }
+        } else {
+          for (int g = 0; g < G; g++)
+            for (int k = 0; k < 4; k++) tot[k] += mine[g][k];
+        }
+      }
       const double b = tot[2] ? (double)tot[3] / (double)tot[2] : 0.0, f = tot[0] ? (double)tot[1] / (double)tot[0] : 0.0;
       ber_v[i] = b;
       fer_v[i] = f;
