@@ -11,7 +11,11 @@ CASES = [("PEG2304 + 4bit_16QAM_Gray (blind)", "PEG2304regular0.5.txt", "4bit_16
          ("PEG2304 + 2bits_QPSK (blind; 0/180 tie floor)", "PEG2304regular0.5.txt", "2bits_QPSK.txt", False, False, [0, 5, 10, 15, 20]),
          ("PEG2304 + 2bits_4PSK (blind)", "PEG2304regular0.5.txt", "2bits_4PSK.txt", False, False, [0, 5, 10, 15, 20]),
          ("PEG2304 + 4bit_16QAM_phi1 (known h)", "PEG2304regular0.5.txt", "4bit_16QAM_phi1.txt", False, True, [10, 15, 20]),
-         ("5G BG2 K960 + 4bit_16QAM_Gray (blind, metric = 4 x 5 iterations)", "5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, False, [6, 10, 14, 18])]
+         ("5G BG2 K960 + 4bit_16QAM_Gray (blind, metric = 4 x 5 iterations)", "5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, False, [6, 10, 14, 18]),
+         ("PEG8064 + 6bits_64QAM_Gray (blind)", "PEG8064regular0.5.txt", "6bits_64QAM_Gray.txt", False, False, [15, 20, 25, 30])]
+only = os.environ.get("ONLY")
+if only:
+    CASES = [c for c in CASES if only in c[0]]
 GPU_FRAMES, REF_FRAMES = int(os.environ.get("GPU_FRAMES", 200000)), int(os.environ.get("REF_FRAMES", 6000))
 out = []
 for name, mat, mod, g5, known, snrs in CASES:
