@@ -34,6 +34,33 @@ __global__ void __launch_bounds__(T, 2) lds_kernel(float *out) {
   out[blockIdx.x * T + threadIdx.x] = acc0 + acc1 + acc2 + acc3;
 }
 
+// stores, and the decoder's mix (one load + one store per word, both conflict free, addresses walking the window)
+template <int W, bool MIX>
+__global__ void __launch_bounds__(T, 2) sts_kernel(float *out) {
+  extern __shared__ __align__(16) float sm[];
+  for (int i = threadIdx.x; i < 8192; i += T) sm[i] = (float)i;
+  __syncthreads();
+  float acc = 0.f;
+  const int base = (threadIdx.x * W) & 8191;
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int a = (base + (it * 8 + u) * 1056) & (8191 & ~(W - 1));
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(sm + a);
+      float v = acc + (float)u;
+      if (MIX) {
+        if (W == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sa));
+        if (W == 2) { float w; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v), "=f"(w) : "r"(sa)); v += w; }
+        acc += v;
+      }
+      if (W == 1) asm volatile("st.shared.f32 [%0], %1;" :: "r"(sa), "f"(v) : "memory");
+      if (W == 2) asm volatile("st.shared.v2.f32 [%0], {%1,%1};" :: "r"(sa), "f"(v) : "memory");
+      if (W == 4) asm volatile("st.shared.v4.f32 [%0], {%1,%1,%1,%1};" :: "r"(sa), "f"(v) : "memory");
+    }
+  }
+  out[blockIdx.x * T + threadIdx.x] = acc + sm[threadIdx.x];
+}
+
 enum Op { OP_RCP, OP_LOP3, OP_FMNMX, OP_FSEL, OP_FFMA, OP_FFMA2 };
 template <int OP>
 __global__ void __launch_bounds__(T, 2) alu_kernel(float *out, float seed) {
@@ -80,6 +107,11 @@ int main() {
     double bps = loads * W * 4 / (ms * 1e-3); \
     printf("LDS.%-3d  %8.1f GB/s  = %6.1f B/clk/SM\n", 32 * W, bps * 1e-9, bps / sms / (ghz * 1e9)); }
   LDS(1) LDS(2) LDS(4)
+#define STS(W, MIX, name) { CK(cudaFuncSetAttribute(sts_kernel<W, MIX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768)); \
+    float ms = time_ms([&] { sts_kernel<W, MIX><<<grid, T, 32768>>>(out); }); CK(cudaGetLastError()); \
+    double bps = loads * W * 4 * (MIX ? 2 : 1) / (ms * 1e-3); \
+    printf("%-16s %8.1f GB/s  = %6.1f B/clk/SM\n", name, bps * 1e-9, bps / sms / (ghz * 1e9)); }
+  STS(1, false, "STS.32") STS(2, false, "STS.64") STS(4, false, "STS.128") STS(1, true, "LDS.32+STS.32") STS(2, true, "LDS.64+STS.64")
   const double ops = (double)grid * T * ITERS * 8;
 #define ALU(OP, name, mult) { float ms = time_ms([&] { alu_kernel<OP><<<grid, T>>>(out, 1.0001f); }); CK(cudaGetLastError()); \
     double ps = ops * mult / (ms * 1e-3); printf("%-10s %8.2f T lane-ops/s = %6.1f per clk per SM\n", name, ps * 1e-12, ps / sms / (ghz * 1e9)); }
