@@ -9,7 +9,8 @@
 //     variable nodes multiply ratios: extrinsic_e = L_ch * prod_{e' != e} x_e'  (reference: alpha/beta products with
 //     per-step renormalisation, which cancels in the ratio).
 //   * variable→check message: (hard bit h, small probability s <= 0.5): P(bit = h) = 1 - s.  s is computed directly
-//     as min(x,1)/(1+x), so probabilities as small as 1e-36 keep full relative precision — the fp32 analogue of the
+//     as min(x,1)/(1+x) (in the regular kernel in the division-free form min(post, x_k)/(x_k + post) with post the
+//     product of all ratios), so probabilities as small as 1e-36 keep full relative precision — the fp32 analogue of the
 //     reference carrying both members of the pair in fp64.  A word packs s, the extrinsic hard bit in the SIGN bit
 //     (so the check node reads s as |word| — a free operand modifier on FFMA2/FFMA/FMNMX) and the POSTERIOR hard
 //     decision of the variable in the mantissa LSB (a 1-ulp perturbation of s), so the check phase can evaluate the
@@ -18,9 +19,12 @@
 //     probabilities (all terms positive → no cancellation) and XOR on the hard bits; forward/backward partial
 //     combinations give every extrinsic output in 3(d-2) combines.
 //
-// One CTA decodes one frame at a time (persistent CTAs, dynamic frame queue).  Per iteration and edge the kernel makes
-// 4 shared-memory word accesses (16 B), 2 MUFU.RCP and ~27 issue slots; nothing but the channel ratios (4 B/variable,
-// coalesced) and the packed decisions (1 bit/variable) touches HBM.
+// One CTA decodes one frame at a time (persistent CTAs, dynamic frame queue).  Per iteration and edge the regular kernel
+// makes 4 shared-memory word accesses (16 B), 2 MUFU.RCP and ~19.5 issue slots; nothing but the channel ratios
+// (4 B/variable, coalesced) and the packed decisions (1 bit/variable) touches HBM.
+//
+// Three kernels: bp_regular_kernel ((3,6)-regular PEG codes, everything unrolled), bp_qc_kernel (quasi-cyclic codes with a
+// compile-time plan: 5G BG2), bp_generic_kernel (any other Tanner graph, run-time work lists).
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
@@ -32,7 +36,6 @@
 namespace kml {
 namespace {
 
-constexpr float kClampLo = 1.0e-36f, kClampHi = 1.0e36f;
 constexpr float kLlrClip = 27.631021f;  // ln((1-1e-12)/1e-12)
 
 __device__ __forceinline__ float rcp_approx(float x) {
