@@ -449,6 +449,8 @@ def test_parity_statistics_at_scale(name, frames, kb):
     """north_star's acceptance numbers on thousands of reference frames (oracle ≡ reference bit for bit, run on all host
     cores): centroids within 1e-4 relative, rotation choice / decoder return value / frame-error flag identical,
     hard decisions bit-identical on >= 99.99 % of the frames the reference converges on."""
+    import os
+    frames *= int(os.environ.get("KML_PARITY_SCALE", "1"))  # profiles/: the same test on 5x the frames
     olink = util.oracle_link(name)
     snr = util.CASES[name][2]
     ref = olink.bulk(snr, frames)
