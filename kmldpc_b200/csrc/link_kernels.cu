@@ -151,35 +151,62 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const 
 // ------------------------------------------------------------------------------------------------ mapper + channel
 // Modem::Mapping (lib/lab/src/modem.cc:12-20), the fading draw (src/simulator.cc:120-128) and
 // ModemLinearSystem::PartitionHAWGNSystem (lib/lab/src/modemlinearsystem.cc:37-48): y = h x + (sigma/sqrt2) (a + jb)
-__global__ void channel_kernel(GenParams g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
-                               float2 *h_out, float2 *y) {
+__device__ __forceinline__ float2 map_symbol(const GenParams &g, const uint32_t *c, int sidx) {
+  int idx = 0;
+  const int b0 = sidx * g.bits_per_symbol;
+  for (int j = 0; j < g.bits_per_symbol; j++) {  // MSB first
+    const int t = b0 + j;
+    idx = (idx << 1) | (int)((c[t >> 5] >> (t & 31)) & 1u);
+  }
+  return __ldg(g.points + idx);
+}
+
+// replay of given fades / noise (parity tests against the reference's own channel outputs): one thread per symbol
+__global__ void channel_replay_kernel(GenParams g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise, float2 *y) {
   const long long total = (long long)g.B * g.n_sym;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i / g.n_sym), sidx = (int)(i % g.n_sym);
+    const float2 x = map_symbol(g, c_packed + (size_t)f * g.tx_words, sidx), h = h_in[f], nz = noise[i];
+    y[i] = make_float2(h.x * x.x - h.y * x.y + g.sigma_over_sqrt2 * nz.x, h.x * x.y + h.y * x.x + g.sigma_over_sqrt2 * nz.y);
+  }
+}
+
+// Philox channel.  The fade is drawn once per frame (fade_kernel); one Philox4x32-10 call feeds the noise of TWO symbols
+// (counter = (symbol pair, frame, stream): independent of batch size, launch shape and GPU count).
+__global__ void fade_kernel(GenParams g, float2 *h_out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= g.B) return;
+  const Philox4 rh = philox_at(g.seed, STREAM_FADE, g.frame0 + f, 0);
+  const float2 gh = gauss_pair(rh.x, rh.y);
+  h_out[f] = make_float2(gh.x * 0.70710678118654752f, gh.y * 0.70710678118654752f);  // CN(0,1)
+}
+
+__global__ void channel_kernel(GenParams g, const uint32_t *c_packed, const float2 *h, float2 *y) {
+  const int pairs = (g.n_sym + 1) >> 1;
+  const long long total = (long long)g.B * pairs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / pairs), pp = (int)(i % pairs);
     const uint32_t *c = c_packed + (size_t)f * g.tx_words;
-    int idx = 0;
-    const int b0 = sidx * g.bits_per_symbol;
-    for (int j = 0; j < g.bits_per_symbol; j++) {  // MSB first
-      const int t = b0 + j;
-      idx = (idx << 1) | (int)((c[t >> 5] >> (t & 31)) & 1u);
-    }
-    const float2 x = __ldg(g.points + idx);
-    float2 h, nz;
-    if (noise) {
-      h = h_in[f];
-      nz = noise[i];
+    const float2 hf = h[f];
+    const Philox4 rn = philox_at(g.seed, STREAM_NOISE, g.frame0 + f, (uint32_t)pp);
+    const float2 n0 = gauss_pair(rn.x, rn.y), n1 = gauss_pair(rn.z, rn.w);
+    float2 *yo = y + (size_t)f * g.n_sym + 2 * pp;
+    const float2 x0 = map_symbol(g, c, 2 * pp);
+    const float2 o0 = make_float2(hf.x * x0.x - hf.y * x0.y + g.sigma_over_sqrt2 * n0.x,
+                                  hf.x * x0.y + hf.y * x0.x + g.sigma_over_sqrt2 * n0.y);
+    if (2 * pp + 1 < g.n_sym) {
+      const float2 x1 = map_symbol(g, c, 2 * pp + 1);
+      const float2 o1 = make_float2(hf.x * x1.x - hf.y * x1.y + g.sigma_over_sqrt2 * n1.x,
+                                    hf.x * x1.y + hf.y * x1.x + g.sigma_over_sqrt2 * n1.y);
+      if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {  // one 128-bit store for the pair
+        *reinterpret_cast<float4 *>(yo) = make_float4(o0.x, o0.y, o1.x, o1.y);
+      } else {
+        yo[0] = o0;
+        yo[1] = o1;
+      }
     } else {
-      const Philox4 rh = philox_at(g.seed, STREAM_FADE, g.frame0 + f, 0);
-      const float2 gh = gauss_pair(rh.x, rh.y);
-      h = make_float2(gh.x * 0.70710678118654752f, gh.y * 0.70710678118654752f);  // CN(0,1)
-      const Philox4 rn = philox_at(g.seed, STREAM_NOISE, g.frame0 + f, (uint32_t)sidx);
-      nz = gauss_pair(rn.x, rn.y);
-      if (sidx == 0 && h_out) h_out[f] = h;
+      yo[0] = o0;
     }
-    float2 o;
-    o.x = h.x * x.x - h.y * x.y + g.sigma_over_sqrt2 * nz.x;
-    o.y = h.x * x.y + h.y * x.x + g.sigma_over_sqrt2 * nz.y;
-    y[i] = o;
   }
 }
 
@@ -860,7 +887,13 @@ cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t
 
 cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
                            float2 *h_out, float2 *y, cudaStream_t s) {
-  channel_kernel<<<grid_for((long long)g.B * g.n_sym, 256), 256, 0, s>>>(g, c_packed, h_in, noise, h_out, y);
+  if (noise) {
+    channel_replay_kernel<<<grid_for((long long)g.B * g.n_sym, 256), 256, 0, s>>>(g, c_packed, h_in, noise, y);
+    return cudaGetLastError();
+  }
+  if (!h_out) return cudaErrorInvalidValue;  // the Philox channel always reports its fades
+  fade_kernel<<<(g.B + 255) / 256, 256, 0, s>>>(g, h_out);
+  channel_kernel<<<grid_for((long long)g.B * ((g.n_sym + 1) / 2), 256), 256, 0, s>>>(g, c_packed, h_out, y);
   return cudaGetLastError();
 }
 
