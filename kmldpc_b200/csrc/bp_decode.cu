@@ -27,6 +27,7 @@
 // compile-time plan: 5G BG2), bp_generic_kernel (any other Tanner graph, run-time work lists).
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <utility>
 
 #include "kml_internal.h"
@@ -165,8 +166,12 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     float ch[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; j++) ch[j] = (kExact || j * T + tid < NV) ? load_channel_ratio(in, j * T + tid, p.in_is_lr) : 1.0f;
-    for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
-    __syncthreads();
+    constexpr bool kPair = PACK && kExact && VPT % 2 == 0;  // two-variable variable nodes (below)
+    if (!kPair) {
+      for (int i = tid; i < n_words; i += T) msg[i] = 0x3f800000u;  // InitMsg: c2v = (0.5, 0.5) → ratio 1
+      __syncthreads();
+    }  // (kPair: the first variable phase takes x = 1 instead of reading, and writes every word — no initialisation pass,
+       //  which is a fifth of the work of a frame that converges in four iterations)
 
     uint32_t bits = 0, latched_bits = 0;
     int ret = p.iters + (p.iters < p.max_iter);
@@ -176,7 +181,9 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
       // ---- variable nodes (binaryldpccodec.cc:177-212)
       bits = 0;
       uint32_t nbits = 0;  // complemented decisions (two-variable path)
-      if (PACK && kExact && VPT % 2 == 0) {
+      if (kPair) {
+       auto vn2 = [&](auto first_tag) {
+        constexpr bool kFirst = decltype(first_tag)::value;  // iteration 0: every c2v is InitMsg's ratio 1
         // Two variables per step, so that EVERY operation is packed.  With post = ch x0 x1 x2 the extrinsic ratio is
         // e_k = post / x_k, hence  s_k = min(e_k, 1) / (1 + e_k) = min(post, x_k) / (x_k + post)  and the hard bit is
         // the sign of post - x_k: the three e_k are never formed.  fp32 range: post overflows / underflows only when
@@ -186,7 +193,8 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           float2 x[3];
 #pragma unroll
           for (int k = 0; k < 3; k++)
-            x[k] = make_float2(__uint_as_float(msg[va[j][k]]), __uint_as_float(msg[va[j + 1][k]]));
+            x[k] = kFirst ? splat(1.0f)
+                          : make_float2(__uint_as_float(msg[va[j][k]]), __uint_as_float(msg[va[j + 1][k]]));
           const float2 post = mul2(mul2(make_float2(ch[j], ch[j + 1]), x[0]), mul2(x[1], x[2]));
           // The messages carry the COMPLEMENT of the posterior decision: it is the sign bit of 1 - post (set iff
           // post > 1, a tie gives +0 → decision 1 like the reference), one shift instead of FSETP + SEL on the
@@ -203,6 +211,9 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
             msg[va[j + 1][k]] = v2c_pack(sgn.y, s2.y, bb);
           }
         }
+       };
+       if (t == 0) vn2(std::true_type{});
+       else vn2(std::false_type{});
       } else
 #pragma unroll
       for (int j = 0; j < VPT; j++) {
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
         msg[va[j][1]] = w1;
         msg[va[j][2]] = w2;
       }
-      if (PACK && kExact && VPT % 2 == 0) bits = ~nbits;
+      if (kPair) bits = ~nbits;
       if (!(DIAG & 1)) __syncthreads();
       // ---- check nodes + syndrome of the decisions just made (binaryldpccodec.cc:217-275)
       int fail = 0;
