@@ -10,7 +10,9 @@
  * (0/1) in the stage entry points — exactly the reference's `int *uu / *cc` — and bit-packed uint32 words
  * (bit t of a frame = word t/32, bit t%32) where a name says `_packed`.  Pointers are HOST pointers unless the
  * function name ends in `_dev`; `_dev` variants take device pointers plus a cudaStream_t passed as void*.
- * A context is owned by one host thread.
+ * A context is owned by one host thread.  `_dev` calls are asynchronous on the caller's stream and share
+ * one work space per context: calls issued on different streams are ordered on the device (each waits for the event the
+ * previous one recorded), so they are safe but do not overlap — use one context per concurrent stream.
  */
 #ifndef KMLDPC_B200_H
 #define KMLDPC_B200_H
@@ -134,6 +136,13 @@ int kml_modulate(kml_ctx *ctx, int B, const int32_t *c, const float *h, const fl
  *     compiled semantics (cumulative sums, cluster 0 anchor).  y[B][n_sym][2] -> hhat[B][2]; passes[B] (may be NULL)
  *     = number of assignment passes executed. */
 int kml_kmeans(kml_ctx *ctx, int B, const float *y, float *hhat, int32_t *passes);
+/*     The same on the reference's own types: y = std::vector<std::complex<double>> received symbols of B frames
+ *     (KMeans ctor, src/kmeans.cc:4-10; ModemLinearSystem::GetRecvSymbol) as double [B][n_sym][2]; hhat[B][2] double =
+ *     clusters()[0] / constellations[0] as carried in fp64.  The samples are narrowed to fp32 on the device only for the
+ *     kernel's first-pass filter; every assignment that the filter cannot decide, the anchor choice and all sums use
+ *     the double values, so the estimate follows the reference to ~1e-12 relative instead of the ~1e-7 an fp32 input
+ *     allows (tests/test_gpu_parity.py). */
+int kml_kmeans_f64(kml_ctx *ctx, int B, const double *y, double *hhat, int32_t *passes);
 
 /* A7+A8  ModemLinearSystem::DeMapping (modemlinearsystem.cc:51-98, modem.cc:23-79) with all bit priors 0.5
  *     (kmcodec.cc:92-103).  One channel estimate per frame: h[B][2].  Output llr[B][n_tx] = ln(P(bit=0)/P(bit=1))
@@ -148,12 +157,31 @@ int kml_resolve(kml_ctx *ctx, int B, const float *y, const float *hhat, double v
  *     llr[B][n_tx] -> cc_hat[B][n_graph], uu_hat[B][k] (int32, either may be NULL), ret[B] = iter + (iter < max_iter)
  *     exactly like the reference's return value.  iter_count as in Decoder(M2V, uu_hat, iter_count). */
 int kml_decode(kml_ctx *ctx, int B, const float *llr, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret);
+/*     The reference's own signature, BinaryLDPCCodec::Decoder(const double *M2V, int *uu_hat, int iter_count)
+ *     (binaryldpccodec.cc:165): p0[B][n_tx] = P(bit = 0) in double, as KmCodec::DeMapping leaves it in bit_l_out_
+ *     (kmcodec.cc:92-103).  The ratio P0 / (1 - P0) is formed in fp64 on the device. */
+int kml_decode_p0(kml_ctx *ctx, int B, const double *p0, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret);
 
 /* KmCodec::Decoder (kmcodec.cc:54-72) preceded by the k-means block of Simulator::run_blocks (simulator.cc:131-148):
  *     the whole receiver for B frames.  y[B][n_sym][2]; true_h[B][2] is read only when opts.known_h.
  *     Outputs (any may be NULL): uu_hat_packed[B][ceil(k/32)], hhat[B][2], kstar[B], ret[B]. */
 int kml_receive(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
                 float *hhat, int32_t *kstar, int32_t *ret);
+
+/*     The same seam on the reference's types (the arguments of KmCodec::Decoder, kmcodec.cc:54-72, batched):
+ *     y[B][n_sym][2] and true_h[B][2] are std::complex<double> as double pairs; hhat[B][2] double.  The conversion to the
+ *     kernels' fp32 happens on the device, inside this call. */
+int kml_receive_f64(kml_ctx *ctx, int B, const double *y, const double *true_h, double var, uint32_t *uu_hat_packed,
+                    double *hhat, int32_t *kstar, int32_t *ret);
+
+/* Soft-syndrome metric ([xcodec] metric_type = true) only: the reference's syndrom_soft_ array is written by the
+ * decoder's check-node phase alone (binaryldpccodec.cc:274), so a Decoder call that leaves at iteration 0
+ * (binaryldpccodec.cc:231-232) leaves it as the PREVIOUS call did, and Metric() (kmcodec.cc:146-155) then sums stale
+ * values.  The context carries that state — the sum of ln(syndrom_soft_[r]) after its last Decoder call — from frame to
+ * frame and call to call, in frame order, exactly like one reference codec object does (a fresh context starts from
+ * syndrom_soft_ = 1, i.e. 0; the reference's array starts uninitialised).  set = 0 reads it into *value, set = 1
+ * writes it (e.g. to start an independent run). */
+int kml_soft_syndrome_state(kml_ctx *ctx, int set, double *value);
 
 /* A11 SourceSink::CntErr (sourcesink.cc:29-47) for B frames: counters[4] += {tot_blk, err_blk, tot_bit, err_bit}
  *     (64-bit; the reference's 32-bit counters wrap at 3.7 M frames).  u_packed / uu_hat_packed [B][ceil(k/32)]. */
@@ -180,6 +208,13 @@ int kml_simulate(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begi
  * (zero) buffer (hard metric). */
 int kml_histogram(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count, float *metrics,
                   uint64_t counters[4]);
+
+/* The same on GIVEN frames — the KmCodec::GetHistogramData seam itself (kmcodec.cc:74-79) followed by the CntErr of
+ * simulator.cc:167: y[B][n_sym][2] received symbols, u_packed[B][ceil(k/32)] the transmitted information bits.
+ * Outputs: metrics[B][4]; kstar[B] (may be NULL) = index of the first minimum, where the line of histogram_<snr>.txt
+ * starts; uu_hat_packed (may be NULL) = the buffer CntErr ran on; counters[4] accumulated. */
+int kml_histogram_rx(kml_ctx *ctx, int B, const float *y, double var, const uint32_t *u_packed, float *metrics,
+                     int32_t *kstar, uint32_t *uu_hat_packed, uint64_t counters[4]);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Device-pointer variants (inputs already resident in HBM; asynchronous on `stream`)

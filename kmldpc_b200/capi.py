@@ -65,13 +65,18 @@ SYMBOLS = {
     "kml_generate": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, c_i32p, c_i32p, c_f32p, c_f32p]),
     "kml_modulate": (C.c_int, [C.c_void_p, C.c_int, c_i32p, c_f32p, c_f32p, C.c_double, c_f32p]),
     "kml_kmeans": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, c_i32p]),
+    "kml_kmeans_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, c_i32p]),
     "kml_demap": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_f32p]),
     "kml_resolve": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_f32p, c_i32p]),
     "kml_decode": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_i32p, c_i32p, c_i32p]),
+    "kml_decode_p0": (C.c_int, [C.c_void_p, C.c_int, c_f64p, C.c_int, c_i32p, c_i32p, c_i32p]),
+    "kml_receive_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, C.c_double, c_u32p, c_f64p, c_i32p, c_i32p]),
+    "kml_soft_syndrome_state": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
     "kml_receive": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p]),
     "kml_count_errors": (C.c_int, [C.c_void_p, C.c_int, c_u32p, c_u32p, c_u64p]),
     "kml_simulate": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, c_u64p, c_u64p]),
     "kml_histogram": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, c_f32p, c_u64p]),
+    "kml_histogram_rx": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_u32p, c_u64p]),
     "kml_generate_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
     "kml_kmeans_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -90,6 +90,14 @@ __device__ __forceinline__ float c2v_ratio(float s, uint32_t x, uint32_t w) {
   return q;
 }
 
+// ln(syndrom_soft[r]) (binaryldpccodec.cc:274): syndrom_soft = P(check satisfied) = the row's small probability when its
+// hard bits have odd parity, 1 - s otherwise — taken as log1p(-s) so that rows the decoder is sure of still contribute
+// their ~ -s (the reference sums them in fp64)
+__device__ __forceinline__ float soft_log(uint32_t odd, float s) {
+  if (odd) return __logf(s);
+  return s < 0.01f ? -s * fmaf(s, fmaf(s, 0.33333334f, 0.5f), 1.0f) : __logf(1.0f - s);
+}
+
 __device__ __forceinline__ float load_channel_ratio(const float *in, int idx, int in_is_lr) {
   float v = __ldg(in + idx);
   if (!in_is_lr) v = __expf(fminf(fmaxf(v, -kLlrClip), kLlrClip));
@@ -158,10 +166,10 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
   }
 
   while (true) {
-    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s_frame = next_frame(p);
     __syncthreads();
     const int f = s_frame;
-    if (f >= p.B) break;
+    if (f < 0) break;
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     float ch[VPT];
 #pragma unroll
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
           if (SOFT) sall = sp_chain(pre[5], s[5], tt[5]);
         }
         if (SOFT)  // syndrom_soft[r] = P(check satisfied) = row_head.alpha[0] (binaryldpccodec.cc:274)
-          soft += __logf((x >> 31) ? sall : 1.0f - sall);
+          soft += soft_log(x >> 31, sall);
       }
       const int any_fail = (DIAG & 1) ? 1 : __syncthreads_or(fail);
       if (!any_fail && !latched) {
@@ -378,9 +386,10 @@ __global__ void __launch_bounds__(T, MINB) bp_regular_kernel(const DecParams p) 
     if (SOFT) {
       // NOTE: when the reference leaves at t = 0 its syndrom_soft_ is stale (left over from the previous call);
       // here that case reports 0.
+      double sd = (double)soft_out;  // per-thread partial sums are short; everything across threads is fp64
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
-      if (lane == 0) atomicAdd(p.out_soft + f, soft_out);
+      for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      if (lane == 0) atomicAdd(p.out_soft + f, sd);
     }
   }
 }
@@ -522,7 +531,7 @@ __device__ __forceinline__ uint32_t cn_node(uint32_t *row, float *s_all) {
         float s_all = 0.0f;                                                                 \
         const uint32_t x = cn_node<(D <= DC ? D : 1), SOFT>(msg + slot * RS, &s_all);       \
         fail += (int)(x & 1u);                                                              \
-        if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);                         \
+        if (SOFT) soft += soft_log(x >> 31, s_all);                                         \
       }                                                                                     \
     }                                                                                       \
     break;
@@ -576,10 +585,10 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
   uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);      // [2][words_n] decisions, double buffered
 
   while (true) {
-    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s_frame = next_frame(p);
     __syncthreads();
     const int f = s_frame;
-    if (f >= p.B) break;
+    if (f < 0) break;
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     for (int v = tid; v < n; v += T)  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
       chan[v] = v < p.t.punct ? 1.0f : load_channel_ratio(in, v - p.t.punct, p.in_is_lr);
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
               if (deg == 0) continue;  // padding slot
               const uint32_t x = cn_lane_dispatch<DC, SOFT>(msg + slot * RS, &s_all, deg);
               fail += (int)(x & 1u);
-              if (SOFT) soft += __logf((x >> 31) ? s_all : 1.0f - s_all);
+              if (SOFT) soft += soft_log(x >> 31, s_all);
             }
             break;
         }
@@ -663,9 +672,10 @@ __global__ void __launch_bounds__(kGenericThreads, 3) bp_generic_kernel(const De
       if (tid == 0) p.out_synd[f] = latched ? 0.0f : (float)total;
     }
     if (SOFT) {
+      double sd = (double)soft_out;  // per-thread partial sums are short; everything across threads is fp64
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) soft_out += __shfl_xor_sync(0xffffffffu, soft_out, o);
-      if (lane == 0) atomicAdd(p.out_soft + f, soft_out);
+      for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+      if (lane == 0) atomicAdd(p.out_soft + f, sd);
     }
   }
 }
@@ -726,10 +736,10 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
   });
   const int n_words = p.t.m_pad * P::RS;
   while (true) {
-    if (tid == 0) *s_frame = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) *s_frame = next_frame(p);
     __syncthreads();
     const int f = *s_frame;
-    if (f >= p.B) break;
+    if (f < 0) break;
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     float ch[P::MAXV];
     static_for<P::MAXV>([&](auto ic) {

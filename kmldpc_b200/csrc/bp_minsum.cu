@@ -40,10 +40,10 @@ __global__ void __launch_bounds__(T, MINB) ms_regular_kernel(const DecParams p) 
     for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[(j * T + tid) * 3 + k];
 
   while (true) {
-    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s_frame = next_frame(p);
     __syncthreads();
     const int f = s_frame;
-    if (f >= p.B) break;
+    if (f < 0) break;
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     float ch[VPT];
 #pragma unroll
@@ -105,10 +105,10 @@ __global__ void __launch_bounds__(512) ms_generic_kernel(const DecParams p) {
   uint32_t *dec = reinterpret_cast<uint32_t *>(chan + n);
   const int n_round = (n + 31) & ~31;
   while (true) {
-    if (tid == 0) s_frame = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s_frame = next_frame(p);
     __syncthreads();
     const int f = s_frame;
-    if (f >= p.B) break;
+    if (f < 0) break;
     const float *in = p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx;
     for (int v = tid; v < n; v += T) chan[v] = v < p.t.punct ? 0.0f : load_channel_llr(in, v - p.t.punct, p.in_is_lr);
     for (int i = tid; i < dcm * plane; i += T) msg[i] = 0u;
@@ -175,7 +175,7 @@ __device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__
 template <int VPT, int CPT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p) {
   extern __shared__ uint32_t msg[];
-  __shared__ int s_pair;
+  __shared__ int s_pair[2];
   const int tid = threadIdx.x;
   constexpr int plane = CPT * T + 1;
   uint32_t va[VPT][3];
@@ -184,14 +184,17 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
 #pragma unroll
     for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[(j * T + tid) * 3 + k];
   const __half2 alpha2 = __float2half2_rn(p.alpha), clip2 = __float2half2_rn(kLlrClip), zero2 = __float2half2_rn(0.0f);
-  const int n_pairs = (p.B + 1) >> 1;
 
   while (true) {
-    if (tid == 0) s_pair = (int)atomicAdd(p.work_counter, 1u);
+    if (tid == 0) {  // a work item = two consecutive entries of the frame queue (the last one may be single: fb = fa)
+      const int nB = frame_count(p), fp = (int)atomicAdd(p.work_counter, 1u);
+      const int ia = 2 * fp, ib = min(2 * fp + 1, nB - 1);
+      s_pair[0] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ia) : ia) : -1;
+      s_pair[1] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ib) : ib) : -1;
+    }
     __syncthreads();
-    const int fp = s_pair;
-    if (fp >= n_pairs) break;
-    const int fa = 2 * fp, fb = min(2 * fp + 1, p.B - 1);
+    const int fa = s_pair[0], fb = s_pair[1];
+    if (fa < 0) break;
     const float *ina = p.in + (size_t)(p.sel ? fa * p.n_cand + __ldg(p.sel + fa) : fa) * p.t.n_tx;
     const float *inb = p.in + (size_t)(p.sel ? fb * p.n_cand + __ldg(p.sel + fb) : fb) * p.t.n_tx;
     __half2 ch[VPT];

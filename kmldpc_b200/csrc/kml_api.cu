@@ -36,9 +36,19 @@ struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf<uint32_t> u_packed, c_packed, uu_hat_packed, cc_hat_packed;
   DevBuf<float2> h, y, hhat, noise;
-  DevBuf<float> lr, metric, soft, llr_io;
-  DevBuf<int32_t> kstar, ret, passes, bits_io;
+  DevBuf<double2> y64, hhat64, h64;  // staging of the reference-typed entry points (complex<double>), allocated on demand
+  DevBuf<double> p0_io;
+  DevBuf<float> lr, metric, llr_io;
+  DevBuf<double> soft, fsoft, chain_state;   // soft-syndrome metric: own sums of the metric / final decodes, chain values
+  DevBuf<int32_t> kstar, ret, mret, passes, bits_io, chain_flags, chain_queue, chain_counts;
   DevBuf<unsigned int> work_counter;
+  DevBuf<unsigned long long> counters;  // 5 x u64: what THIS lane's batches of the current kml_simulate call counted
+  // The work space above belongs to ONE stream at a time.  Every entry point calls lane_acquire() before it enqueues
+  // work that touches it and lane_release() after: a call on another stream first waits (on the device) for the event
+  // the previous user recorded, so calls on different streams of one context serialise instead of racing.
+  cudaEvent_t owner_ev = nullptr;
+  cudaStream_t owner = nullptr;
+  bool owned = false;
 };
 
 }  // namespace
@@ -54,8 +64,8 @@ struct kml_ctx {
   // device tables
   DevBuf<uint32_t> enc_t;
   DevBuf<float2> points;
-  DevBuf<int32_t> row_ptr, col_idx, km_nb;
-  int km_n_nb = 0;
+  DevBuf<int32_t> row_ptr, col_idx;
+  KmConst km{};  // fp64 constants of the k-means kernel (n_nb = 0: general kernel)
   DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
   DevBuf<uint32_t> vn_items, cn_items;
   int ell_width = 0;
@@ -66,6 +76,8 @@ struct kml_ctx {
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
+  DevBuf<double> soft_carry;  // [1] sum of ln(syndrom_soft_) as the last Decoder call of this context left it
+  int32_t *h_chain_counts = nullptr;  // pinned [2]
   uint64_t launches = 0;
   int layout_residual = 0, layout_excess = 0, layout_excess_planar = 0;  // layout_opt.cpp: annealing cost left / wavefronts above the ideal
   std::string err;
@@ -86,6 +98,19 @@ namespace {
     KML_CUDA(ctx, expr);        \
     (ctx)->launches++;          \
   } while (0)
+#define KML_RC(expr)                  \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != KML_OK) return rc__;  \
+  } while (0)
+
+template <class T>
+int ensure(kml_ctx *c, DevBuf<T> &b, size_t count) {
+  if (b.n >= count && b.p) return KML_OK;
+  b.release();
+  KML_CUDA(c, b.alloc(count));
+  return KML_OK;
+}
 
 int fail_arg(kml_ctx *ctx, const char *msg) {
   if (ctx) ctx->err = msg;
@@ -109,6 +134,7 @@ GenParams gen_params(const kml_ctx *c, int B, double snr_db, uint64_t seed, uint
 int alloc_lane(kml_ctx *c, Lane &l) {
   const size_t B = (size_t)c->max_batch;
   KML_CUDA(c, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+  KML_CUDA(c, cudaEventCreateWithFlags(&l.owner_ev, cudaEventDisableTiming));
   KML_CUDA(c, l.u_packed.alloc(B * c->k_words));
   KML_CUDA(c, l.c_packed.alloc(B * c->tx_words));
   KML_CUDA(c, l.uu_hat_packed.alloc(B * c->k_words));
@@ -118,21 +144,47 @@ int alloc_lane(kml_ctx *c, Lane &l) {
   KML_CUDA(c, l.hhat.alloc(B));
   KML_CUDA(c, l.lr.alloc(4 * B * c->n_tx));
   KML_CUDA(c, l.metric.alloc(4 * B));
-  KML_CUDA(c, l.soft.alloc(4 * B));
   KML_CUDA(c, l.kstar.alloc(B));
-  KML_CUDA(c, l.ret.alloc(4 * B));
+  KML_CUDA(c, l.ret.alloc(B));
+  KML_CUDA(c, l.mret.alloc(4 * B));
+  if (c->opts.metric_type) {
+    KML_CUDA(c, l.soft.alloc(4 * B));
+    KML_CUDA(c, l.fsoft.alloc(B));
+    KML_CUDA(c, l.chain_state.alloc(B));
+    KML_CUDA(c, l.chain_flags.alloc(B));
+    KML_CUDA(c, l.chain_queue.alloc(B));
+    KML_CUDA(c, l.chain_counts.alloc(2));
+  }
   KML_CUDA(c, l.passes.alloc(B));
   KML_CUDA(c, l.work_counter.alloc(1));
+  KML_CUDA(c, l.counters.alloc(5));
   return KML_OK;
 }
 
 void free_lane(Lane &l) {
   l.u_packed.release(); l.c_packed.release(); l.uu_hat_packed.release(); l.cc_hat_packed.release();
   l.h.release(); l.y.release(); l.hhat.release(); l.noise.release(); l.lr.release(); l.metric.release();
-  l.soft.release(); l.llr_io.release(); l.kstar.release(); l.ret.release(); l.passes.release(); l.bits_io.release();
-  l.work_counter.release();
+  l.soft.release(); l.fsoft.release(); l.chain_state.release(); l.chain_flags.release(); l.chain_queue.release();
+  l.chain_counts.release(); l.mret.release();
+  l.llr_io.release(); l.kstar.release(); l.ret.release(); l.passes.release(); l.bits_io.release();
+  l.work_counter.release(); l.counters.release();
+  l.y64.release(); l.hhat64.release(); l.h64.release(); l.p0_io.release();
+  if (l.owner_ev) cudaEventDestroy(l.owner_ev);
+  l.owner_ev = nullptr;
   if (l.stream) cudaStreamDestroy(l.stream);
   l.stream = nullptr;
+}
+
+// see Lane: serialises users of a lane's work space across streams (device-side wait, no host block)
+int lane_acquire(kml_ctx *c, Lane &l, cudaStream_t s) {
+  if (l.owned && l.owner != s) KML_CUDA(c, cudaStreamWaitEvent(s, l.owner_ev, 0));
+  return KML_OK;
+}
+int lane_release(kml_ctx *c, Lane &l, cudaStream_t s) {
+  KML_CUDA(c, cudaEventRecord(l.owner_ev, s));
+  l.owner = s;
+  l.owned = true;
+  return KML_OK;
 }
 
 // Builds the shared-memory layout of the decoder: edge (row r, position k) at word k * plane + slot(r); slot() and the
@@ -323,7 +375,7 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
 }
 
 DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t *sel, int n_cand, int in_is_lr, int iters,
-                     uint32_t *out_bits, int32_t *out_ret, float *out_soft) {
+                     uint32_t *out_bits, int32_t *out_ret, double *out_soft) {
   DecParams p{};
   p.t = c->dl.rowmajor ? c->dt_rm : c->dt;
   p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
@@ -333,24 +385,75 @@ DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t 
   return p;
 }
 
-// k-means → 4 candidates → metric → argmin → demap → decode (simulator.cc:131-148 + kmcodec.cc:54-72), all on l.stream.
-// y and (for known_h) true_h are device pointers; decisions land in l.cc_hat_packed / l.ret / l.uu_hat_packed.
-int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *true_h, double var) {
-  cudaStream_t s = l.stream;
+// Metric() for the decode-based metrics (kmcodec.cc:140-163): Decoder(metric_iter) on the four candidates of every frame.
+// Hard metric of the 5G codec: l.metric / l.kstar are final on return.  Soft metric: the decodes' own ln-sums land in
+// l.soft and their return values in l.mret; the caller runs the syndrom_soft_ chain (soft_chain) next.
+int metric_decodes(kml_ctx *c, Lane &l, cudaStream_t s, int B) {
+  const bool soft = c->opts.metric_type != 0;
+  if (soft) KML_CUDA(c, cudaMemsetAsync(l.soft.p, 0, sizeof(double) * 4 * (size_t)B, s));
+  DecParams p = dec_params(c, l, 4 * B, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.mret.p, soft ? l.soft.p : nullptr);
+  p.early_exit = 1;
+  if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
+  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+  if (soft) return KML_OK;
+  if (!p.out_synd)
+    KML_LAUNCH(c, launch_syndrome_weight(4 * B, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
+  KML_LAUNCH(c, launch_argmin4(B, l.metric.p, l.kstar.p, s));
+  return KML_OK;
+}
+
+// The soft metric's candidate choice with the reference's stale syndrom_soft_ semantics (see soft_chain_kernel), and —
+// when final_decode — the final decodes themselves (their ln-sums feed the chain): l.metric, l.kstar, and with
+// final_decode l.cc_hat_packed[B][words_n] / l.ret.  Blocks the host once per round (this mode is sequential by nature).
+int soft_chain(kml_ctx *c, Lane &l, cudaStream_t s, int B, bool final_decode) {
+  if (B < 1) return KML_OK;
+  KML_CUDA(c, cudaMemsetAsync(l.kstar.p, 0xFF, sizeof(int32_t) * (size_t)B, s));
+  KML_CUDA(c, cudaMemsetAsync(l.chain_flags.p, 0, sizeof(int32_t) * (size_t)B, s));
+  KML_CUDA(c, cudaMemsetAsync(l.fsoft.p, 0, sizeof(double) * (size_t)B, s));
+  KML_CUDA(c, cudaMemsetAsync(l.ret.p, 0, sizeof(int32_t) * (size_t)B, s));
+  SoftChainParams q{};
+  q.B = B; q.final_decode = final_decode ? 1 : 0;
+  q.own = l.soft.p; q.mret = l.mret.p; q.fown = l.fsoft.p; q.fret = l.ret.p; q.carry = c->soft_carry.p;
+  q.metric = l.metric.p; q.kstar = l.kstar.p; q.state = l.chain_state.p; q.flags = l.chain_flags.p;
+  q.queue = l.chain_queue.p; q.counts = l.chain_counts.p;
+  for (int round = 0; round <= B + 1; round++) {
+    KML_LAUNCH(c, launch_soft_chain(q, round, s));
+    KML_CUDA(c, cudaMemcpyAsync(c->h_chain_counts, l.chain_counts.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    KML_CUDA(c, cudaStreamSynchronize(s));
+    const int queued = c->h_chain_counts[0], left = c->h_chain_counts[1];
+    if (queued > 0) {  // the frames chosen in this round: final Decoder(max_iter) on the chosen candidate (kmcodec.cc:70-71)
+      DecParams p = dec_params(c, l, queued, l.lr.p, l.kstar.p, 4, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, l.fsoft.p);
+      p.frame_idx = l.chain_queue.p;
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+    }
+    if (left == 0) return KML_OK;
+    if (queued == 0) break;  // no progress: cannot happen (frame 0 never waits)
+  }
+  c->err = "soft-syndrome chain did not resolve";
+  return KML_ERR_STATE;
+}
+
+// k-means → 4 candidates → metric → argmin → demap → decode (simulator.cc:131-148 + kmcodec.cc:54-72), all on stream s.
+// y (float2, or double2 when y_is_f64 — then l.y receives the fp32 copy) and, for known_h, true_h are device pointers;
+// decisions land in l.cc_hat_packed / l.ret / l.uu_hat_packed, the estimate in l.hhat (and l.hhat64 when want_h64).
+int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, int y_is_f64, const float2 *true_h,
+                    double var, bool want_h64 = false) {
+  const float2 *y32 = y_is_f64 ? l.y.p : reinterpret_cast<const float2 *>(y);
   DemapParams d{};
   d.B = B; d.n_sym = c->n_sym; d.n_tx = c->n_tx; d.bits_per_symbol = c->bits; d.q = c->Q;
-  d.m_rows = c->M; d.punct = c->punct; d.y = y; d.inv_var = (float)(1.0 / var);
+  d.m_rows = c->M; d.punct = c->punct; d.y = y32; d.inv_var = (float)(1.0 / var);
   for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
   d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p; d.col_ell = c->col_ell.p; d.ell_width = c->ell_width;
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   const int32_t *sel = nullptr;
   int n_cand = 1;
   if (c->opts.known_h) {
+    if (y_is_f64) KML_LAUNCH(c, launch_f64_to_f32((size_t)B * c->n_sym * 2, reinterpret_cast<const double *>(y), reinterpret_cast<float *>(l.y.p), s));
     d.h = true_h; d.n_cand = 1; d.hard_metric = 0;
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
   } else {
-    KML_LAUNCH(c, launch_kmeans(B, y, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, l.hhat.p, l.passes.p,
-                               c->num_sms, s));
+    KML_LAUNCH(c, launch_kmeans(B, y, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
+                               want_h64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
     // hard metric: the four ratio vectors stay in shared memory and only the winner's reaches HBM — as long as that
@@ -363,21 +466,11 @@ int receive_on_lane(kml_ctx *c, Lane &l, int B, const float2 *y, const float2 *t
       KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
       return KML_OK;
     }
-    if (decode_metric) {  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
-      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
-      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * B, s));
-      DecParams p = dec_params(c, l, 4 * B, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
-      p.early_exit = 1;
-      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
-      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
-      if (soft) {
-        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * B, cudaMemcpyDeviceToDevice, s));
-        KML_LAUNCH(c, launch_abs_inplace(4 * B, l.metric.p, s));
-      } else if (!p.out_synd) {
-        KML_LAUNCH(c, launch_syndrome_weight(4 * B, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p,
-                                            l.metric.p, s));
-      }
-      KML_LAUNCH(c, launch_argmin4(B, l.metric.p, l.kstar.p, s));
+    KML_RC(metric_decodes(c, l, s, B));  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
+    if (c->opts.metric_type) {          // soft metric: choice and final decodes are interleaved (stale syndrom_soft_ chain)
+      KML_RC(soft_chain(c, l, s, B, true));
+      KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
+      return KML_OK;
     }
     sel = l.kstar.p;
     n_cand = 4;
@@ -463,10 +556,18 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     for (int i = 0; i < c->Q; i++) pts[i] = make_float2((float)modem->points[2 * i], (float)modem->points[2 * i + 1]);
     KML_CUDA(c, c->points.alloc(c->Q));
     KML_CUDA(c, cudaMemcpy(c->points.p, pts.data(), sizeof(float2) * c->Q, cudaMemcpyHostToDevice));
-    const std::vector<int> nb = voronoi_neighbours_of_first(modem->points, c->Q);
-    c->km_n_nb = (int)nb.size();
-    KML_CUDA(c, c->km_nb.alloc(nb.size()));
-    if (!nb.empty()) KML_CUDA(c, cudaMemcpy(c->km_nb.p, nb.data(), sizeof(int) * nb.size(), cudaMemcpyHostToDevice));
+    {  // k-means: only "nearest centroid is cluster 0" matters, decided by the Voronoi neighbours of s_0 (host_code.cpp)
+      const std::vector<int> nb = voronoi_neighbours_of_first(modem->points, c->Q);
+      const double s0r = modem->points[0], s0i = modem->points[1], s0n = s0r * s0r + s0i * s0i;
+      c->km.s0r = s0r; c->km.s0i = s0i;
+      c->km.is0r = s0r / s0n; c->km.is0i = -s0i / s0n;  // 1 / s_0 = conj(s_0) / |s_0|^2
+      c->km.n_nb = nb.size() <= 8 ? (int)nb.size() : 0;
+      for (int t = 0; t < c->km.n_nb; t++) {
+        const double sr = modem->points[2 * nb[t]], si = modem->points[2 * nb[t] + 1];
+        c->km.dsr[t] = sr - s0r; c->km.dsi[t] = si - s0i;
+        c->km.dn[t] = 0.5 * ((sr * sr + si * si) - s0n);
+      }
+    }
     KML_CUDA(c, c->row_ptr.alloc(c->M + 1));
     KML_CUDA(c, cudaMemcpy(c->row_ptr.p, code->row_ptr, sizeof(int32_t) * (c->M + 1), cudaMemcpyHostToDevice));
     KML_CUDA(c, c->col_idx.alloc(c->E));
@@ -484,6 +585,11 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     KML_CUDA(c, c->counters.alloc(5));
     KML_CUDA(c, cudaMemset(c->counters.p, 0, 5 * sizeof(unsigned long long)));
     KML_CUDA(c, cudaMallocHost(&c->h_counters, 5 * sizeof(unsigned long long)));
+    KML_CUDA(c, cudaMallocHost(&c->h_chain_counts, 2 * sizeof(int32_t)));
+    // syndrom_soft_ before the first Decoder call: the reference leaves the array uninitialised
+    // (binaryldpccodec.cc:88); here, and in oracle/ref/ref_harness.cc, it starts as all ones → ln-sum 0
+    KML_CUDA(c, c->soft_carry.alloc(1));
+    KML_CUDA(c, cudaMemset(c->soft_carry.p, 0, sizeof(double)));
     return KML_OK;
   };
   KML_TRY(upload());
@@ -501,9 +607,11 @@ extern "C" void kml_destroy(kml_ctx *c) {
   cudaDeviceSynchronize();
   free_lane(c->lane[0]);
   free_lane(c->lane[1]);
-  c->enc_t.release(); c->points.release(); c->km_nb.release(); c->row_ptr.release(); c->col_idx.release();
+  c->enc_t.release(); c->points.release(); c->row_ptr.release(); c->col_idx.release();
   c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_g.release(); c->vn_items.release(); c->cn_items.release(); c->cn_deg_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_chain_counts) cudaFreeHost(c->h_chain_counts);
+  c->soft_carry.release();
   delete c;
 }
 
@@ -555,25 +663,18 @@ extern "C" uint64_t kml_launch_count(const kml_ctx *c) { return c ? c->launches 
 // Host-pointer stages run batch by batch on lane 0; temporaries for the int32 <-> packed conversions are (re)allocated
 // on demand.  They exist for parity tests and standalone measurements, not for peak throughput.
 namespace {
-template <class T>
-int ensure(kml_ctx *c, DevBuf<T> &b, size_t count) {
-  if (b.n >= count && b.p) return KML_OK;
-  b.release();
-  KML_CUDA(c, b.alloc(count));
-  return KML_OK;
-}
-#define KML_RC(expr)                  \
-  do {                                \
-    int rc__ = (expr);                \
-    if (rc__ != KML_OK) return rc__;  \
-  } while (0)
+// begin / end of an entry point that uses lane `l` on stream `s`
+#define KML_ENTER(c, l, s)                      \
+  KML_CUDA(c, cudaSetDevice((c)->device));      \
+  KML_RC(lane_acquire(c, l, s))
+#define KML_LEAVE(c, l, s) KML_RC(lane_release(c, l, s))
 }  // namespace
 
 extern "C" int kml_encode(kml_ctx *c, int B, const int32_t *u, int32_t *cw) {
   KML_RC(check_batch(c, B));
   if (!u || !cw) return fail_arg(c, "kml_encode: null buffer");
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
+  KML_ENTER(c, l, l.stream);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     KML_RC(ensure(c, l.bits_io, (size_t)nb * std::max(c->K, c->n_tx)));
@@ -585,14 +686,15 @@ extern "C" int kml_encode(kml_ctx *c, int B, const int32_t *u, int32_t *cw) {
     KML_CUDA(c, cudaMemcpyAsync(cw + (size_t)b0 * c->n_tx, l.bits_io.p, sizeof(int32_t) * nb * c->n_tx, cudaMemcpyDeviceToHost, l.stream));
     KML_CUDA(c, cudaStreamSynchronize(l.stream));
   }
+  KML_LEAVE(c, l, l.stream);
   return KML_OK;
 }
 
 extern "C" int kml_generate(kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0, int32_t *u, int32_t *cw,
                             float *h, float *y) {
   KML_RC(check_batch(c, B));
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
+  KML_ENTER(c, l, l.stream);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     GenParams g = gen_params(c, nb, snr_db, seed, frame0 + b0);
@@ -613,14 +715,15 @@ extern "C" int kml_generate(kml_ctx *c, int B, double snr_db, uint64_t seed, uin
     if (y) KML_CUDA(c, cudaMemcpyAsync(y + (size_t)b0 * c->n_sym * 2, l.y.p, sizeof(float2) * nb * c->n_sym, cudaMemcpyDeviceToHost, l.stream));
     KML_CUDA(c, cudaStreamSynchronize(l.stream));
   }
+  KML_LEAVE(c, l, l.stream);
   return KML_OK;
 }
 
 extern "C" int kml_modulate(kml_ctx *c, int B, const int32_t *cw, const float *h, const float *noise, double sigma, float *y) {
   KML_RC(check_batch(c, B));
   if (!cw || !h || !y) return fail_arg(c, "kml_modulate: null buffer");
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
+  KML_ENTER(c, l, l.stream);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     KML_RC(ensure(c, l.bits_io, (size_t)nb * std::max(c->K, c->n_tx)));
@@ -636,23 +739,47 @@ extern "C" int kml_modulate(kml_ctx *c, int B, const int32_t *cw, const float *h
     KML_CUDA(c, cudaMemcpyAsync(y + (size_t)b0 * c->n_sym * 2, l.y.p, sizeof(float2) * nb * c->n_sym, cudaMemcpyDeviceToHost, l.stream));
     KML_CUDA(c, cudaStreamSynchronize(l.stream));
   }
+  KML_LEAVE(c, l, l.stream);
   return KML_OK;
 }
+
+namespace {
+// y: float [B][n_sym][2] or, with y_is_f64, double (the reference's std::complex<double> received symbols)
+int kmeans_host(kml_ctx *c, int B, const void *y, int y_is_f64, float *hhat, double *hhat64, int32_t *passes) {
+  Lane &l = c->lane[0];
+  KML_ENTER(c, l, l.stream);
+  const size_t ysz = y_is_f64 ? sizeof(double2) : sizeof(float2);
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    void *ydev = l.y.p;
+    if (y_is_f64) {
+      KML_RC(ensure(c, l.y64, (size_t)c->max_batch * c->n_sym));
+      ydev = l.y64.p;
+    }
+    if (hhat64) KML_RC(ensure(c, l.hhat64, (size_t)c->max_batch));
+    KML_CUDA(c, cudaMemcpyAsync(ydev, (const char *)y + (size_t)b0 * c->n_sym * ysz, ysz * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
+    KML_LAUNCH(c, launch_kmeans(nb, ydev, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
+                               hhat64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, l.stream));
+    if (hhat) KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
+    if (hhat64) KML_CUDA(c, cudaMemcpyAsync(hhat64 + (size_t)b0 * 2, l.hhat64.p, sizeof(double2) * nb, cudaMemcpyDeviceToHost, l.stream));
+    if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+  }
+  KML_LEAVE(c, l, l.stream);
+  return KML_OK;
+}
+}  // namespace
 
 extern "C" int kml_kmeans(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat) return fail_arg(c, "kml_kmeans: null buffer");
-  KML_CUDA(c, cudaSetDevice(c->device));
-  Lane &l = c->lane[0];
-  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
-    const int nb = std::min(c->max_batch, B - b0);
-    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
-    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, l.hhat.p, l.passes.p, c->num_sms, l.stream));
-    KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
-    if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
-    KML_CUDA(c, cudaStreamSynchronize(l.stream));
-  }
-  return KML_OK;
+  return kmeans_host(c, B, y, 0, hhat, nullptr, passes);
+}
+
+extern "C" int kml_kmeans_f64(kml_ctx *c, int B, const double *y, double *hhat, int32_t *passes) {
+  KML_RC(check_batch(c, B));
+  if (!y || !hhat) return fail_arg(c, "kml_kmeans_f64: null buffer");
+  return kmeans_host(c, B, y, 1, nullptr, hhat, passes);
 }
 
 namespace {
@@ -666,13 +793,25 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   return d;
 }
+
+// GetMetrics on the four candidates of nb frames whose y / hhat sit in l.y / l.hhat (kmcodec.cc:122-139): l.metric, l.kstar
+int resolve_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int nb, double var) {
+  const bool decode_metric = c->is_5g || c->opts.metric_type;
+  DemapParams d = demap_params(c, l, nb, var, 4, decode_metric ? 0 : 1);
+  KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
+  if (decode_metric) {
+    KML_RC(metric_decodes(c, l, s, nb));
+    if (c->opts.metric_type) KML_RC(soft_chain(c, l, s, nb, false));
+  }
+  return KML_OK;
+}
 }  // namespace
 
 extern "C" int kml_demap(kml_ctx *c, int B, const float *y, const float *h, double var, float *llr) {
   KML_RC(check_batch(c, B));
   if (!y || !h || !llr || !(var > 0)) return fail_arg(c, "kml_demap: bad argument");
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
+  KML_ENTER(c, l, l.stream);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
@@ -683,54 +822,46 @@ extern "C" int kml_demap(kml_ctx *c, int B, const float *y, const float *h, doub
     KML_CUDA(c, cudaMemcpyAsync(llr + (size_t)b0 * c->n_tx, l.lr.p, sizeof(float) * nb * c->n_tx, cudaMemcpyDeviceToHost, l.stream));
     KML_CUDA(c, cudaStreamSynchronize(l.stream));
   }
+  KML_LEAVE(c, l, l.stream);
   return KML_OK;
 }
 
 extern "C" int kml_resolve(kml_ctx *c, int B, const float *y, const float *hhat, double var, float *metric, int32_t *kstar) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat || !(var > 0)) return fail_arg(c, "kml_resolve: bad argument");
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
   cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
     KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
     KML_CUDA(c, cudaMemcpyAsync(l.hhat.p, hhat + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, s));
-    const bool decode_metric = c->is_5g || c->opts.metric_type;
-    DemapParams d = demap_params(c, l, nb, var, 4, decode_metric ? 0 : 1);
-    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
-    if (decode_metric) {
-      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
-      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
-      DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
-      p.early_exit = 1;
-      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
-      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
-      if (soft) {
-        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
-        KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
-      } else if (!p.out_synd) {
-        KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
-      }
-      KML_LAUNCH(c, launch_argmin4(nb, l.metric.p, l.kstar.p, s));
-    }
+    KML_RC(resolve_on_lane(c, l, s, nb, var));
     if (metric) KML_CUDA(c, cudaMemcpyAsync(metric + (size_t)b0 * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
     if (kstar) KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     KML_CUDA(c, cudaStreamSynchronize(s));
   }
+  KML_LEAVE(c, l, s);
   return KML_OK;
 }
 
-extern "C" int kml_decode(kml_ctx *c, int B, const float *llr, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret) {
-  KML_RC(check_batch(c, B));
-  if (!llr || iter_count < 1) return fail_arg(c, "kml_decode: bad argument");
-  KML_CUDA(c, cudaSetDevice(c->device));
+namespace {
+// in: float natural-log LLR [B][n_tx] (p0_is_f64 = 0) or the reference's own decoder input, double P(bit = 0) [B][n_tx]
+int decode_host(kml_ctx *c, int B, const void *in, int p0_is_f64, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret) {
   Lane &l = c->lane[0];
   cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
-    KML_CUDA(c, cudaMemcpyAsync(l.lr.p, llr + (size_t)b0 * c->n_tx, sizeof(float) * nb * c->n_tx, cudaMemcpyHostToDevice, s));
-    DecParams p = dec_params(c, l, nb, l.lr.p, nullptr, 1, 0, iter_count, l.cc_hat_packed.p, l.ret.p, nullptr);
+    const size_t n = (size_t)nb * c->n_tx;
+    if (p0_is_f64) {  // ratio P0 / (1 - P0) formed in fp64 on the device, then narrowed: the decoder's own input format
+      KML_RC(ensure(c, l.p0_io, (size_t)c->max_batch * c->n_tx));
+      KML_CUDA(c, cudaMemcpyAsync(l.p0_io.p, (const double *)in + (size_t)b0 * c->n_tx, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+      KML_LAUNCH(c, launch_p0_to_lr(n, l.p0_io.p, l.lr.p, s));
+    } else {
+      KML_CUDA(c, cudaMemcpyAsync(l.lr.p, (const float *)in + (size_t)b0 * c->n_tx, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+    }
+    DecParams p = dec_params(c, l, nb, l.lr.p, nullptr, 1, p0_is_f64 ? 1 : 0, iter_count, l.cc_hat_packed.p, l.ret.p, nullptr);
     KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
     KML_RC(ensure(c, l.bits_io, (size_t)nb * c->N));
     if (cc_hat) {
@@ -745,52 +876,113 @@ extern "C" int kml_decode(kml_ctx *c, int B, const float *llr, int iter_count, i
     if (ret) KML_CUDA(c, cudaMemcpyAsync(ret + b0, l.ret.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     KML_CUDA(c, cudaStreamSynchronize(s));
   }
+  KML_LEAVE(c, l, s);
   return KML_OK;
 }
+}  // namespace
 
+extern "C" int kml_decode(kml_ctx *c, int B, const float *llr, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!llr || iter_count < 1) return fail_arg(c, "kml_decode: bad argument");
+  return decode_host(c, B, llr, 0, iter_count, cc_hat, uu_hat, ret);
+}
+
+extern "C" int kml_decode_p0(kml_ctx *c, int B, const double *p0, int iter_count, int32_t *cc_hat, int32_t *uu_hat, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!p0 || iter_count < 1) return fail_arg(c, "kml_decode_p0: bad argument");
+  return decode_host(c, B, p0, 1, iter_count, cc_hat, uu_hat, ret);
+}
+
+namespace {
 // Host-buffer receiver: batches alternate between the two lanes so the H2D copy of batch i+1 and the D2H copy of batch
 // i-1 overlap the kernels of batch i (true overlap needs pinned host buffers; pageable ones still work).
-extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
-                           float *hhat, int32_t *kstar, int32_t *ret) {
-  KML_RC(check_batch(c, B));
-  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive: bad argument");
+int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *true_h, double var, uint32_t *uu_hat_packed,
+                 float *hhat, double *hhat64, int32_t *kstar, int32_t *ret) {
   KML_CUDA(c, cudaSetDevice(c->device));
   // sub-batches of ~2048 frames (measured best on B200: the first H2D and the last D2H are the only exposed copies,
   // and the other lane's kernels fill the tail of each decoder launch); never fewer than ~1 frame per resident CTA
   int step = c->max_batch;
   if (B > 2 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, std::min(2048, (B + 1) / 2)));
-  if (const char *e = getenv("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));  // tuning knob
-  int li = 0, chunk_no = 0, slow = 2;
-  if (const char *e = getenv("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));  // tuning knob
-  for (int b0 = 0, nb = 0; b0 < B; b0 += nb, li ^= 1, chunk_no++) {
+  int slow = 2;
+#ifdef KML_TUNING
+  if (const char *e = getenv("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));
+  if (const char *e = getenv("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));
+#endif
+  // the soft metric's syndrom_soft_ chain runs through the frames in order: one lane, one batch at a time
+  const bool sequential = c->opts.metric_type && !c->opts.known_h;
+  const size_t ysz = y_is_f64 ? sizeof(double2) : sizeof(float2), hsz = y_is_f64 ? sizeof(double2) : sizeof(float2);
+  int li = 0, chunk_no = 0;
+  for (int b0 = 0, nb = 0; b0 < B; b0 += nb, li ^= sequential ? 0 : 1, chunk_no++) {
     Lane &l = c->lane[li];
     cudaStream_t s = l.stream;
+    KML_RC(lane_acquire(c, l, s));
     // slow start: the first copy is the only one nothing can hide, so the first two sub-batches are a quarter / a half
     const int want = (B > 4 * step && chunk_no < slow) ? std::max(c->num_sms, step >> (slow - chunk_no)) : step;
     nb = std::min(want, B - b0);
-    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
-    if (c->opts.known_h)
-      KML_CUDA(c, cudaMemcpyAsync(l.h.p, true_h + (size_t)b0 * 2, sizeof(float2) * nb, cudaMemcpyHostToDevice, s));
-    KML_RC(receive_on_lane(c, l, nb, l.y.p, l.h.p, var));
+    void *ydev = l.y.p;
+    if (y_is_f64) {
+      KML_RC(ensure(c, l.y64, (size_t)c->max_batch * c->n_sym));
+      ydev = l.y64.p;
+      if (hhat64) KML_RC(ensure(c, l.hhat64, (size_t)c->max_batch));
+    }
+    KML_CUDA(c, cudaMemcpyAsync(ydev, (const char *)y + (size_t)b0 * c->n_sym * ysz, ysz * nb * c->n_sym, cudaMemcpyHostToDevice, s));
+    if (c->opts.known_h) {
+      if (y_is_f64) {
+        KML_RC(ensure(c, l.h64, (size_t)c->max_batch));
+        KML_CUDA(c, cudaMemcpyAsync(l.h64.p, (const char *)true_h + (size_t)b0 * hsz, hsz * nb, cudaMemcpyHostToDevice, s));
+        KML_LAUNCH(c, launch_f64_to_f32((size_t)nb * 2, reinterpret_cast<const double *>(l.h64.p), reinterpret_cast<float *>(l.h.p), s));
+      } else {
+        KML_CUDA(c, cudaMemcpyAsync(l.h.p, (const char *)true_h + (size_t)b0 * hsz, hsz * nb, cudaMemcpyHostToDevice, s));
+      }
+    }
+    KML_RC(receive_on_lane(c, l, s, nb, ydev, y_is_f64, l.h.p, var, hhat64 != nullptr));
     if (uu_hat_packed)
       KML_CUDA(c, cudaMemcpyAsync(uu_hat_packed + (size_t)b0 * c->k_words, l.uu_hat_packed.p, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyDeviceToHost, s));
     if (hhat && !c->opts.known_h)
       KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, s));
+    if (hhat64 && !c->opts.known_h)
+      KML_CUDA(c, cudaMemcpyAsync(hhat64 + (size_t)b0 * 2, l.hhat64.p, sizeof(double2) * nb, cudaMemcpyDeviceToHost, s));
     if (kstar && !c->opts.known_h)
       KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     if (ret) KML_CUDA(c, cudaMemcpyAsync(ret + b0, l.ret.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    KML_RC(lane_release(c, l, s));
+    if (sequential) KML_CUDA(c, cudaStreamSynchronize(s));
   }
   KML_CUDA(c, cudaStreamSynchronize(c->lane[0].stream));
   KML_CUDA(c, cudaStreamSynchronize(c->lane[1].stream));
+  return KML_OK;
+}
+}  // namespace
+
+extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                           float *hhat, int32_t *kstar, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive: bad argument");
+  return receive_host(c, B, y, 0, true_h, var, uu_hat_packed, hhat, nullptr, kstar, ret);
+}
+
+extern "C" int kml_receive_f64(kml_ctx *c, int B, const double *y, const double *true_h, double var, uint32_t *uu_hat_packed,
+                               double *hhat, int32_t *kstar, int32_t *ret) {
+  KML_RC(check_batch(c, B));
+  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive_f64: bad argument");
+  return receive_host(c, B, y, 1, true_h, var, uu_hat_packed, nullptr, hhat, kstar, ret);
+}
+
+extern "C" int kml_soft_syndrome_state(kml_ctx *c, int set, double *value) {
+  if (!c || !value) return KML_ERR_ARG;
+  KML_CUDA(c, cudaSetDevice(c->device));
+  KML_CUDA(c, cudaDeviceSynchronize());
+  if (set) KML_CUDA(c, cudaMemcpy(c->soft_carry.p, value, sizeof(double), cudaMemcpyHostToDevice));
+  else KML_CUDA(c, cudaMemcpy(value, c->soft_carry.p, sizeof(double), cudaMemcpyDeviceToHost));
   return KML_OK;
 }
 
 extern "C" int kml_count_errors(kml_ctx *c, int B, const uint32_t *u_packed, const uint32_t *uu_hat_packed, uint64_t counters[4]) {
   KML_RC(check_batch(c, B));
   if (!u_packed || !uu_hat_packed || !counters) return fail_arg(c, "kml_count_errors: null buffer");
-  KML_CUDA(c, cudaSetDevice(c->device));
   Lane &l = c->lane[0];
   cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
   KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), s));
   for (int b0 = 0; b0 < B; b0 += c->max_batch) {
     const int nb = std::min(c->max_batch, B - b0);
@@ -800,161 +992,204 @@ extern "C" int kml_count_errors(kml_ctx *c, int B, const uint32_t *u_packed, con
   }
   KML_CUDA(c, cudaMemcpyAsync(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
   KML_CUDA(c, cudaStreamSynchronize(s));
+  KML_LEAVE(c, l, s);
   for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
   return KML_OK;
 }
 
 // ================================================================================================ fused path
+// Each lane accumulates into its OWN device counters, read back only when that lane is idle: the stop rule then depends
+// on completed batches alone (same seed → same stopping point), and nothing reads a counter another stream is adding to.
 extern "C" int kml_simulate(kml_ctx *c, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
                             uint64_t max_err_blk, uint64_t counters[4], uint64_t *iters_sum) {
   if (!c || !counters) return KML_ERR_ARG;
   KML_CUDA(c, cudaSetDevice(c->device));
   const double var = std::pow(10.0, -0.1 * snr_db);
-  KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), c->lane[0].stream));
-  KML_CUDA(c, cudaStreamSynchronize(c->lane[0].stream));
+  const bool sequential = c->opts.metric_type && !c->opts.known_h;  // see receive_host
+  for (int li = 0; li < 2; li++) {
+    Lane &l = c->lane[li];
+    KML_RC(lane_acquire(c, l, l.stream));
+    KML_CUDA(c, cudaMemsetAsync(l.counters.p, 0, 5 * sizeof(unsigned long long), l.stream));
+  }
+  unsigned long long seen[2][5] = {{0}, {0}};  // each lane's counters as of its last completed batch
   uint64_t done = 0;
   int li = 0;
-  cudaEvent_t ev[2];
-  KML_CUDA(c, cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-  KML_CUDA(c, cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
   bool pending[2] = {false, false};
-  int rc = KML_OK;
+  auto read_lane = [&](int k) -> int {  // lane k is idle: its counters are final for everything it was given
+    Lane &l = c->lane[k];
+    KML_CUDA(c, cudaMemcpyAsync(c->h_counters, l.counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, l.stream));
+    KML_CUDA(c, cudaStreamSynchronize(l.stream));
+    for (int j = 0; j < 5; j++) seen[k][j] = c->h_counters[j];
+    return KML_OK;
+  };
   auto run = [&]() -> int {
     while (done < frame_count) {
       Lane &l = c->lane[li];
       if (pending[li]) {  // the lane's previous batch must be finished before its buffers are reused
-        KML_CUDA(c, cudaEventSynchronize(ev[li]));
+        KML_RC(read_lane(li));
         pending[li] = false;
-        if (max_err_blk) {  // stop rule with one-batch lag (simulator.cc:117 checks before every frame)
-          KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-          if (counters[1] + c->h_counters[1] >= max_err_blk) break;
-        }
+        // stop rule with one-batch lag (simulator.cc:117 checks before every frame)
+        if (max_err_blk && counters[1] + seen[0][1] + seen[1][1] >= max_err_blk) break;
       }
       const int nb = (int)std::min<uint64_t>((uint64_t)c->max_batch, frame_count - done);
       GenParams g = gen_params(c, nb, snr_db, seed, frame_begin + done);
       KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, l.stream));
       KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
       KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, l.stream));
-      KML_RC(receive_on_lane(c, l, nb, l.y.p, l.h.p, var));
+      KML_RC(receive_on_lane(c, l, l.stream, nb, l.y.p, 0, l.h.p, var));
       KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, l.ret.p, c->opts.max_iter,
-                                       c->counters.p, l.stream));
-      KML_CUDA(c, cudaEventRecord(ev[li], l.stream));
+                                       l.counters.p, l.stream));
       pending[li] = true;
       done += nb;
-      li ^= 1;
+      if (!sequential) li ^= 1;
     }
     return KML_OK;
   };
-  rc = run();
-  cudaStreamSynchronize(c->lane[0].stream);
-  cudaStreamSynchronize(c->lane[1].stream);
-  cudaEventDestroy(ev[0]);
-  cudaEventDestroy(ev[1]);
+  int rc = run();
+  for (int k = 0; k < 2 && rc == KML_OK; k++) rc = read_lane(k);
+  for (int k = 0; k < 2; k++) {
+    cudaStreamSynchronize(c->lane[k].stream);
+    lane_release(c, c->lane[k], c->lane[k].stream);
+  }
   if (rc != KML_OK) return rc;
-  KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
-  if (iters_sum) *iters_sum += c->h_counters[4];
+  for (int k = 0; k < 4; k++) counters[k] += seen[0][k] + seen[1][k];
+  if (iters_sum) *iters_sum += seen[0][4] + seen[1][4];
   return KML_OK;
 }
+
+namespace {
+// GetHistogramData + CntErr for nb frames whose symbols and information bits sit in l.y / l.u_packed
+// (kmcodec.cc:74-79, simulator.cc:154-167): l.metric[nb][4], c->counters += CntErr on a uu_hat no final decoder wrote.
+int histogram_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int nb, double var) {
+  const bool decode_metric = c->is_5g || c->opts.metric_type;
+  KML_LAUNCH(c, launch_kmeans(nb, l.y.p, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p, nullptr,
+                             l.passes.p, nullptr, c->num_sms, s));
+  KML_RC(resolve_on_lane(c, l, s, nb, var));
+  if (decode_metric) {
+    // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)
+    KML_LAUNCH(c, launch_extract_bits(nb, c->K, c->info_offset, 4 * c->words_n, l.cc_hat_packed.p + 3 * c->words_n,
+                                     l.uu_hat_packed.p, s));
+  } else {  // hard metric: nothing ever writes cdata.uu_hat_ (uninitialised in the reference, zeros here)
+    KML_CUDA(c, cudaMemsetAsync(l.uu_hat_packed.p, 0, sizeof(uint32_t) * (size_t)nb * c->k_words, s));
+  }
+  KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, nullptr, c->opts.max_iter,
+                                   c->counters.p, s));
+  return KML_OK;
+}
+}  // namespace
 
 extern "C" int kml_histogram(kml_ctx *c, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
                              float *metrics, uint64_t counters[4]) {
   if (!c || !metrics || !counters) return KML_ERR_ARG;
   if (c->opts.known_h) return fail_arg(c, "kml_histogram: needs the four blind candidates (true_h_arg = false)");
-  KML_CUDA(c, cudaSetDevice(c->device));
   const double var = std::pow(10.0, -0.1 * snr_db);
   Lane &l = c->lane[0];
   cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
   KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), s));
-  const bool decode_metric = c->is_5g || c->opts.metric_type;
   for (uint64_t done = 0; done < frame_count;) {
     const int nb = (int)std::min<uint64_t>((uint64_t)c->max_batch, frame_count - done);
     GenParams g = gen_params(c, nb, snr_db, seed, frame_begin + done);
     KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, s));
     KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, s));
     KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, s));
-    KML_LAUNCH(c, launch_kmeans(nb, l.y.p, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter,
-                               l.hhat.p, l.passes.p, c->num_sms, s));
-    DemapParams d = demap_params(c, l, nb, var, 4, decode_metric ? 0 : 1);
-    KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
-    if (decode_metric) {
-      float *soft = c->opts.metric_type ? l.soft.p : nullptr;
-      if (soft) KML_CUDA(c, cudaMemsetAsync(soft, 0, sizeof(float) * 4 * nb, s));
-      DecParams p = dec_params(c, l, 4 * nb, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.ret.p, soft);
-      p.early_exit = 1;
-      if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
-      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
-      if (soft) {
-        KML_CUDA(c, cudaMemcpyAsync(l.metric.p, soft, sizeof(float) * 4 * nb, cudaMemcpyDeviceToDevice, s));
-        KML_LAUNCH(c, launch_abs_inplace(4 * nb, l.metric.p, s));
-      } else if (!p.out_synd) {
-        KML_LAUNCH(c, launch_syndrome_weight(4 * nb, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
-      }
-      // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)
-      KML_LAUNCH(c, launch_extract_bits(nb, c->K, c->info_offset, 4 * c->words_n, l.cc_hat_packed.p + 3 * c->words_n,
-                                       l.uu_hat_packed.p, s));
-    } else {
-      KML_CUDA(c, cudaMemsetAsync(l.uu_hat_packed.p, 0, sizeof(uint32_t) * (size_t)nb * c->k_words, s));
-    }
-    KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, nullptr, c->opts.max_iter,
-                                     c->counters.p, s));
+    KML_RC(histogram_on_lane(c, l, s, nb, var));
     KML_CUDA(c, cudaMemcpyAsync(metrics + done * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
     KML_CUDA(c, cudaStreamSynchronize(s));
     done += nb;
   }
-  KML_CUDA(c, cudaMemcpy(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  KML_CUDA(c, cudaMemcpyAsync(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  KML_CUDA(c, cudaStreamSynchronize(s));
+  KML_LEAVE(c, l, s);
+  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
+  return KML_OK;
+}
+
+extern "C" int kml_histogram_rx(kml_ctx *c, int B, const float *y, double var, const uint32_t *u_packed, float *metrics,
+                                int32_t *kstar, uint32_t *uu_hat_packed, uint64_t counters[4]) {
+  KML_RC(check_batch(c, B));
+  if (!y || !u_packed || !metrics || !counters || !(var > 0)) return fail_arg(c, "kml_histogram_rx: bad argument");
+  if (c->opts.known_h) return fail_arg(c, "kml_histogram_rx: needs the four blind candidates (true_h_arg = false)");
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
+  KML_CUDA(c, cudaMemsetAsync(c->counters.p, 0, 5 * sizeof(unsigned long long), s));
+  for (int b0 = 0; b0 < B; b0 += c->max_batch) {
+    const int nb = std::min(c->max_batch, B - b0);
+    KML_CUDA(c, cudaMemcpyAsync(l.y.p, y + (size_t)b0 * c->n_sym * 2, sizeof(float2) * nb * c->n_sym, cudaMemcpyHostToDevice, s));
+    KML_CUDA(c, cudaMemcpyAsync(l.u_packed.p, u_packed + (size_t)b0 * c->k_words, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyHostToDevice, s));
+    KML_RC(histogram_on_lane(c, l, s, nb, var));
+    KML_CUDA(c, cudaMemcpyAsync(metrics + (size_t)b0 * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
+    if (kstar) KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    if (uu_hat_packed)
+      KML_CUDA(c, cudaMemcpyAsync(uu_hat_packed + (size_t)b0 * c->k_words, l.uu_hat_packed.p, sizeof(uint32_t) * nb * c->k_words, cudaMemcpyDeviceToHost, s));
+    KML_CUDA(c, cudaStreamSynchronize(s));
+  }
+  KML_CUDA(c, cudaMemcpyAsync(c->h_counters, c->counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  KML_CUDA(c, cudaStreamSynchronize(s));
+  KML_LEAVE(c, l, s);
   for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
   return KML_OK;
 }
 
 // ================================================================================================ device-pointer variants
+// Asynchronous on the caller's stream; scratch comes from lane 0.  Calls on different streams of one context are
+// ordered on the device by the lane's ownership event (lane_acquire), so they are safe — and serial.
+namespace {
+int check_dev_batch(kml_ctx *c, int B, const char *who) {
+  KML_RC(check_batch(c, B));
+  if (B > c->max_batch) {
+    c->err = std::string(who) + ": B exceeds max_batch";
+    return KML_ERR_ARG;
+  }
+  return KML_OK;
+}
+}  // namespace
+
 extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed, uint64_t frame0, uint32_t *u_packed,
                                 float *h, float *y, void *stream) {
-  KML_RC(check_batch(c, B));
+  KML_RC(check_dev_batch(c, B, "kml_generate_dev"));
   if (!u_packed || !h || !y) return fail_arg(c, "kml_generate_dev: null buffer");
-  if (B > c->max_batch) return fail_arg(c, "kml_generate_dev: B exceeds max_batch");
   cudaStream_t s = (cudaStream_t)stream;
   Lane &l = c->lane[0];
+  KML_ENTER(c, l, s);
   GenParams g = gen_params(c, B, snr_db, seed, frame0);
   KML_LAUNCH(c, launch_gen_bits(g, u_packed, s));
   KML_LAUNCH(c, launch_encode(g, u_packed, l.c_packed.p, s));
   KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, (float2 *)h, (float2 *)y, s));
+  KML_LEAVE(c, l, s);
   return KML_OK;
 }
 
 extern "C" int kml_kmeans_dev(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes, void *stream) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat) return fail_arg(c, "kml_kmeans_dev: null buffer");
-  KML_LAUNCH(c, launch_kmeans(B, (const float2 *)y, c->n_sym, c->points.p, c->Q, c->km_nb.p, c->km_n_nb, c->opts.kmeans_iter, (float2 *)hhat,
-                             passes, c->num_sms, (cudaStream_t)stream));
+  KML_CUDA(c, cudaSetDevice(c->device));  // (no scratch: reads y, writes hhat / passes)
+  KML_LAUNCH(c, launch_kmeans(B, y, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, (float2 *)hhat, nullptr,
+                             passes, nullptr, c->num_sms, (cudaStream_t)stream));
   return KML_OK;
 }
 
 extern "C" int kml_receive_dev(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
                                int32_t *ret, void *stream) {
-  KML_RC(check_batch(c, B));
+  KML_RC(check_dev_batch(c, B, "kml_receive_dev"));
   if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive_dev: bad argument");
-  if (B > c->max_batch) return fail_arg(c, "kml_receive_dev: B exceeds max_batch");
   Lane &l = c->lane[0];
-  cudaStream_t saved = l.stream;
-  l.stream = (cudaStream_t)stream;  // run the chain on the caller's stream with lane-0 work space
-  int rc = receive_on_lane(c, l, B, (const float2 *)y, (const float2 *)true_h, var);
-  if (rc == KML_OK && uu_hat_packed) {
-    cudaError_t e = cudaMemcpyAsync(uu_hat_packed, l.uu_hat_packed.p, sizeof(uint32_t) * (size_t)B * c->k_words, cudaMemcpyDeviceToDevice, l.stream);
-    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = KML_ERR_CUDA; }
-  }
-  if (rc == KML_OK && ret) {
-    cudaError_t e = cudaMemcpyAsync(ret, l.ret.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, l.stream);
-    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = KML_ERR_CUDA; }
-  }
-  l.stream = saved;
-  return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  KML_ENTER(c, l, s);
+  KML_RC(receive_on_lane(c, l, s, B, y, 0, (const float2 *)true_h, var));
+  if (uu_hat_packed)
+    KML_CUDA(c, cudaMemcpyAsync(uu_hat_packed, l.uu_hat_packed.p, sizeof(uint32_t) * (size_t)B * c->k_words, cudaMemcpyDeviceToDevice, s));
+  if (ret) KML_CUDA(c, cudaMemcpyAsync(ret, l.ret.p, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, s));
+  KML_LEAVE(c, l, s);
+  return KML_OK;
 }
 
 extern "C" int kml_demap_dev(kml_ctx *c, int B, const float *y, const float *h, double var, float *llr, void *stream) {
-  KML_RC(check_batch(c, B));
+  KML_RC(check_dev_batch(c, B, "kml_demap_dev"));
   if (!y || !h || !llr || !(var > 0)) return fail_arg(c, "kml_demap_dev: bad argument");
   Lane &l = c->lane[0];
+  KML_CUDA(c, cudaSetDevice(c->device));  // (no scratch: the ratios go straight to the caller's buffer)
   DemapParams d = demap_params(c, l, B, var, 1, 0);
   d.y = (const float2 *)y;
   d.h = (const float2 *)h;
@@ -966,11 +1201,14 @@ extern "C" int kml_demap_dev(kml_ctx *c, int B, const float *y, const float *h, 
 
 extern "C" int kml_decode_dev(kml_ctx *c, int B, const float *llr, int in_is_lr, int iter_count, uint32_t *cc_hat_packed,
                               int32_t *ret, void *stream) {
-  KML_RC(check_batch(c, B));
+  KML_RC(check_dev_batch(c, B, "kml_decode_dev"));
   if (!llr || !cc_hat_packed || !ret || iter_count < 1) return fail_arg(c, "kml_decode_dev: bad argument");
   Lane &l = c->lane[0];
+  cudaStream_t s = (cudaStream_t)stream;
+  KML_ENTER(c, l, s);  // (the frame queue's counter is lane scratch)
   DecParams p = dec_params(c, l, B, llr, nullptr, 1, in_is_lr, iter_count, cc_hat_packed, ret, nullptr);
-  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, (cudaStream_t)stream));
+  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+  KML_LEAVE(c, l, s);
   return KML_OK;
 }
 
@@ -978,6 +1216,7 @@ extern "C" int kml_count_errors_dev(kml_ctx *c, int B, const uint32_t *u_packed,
                                     uint64_t *counters_dev, void *stream) {
   KML_RC(check_batch(c, B));
   if (!u_packed || !uu_hat_packed || !counters_dev) return fail_arg(c, "kml_count_errors_dev: null buffer");
+  KML_CUDA(c, cudaSetDevice(c->device));
   KML_LAUNCH(c, launch_count_errors(B, c->K, c->k_words, u_packed, uu_hat_packed, nullptr, c->opts.max_iter,
                                    (unsigned long long *)counters_dev, (cudaStream_t)stream));
   return KML_OK;

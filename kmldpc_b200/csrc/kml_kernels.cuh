@@ -33,13 +33,29 @@ struct DecParams {
   int B, iters, max_iter, early_exit;
   uint32_t *out_bits;       // [B][words_n] hard decisions of all graph variables, bit-packed
   int32_t *out_ret;         // [B] reference return value: iter + (iter < max_iter)
-  float *out_soft;          // optional [B]: sum over rows of ln(syndrom_soft) after the LAST check-node phase executed
+  double *out_soft;         // optional [B]: sum over rows of ln(syndrom_soft) after the LAST check-node phase executed
+                            // (accumulated with atomics: zero it first; untouched for a frame that leaves at t = 0)
   float *out_synd;          // optional [B]: unsatisfied checks of the final decisions (= ParityCheck(cc_hat)); only the
                             // kernels dec_has_synd_output() names fill it
   unsigned int *work_counter;  // dynamic frame scheduler (zeroed by the launcher)
   int words_n;
   float alpha;              // min-sum normalisation (algorithm = 1 only)
+  // optional frame queue: entry i of the queue decodes frame frame_idx[i]; the queue length is *n_frames_dev (written by
+  // an earlier kernel of the stream; B is then only the upper bound the grid is sized for).  Inputs and outputs stay
+  // indexed by the frame number, so a queue is just a subset / an order of the batch.
+  const int32_t *frame_idx;
+  const int32_t *n_frames_dev;
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int frame_count(const DecParams &p) { return p.n_frames_dev ? min(__ldg(p.n_frames_dev), p.B) : p.B; }
+// thread 0 of a CTA: the next frame of the queue, or -1 when it is empty
+__device__ __forceinline__ int next_frame(const DecParams &p) {
+  const int i = (int)atomicAdd(p.work_counter, 1u);
+  if (i >= frame_count(p)) return -1;
+  return p.frame_idx ? __ldg(p.frame_idx + i) : i;
+}
+#endif
 
 enum DecKernelKind { DEC_REG_6_3 = 0, DEC_REG_12_6 = 1, DEC_GEN_4_8 = 2, DEC_GEN_9_10 = 3, DEC_GEN_16_32 = 4 };
 
@@ -84,9 +100,21 @@ cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const f
                            float2 *h_out, float2 *y, cudaStream_t s);
 
 // ---- k-means blind channel estimate ------------------------------------------------------------------------------
-// nb[n_nb] = Voronoi neighbours of constellation point 0 (host_code.cpp); nullptr → full comparison kernel
-cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, const int *nb, int n_nb,
-                          int iters, float2 *hhat, int32_t *passes, int num_sms, cudaStream_t s);
+// fp64 constants of the warp kernel (host_code.cpp fills them from the constellation): s_0, 1 / s_0 and, for each Voronoi
+// neighbour t of s_0, ds_t = s_t - s_0 and dn_t = (|s_t|^2 - |s_0|^2) / 2 — the half-plane of neighbour t under the
+// estimate h is  Re(conj(ds_t h) y) <= dn_t |h|^2.
+struct KmConst {
+  double s0r, s0i, is0r, is0i;
+  double dsr[8], dsi[8], dn[8];
+  int n_nb;  // 0 → the general kernel (full distance comparison against every constellation point)
+};
+// y: float2 [B][n_sym], or double2 when y_is_f64 (then y32_out, if given, receives the fp32 copy the demapper reads).
+// hhat64 (optional): the estimate as carried (fp64).
+cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms,
+                          cudaStream_t s);
+cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream_t s);
+cudaError_t launch_p0_to_lr(size_t n, const double *p0, float *lr, cudaStream_t s);
 
 // ---- soft demapper + candidate resolver ---------------------------------------------------------------------------
 struct DemapParams {
@@ -113,6 +141,22 @@ cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s);
 cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
                                    const int32_t *col_idx, float *metric, cudaStream_t s);
 cudaError_t launch_abs_inplace(int n, float *v, cudaStream_t s);
+// the reference's stale-syndrom_soft_ chain of the soft metric (see soft_chain_kernel)
+struct SoftChainParams {
+  int B, final_decode;    // final_decode = 0: GetMetrics only (histogram mode, kml_resolve)
+  const double *own;      // [B][4] sum of ln(syndrom_soft) each metric decode produced itself
+  const int32_t *mret;    // [B][4] its return value; 1 = left at iteration 0 = syndrom_soft_ untouched
+  const double *fown;     // [B] the same of the frame's final decode (valid once it has been through the queue)
+  const int32_t *fret;    // [B]
+  double *carry;          // [1] in: the sum as the previous call left it; out: as this batch leaves it
+  float *metric;          // [B][4] |metric| (kmcodec.cc:137)
+  int32_t *kstar;         // [B] -1 = not chosen yet
+  double *state;          // [B] value after the frame
+  int32_t *flags;         // [B] zeroed by the caller
+  int32_t *queue;         // [B] frames chosen in this round (to be decoded before the next round)
+  int32_t *counts;        // [2] queue length of this round, frames whose state is still unknown
+};
+cudaError_t launch_soft_chain(const SoftChainParams &p, int round, cudaStream_t s);
 cudaError_t launch_argmin4(int B, const float *metric, int32_t *kstar, cudaStream_t s);
 
 // ---- small utilities ------------------------------------------------------------------------------------------------

@@ -218,7 +218,7 @@ __global__ void channel_kernel(GenParams g, const uint32_t *c_packed, const floa
 constexpr int KM_THREADS = 128;
 template <int SPT>
 __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 *y, int n, const float2 *points, int q,
-                                                           int iters, float2 *hhat_out, int32_t *passes_out) {
+                                                           int iters, float2 *hhat_out, double2 *hhat64_out, int32_t *passes_out) {
   extern __shared__ float2 s_c[];  // [q] centroids
   __shared__ float s_red[3][KM_THREADS / 32];
   __shared__ unsigned long long s_best[KM_THREADS / 32];
@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 
     }
     if (tid == 0) {
       hhat_out[f] = make_float2((float)s_h[0], (float)s_h[1]);
+      if (hhat64_out) hhat64_out[f] = make_double2(s_h[0], s_h[1]);
       if (passes_out) passes_out[f] = passes;
     }
     __syncthreads();
@@ -339,17 +340,19 @@ __global__ void __launch_bounds__(KM_THREADS) kmeans_kernel(int B, const float2 
 
 // Warp-per-frame variant (the fast path): no block barriers, samples in registers (lane l holds samples l, l+32, …),
 // and the nearest-is-cluster-0 predicate evaluated only against the Voronoi neighbours of s_0 as half-plane tests
-//   |y - c_0|^2 <= |y - c_k|^2   <=>   Re(conj(c_k - c_0) y) <= (|c_k|^2 - |c_0|^2) / 2 ,
-// 2 FMA + 1 compare per neighbour instead of a full distance per constellation point.  Every lane carries the same fp64
-// cumulative sums (xor-shuffle reductions give all lanes the same value), so no broadcast is needed.
+//   |y - c_0|^2 <= |y - c_k|^2   <=>   Re(conj(c_k - c_0) y) <= (|c_k|^2 - |c_0|^2) / 2 .
+//
+// EXACT ASSIGNMENTS.  north_star asks for centroids within 1e-4 of the reference on every frame, and one sample that
+// falls on the other side of a cell boundary moves the (cumulative) mean by more than that.  So the estimate is carried
+// in fp64 like the reference's, and the fp32 arithmetic is only a FILTER: d = Re(conj(a) y) - th is evaluated in packed
+// fp32 with a bound tau on its own rounding error; |d| > tau decides the sample, and a pass in which any sample of the
+// warp lands inside the band re-evaluates its membership in fp64 (a few per thousand passes).  The sums the reference
+// accumulates sample by sample (kmeans.cc:44-45) are kept exact the cheap way: cluster 0's membership barely changes
+// from one pass to the next, so the kernel keeps the fp64 sum of the CURRENT member set and corrects it by the samples
+// that entered or left (fp64, from the exact input values) — the common pass adds nothing per sample.
+// Every lane carries the same fp64 state (xor-shuffle reductions give all lanes the same value): no broadcasts.
 constexpr int KMW_WARPS = 4;
 // Blackwell packed fp32 (SASS FMUL2 / FFMA2): two neighbour half-plane tests per instruction
-__device__ __forceinline__ float2 km_mul2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
 __device__ __forceinline__ float2 km_fma2(float2 a, float2 b, float2 c) {
   float2 d;
   asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
@@ -357,97 +360,232 @@ __device__ __forceinline__ float2 km_fma2(float2 a, float2 b, float2 c) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+// 1 / c for an integer-valued c in [1, 2^24): MUFU seed + two Newton steps in fp64 (relative error ~1e-16)
+__device__ __forceinline__ double km_rcp_count(double c) {
+  float rf;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)c));
+  double r = (double)rf;
+  r = fma(r, fma(-c, r, 1.0), r);
+  r = fma(r, fma(-c, r, 1.0), r);
+  return r;
+}
+// The exact input value of a sample for the rare fp64 blocks: re-read from memory (an L1 / L2 hit) through a volatile
+// asm, so that the compiler cannot hoist 2 x SPL conversions to fp64 out of those blocks into the hot loop's registers.
+__device__ __forceinline__ double2 km_exact_load(const float2 *p) {
+  float x, y;
+  asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
+  return make_double2((double)x, (double)y);
+}
+__device__ __forceinline__ double2 km_exact_load(const double2 *p) {
+  double x, y;
+  asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(x), "=d"(y) : "l"(p));
+  return make_double2(x, y);
+}
+__device__ __forceinline__ double km_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-template <int SPL, int MAXNB>
-__global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 24 ? 6 : (SPL <= 36 ? 5 : (SPL <= 48 ? 4 : 3)))
-kmeans_warp_kernel(int B, const float2 *y, int n, const float2 *points, const int *nb, int n_nb, int iters,
-                   float2 *hhat_out, int32_t *passes_out) {
-  static_assert(MAXNB % 2 == 0, "neighbours are tested in pairs");
+template <int SPL>
+struct KmMask {  // one membership bit per sample of the lane
+  uint32_t lo = 0, hi = 0;
+  __device__ __forceinline__ void set(int j, bool v) {
+    if (v) {
+      if (j < 32) lo |= 1u << j;
+      else hi |= 1u << (j - 32);
+    }
+  }
+  __device__ __forceinline__ bool get(int j) const { return j < 32 ? (lo >> j) & 1u : (hi >> (j - 32)) & 1u; }
+  __device__ __forceinline__ bool any() const { return SPL > 32 ? (lo | hi) != 0 : lo != 0; }
+};
+
+template <int SPL, int MAXNB, bool F64IN>
+__global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 16 ? 6 : (SPL <= 24 ? 5 : (SPL <= 36 ? 4 : (SPL <= 48 ? 3 : 2))))
+kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, float2 *hhat_out, double2 *hhat64_out,
+                   int32_t *passes_out, float2 *y32_out) {
+  static_assert(MAXNB % 2 == 0 && SPL <= 64, "neighbours are tested in pairs; one mask bit per sample");
+  constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
-  const float2 s0f = __ldg(points);
-  // 1 / s_0 = conj(s_0) / |s_0|^2, so that hhat = (cluster-0 mean) / s_0 is one complex multiply
-  const double s0n = (double)s0f.x * s0f.x + (double)s0f.y * s0f.y;
-  const float is0r = (float)((double)s0f.x / s0n), is0i = (float)(-(double)s0f.y / s0n);
+  const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
   float2 snb[MAXNB];
 #pragma unroll
-  for (int t = 0; t < MAXNB; t++) snb[t] = t < n_nb ? __ldg(points + __ldg(nb + t)) : s0f;
+  for (int t = 0; t < MAXNB; t++)
+    snb[t] = make_float2((float)(kc.s0r + kc.dsr[t < kc.n_nb ? t : 0]), (float)(kc.s0i + kc.dsi[t < kc.n_nb ? t : 0]));
   for (int f = wglobal; f < B; f += wstride) {
-    const float2 *yf = y + (size_t)f * n;
+    const float2 *yf = reinterpret_cast<const float2 *>(y_in) + (size_t)f * n;
+    const double2 *yd = reinterpret_cast<const double2 *>(y_in) + (size_t)f * n;
+    auto exact = [&](int j) -> double2 {  // the input value itself, as the reference sees it
+      return F64IN ? km_exact_load(yd + j * 32 + lane) : km_exact_load(yf + j * 32 + lane);
+    };
     float2 ys[SPL];
     unsigned long long best = 0ull;
-    const float qnan = __int_as_float(0x7fc00000);
+    KmMask<SPL> valid;
 #pragma unroll
     for (int j = 0; j < SPL; j++) {
       const int i = j * 32 + lane;
       if (i < n) {
-        ys[j] = yf[i];
-        const float a2 = ys[j].x * ys[j].x + ys[j].y * ys[j].y;
+        if (F64IN) {
+          const double2 v = yd[i];
+          ys[j] = make_float2((float)v.x, (float)v.y);
+          if (y32_out) y32_out[(size_t)f * n + i] = ys[j];  // the fp32 copy the demapper reads
+        } else {
+          ys[j] = yf[i];
+        }
+        valid.set(j, true);
+        // |y|^2 is monotone in |y|; ties → smallest index (max_element returns the first maximum)
+        const float a2 = fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x);
         const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
         best = key > best ? key : best;
       } else {
-        ys[j] = make_float2(qnan, qnan);  // fails every half-plane test → never counted
+        ys[j] = make_float2(0.f, 0.f);  // masked out of the membership below
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      const unsigned long long other = __shfl_xor_sync(FULL, best, o);
       best = other > best ? other : best;
     }
-    const float2 ya = yf[0x7fffffff - (int)(uint32_t)(best & 0xffffffffu)];
-    float hr = ya.x * is0r - ya.y * is0i, hi = ya.x * is0i + ya.y * is0r;  // y_a / s_0
+    int anchor = 0x7fffffff - (int)(uint32_t)(best & 0xffffffffu);
+    const float amax2 = __uint_as_float((uint32_t)(best >> 32));
+    {  // fp32 cannot order magnitudes closer than a few ulp: when a second sample is that close, order them in fp64
+      const float thr = amax2 * (1.0f - 2.0e-6f);
+      int near = 0;
+#pragma unroll
+      for (int j = 0; j < SPL; j++) near += (valid.get(j) && fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x) >= thr) ? 1 : 0;
+      const unsigned who = __ballot_sync(FULL, near > 0);
+      if (__popc(who) > 1 || __any_sync(FULL, near > 1)) {
+        double bd = -1.0;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < SPL; j++)
+          if (valid.get(j) && fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x) >= thr) {
+            const double2 v = exact(j);
+            const double d2 = fma(v.y, v.y, v.x * v.x);
+            if (d2 > bd) { bd = d2; bi = j * 32 + lane; }  // ascending index within the lane: first maximum kept
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double od = __shfl_xor_sync(FULL, bd, o);
+          const int oi = __shfl_xor_sync(FULL, bi, o);
+          if (od > bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
+        anchor = bi;
+      }
+    }
+    const float ymax_l1 = 1.4142137f * sqrtf(amax2);  // |y_x| + |y_y| <= sqrt(2) |y|
+    double hr, hi;
+    {
+      const double2 ya = F64IN ? yd[anchor] : make_double2((double)yf[anchor].x, (double)yf[anchor].y);
+      hr = ya.x * kc.is0r - ya.y * kc.is0i;  // y_a / s_0
+      hi = ya.x * kc.is0i + ya.y * kc.is0r;
+    }
     double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0;  // cumulative over passes (never reset: kmeans.cc:33-34 as compiled)
-    float prev_r = 0.f, prev_i = 0.f;
+    double set_re = 0.0, set_im = 0.0;                 // exact sums over the current member set of cluster 0
+    int set_cnt = 0;
+    KmMask<SPL> member;
+    double prev_r = 0.0, prev_i = 0.0;
     bool have_prev = false;
     int passes = 0;
     for (int it = 0; it < iters; it++) {
       passes++;
-      const float2 c0 = make_float2(s0f.x * hr - s0f.y * hi, s0f.x * hi + s0f.y * hr);
+      // ---- fp32 filter: d_t = Re(conj(c_t - c_0) y) - (|c_t|^2 - |c_0|^2) / 2, in cluster 0 iff every d_t <= 0
+      const float fhr = (float)hr, fhi = (float)hi;
+      const float2 c0 = make_float2(s0f.x * fhr - s0f.y * fhi, s0f.x * fhi + s0f.y * fhr);
       const float n0 = c0.x * c0.x + c0.y * c0.y;
-      float2 ax[MAXNB / 2], ay[MAXNB / 2], th[MAXNB / 2];
+      float2 ax[MAXNB / 2], ay[MAXNB / 2], nth[MAXNB / 2];
+      float cmax2 = n0;
 #pragma unroll
       for (int t = 0; t < MAXNB; t++) {
-        const float2 ck = make_float2(snb[t].x * hr - snb[t].y * hi, snb[t].x * hi + snb[t].y * hr);
-        const float axx = ck.x - c0.x, ayy = ck.y - c0.y;
-        const float thh = t < n_nb ? 0.5f * (ck.x * ck.x + ck.y * ck.y - n0) : 3.0e38f;
-        if (t & 1) { ax[t / 2].y = axx; ay[t / 2].y = ayy; th[t / 2].y = thh; }
-        else { ax[t / 2].x = axx; ay[t / 2].x = ayy; th[t / 2].x = thh; }
+        const float2 ck = make_float2(snb[t].x * fhr - snb[t].y * fhi, snb[t].x * fhi + snb[t].y * fhr);
+        const float nk = ck.x * ck.x + ck.y * ck.y;
+        cmax2 = fmaxf(cmax2, nk);
+        const bool used = t < kc.n_nb;
+        const float axx = used ? ck.x - c0.x : 0.f, ayy = used ? ck.y - c0.y : 0.f;
+        const float nt = used ? -0.5f * (nk - n0) : -3.0e38f;  // unused slot: never the maximum
+        if (t & 1) { ax[t / 2].y = axx; ay[t / 2].y = ayy; nth[t / 2].y = nt; }
+        else { ax[t / 2].x = axx; ay[t / 2].x = ayy; nth[t / 2].x = nt; }
       }
-      float cnt = 0.f, sr = 0.f, si = 0.f;
+      // rounding of the filter: hhat, c_t, a_t, th_t and the two FMAs each within a few 6e-8 of |c| (|y| + |c|): the
+      // band is >= 5x that bound
+      const float cmax = sqrtf(cmax2);
+      const float tau = 4.0e-6f * cmax * (ymax_l1 + cmax);
+      KmMask<SPL> now;
+      bool unsure = false;
 #pragma unroll
       for (int j = 0; j < SPL; j++) {
-        bool in0 = true;
+        float dmax = -3.0e38f;
 #pragma unroll
         for (int t = 0; t < MAXNB / 2; t++) {
-          const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_mul2(ay[t], make_float2(ys[j].y, ys[j].y)));
-          in0 = in0 && (v.x <= th[t].x) && (v.y <= th[t].y);
+          const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_fma2(ay[t], make_float2(ys[j].y, ys[j].y), nth[t]));
+          dmax = fmaxf(dmax, fmaxf(v.x, v.y));
         }
-        if (in0) {
-          cnt += 1.f;
-          sr += ys[j].x;
-          si += ys[j].y;
-        }
+        now.set(j, dmax <= 0.0f);  // first minimum wins ties → cluster 0 keeps them
+        unsure = unsure || (fabsf(dmax) <= tau);
       }
+      if (__any_sync(FULL, unsure)) {  // rare: this pass's membership in fp64 from the fp64 estimate
+        double ar[MAXNB], ai[MAXNB], th[MAXNB];
+        const double h2 = hr * hr + hi * hi;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        si += __shfl_xor_sync(0xffffffffu, si, o);
+        for (int t = 0; t < MAXNB; t++) {
+          ar[t] = kc.dsr[t] * hr - kc.dsi[t] * hi;
+          ai[t] = kc.dsr[t] * hi + kc.dsi[t] * hr;
+          th[t] = kc.dn[t] * h2;
+        }
+        now = KmMask<SPL>();
+#pragma unroll
+        for (int j = 0; j < SPL; j++) {
+          if (!valid.get(j)) continue;
+          const double2 v = exact(j);
+          bool in0 = true;
+#pragma unroll
+          for (int t = 0; t < MAXNB; t++)
+            if (t < kc.n_nb) in0 = in0 && (fma(ar[t], v.x, ai[t] * v.y) <= th[t]);
+          now.set(j, in0);
+        }
       }
-      cum_cnt += (double)cnt;
-      cum_re += (double)sr;
-      cum_im += (double)si;
+      now.lo &= valid.lo;
+      now.hi &= valid.hi;
+      KmMask<SPL> chg;
+      chg.lo = now.lo ^ member.lo;
+      chg.hi = now.hi ^ member.hi;
+      if (__any_sync(FULL, chg.any())) {  // samples that entered / left cluster 0 since the last pass
+        double dr = 0.0, di = 0.0;
+        int dc = 0;
+#pragma unroll
+        for (int j = 0; j < SPL; j++) {
+          if (!__any_sync(FULL, chg.get(j))) continue;
+          if (chg.get(j)) {
+            const double2 v = exact(j);
+            const bool in = now.get(j);
+            dr += in ? v.x : -v.x;
+            di += in ? v.y : -v.y;
+            dc += in ? 1 : -1;
+          }
+        }
+        set_re += km_warp_sum(dr);
+        set_im += km_warp_sum(di);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dc += __shfl_xor_sync(FULL, dc, o);
+        set_cnt += dc;
+        member = now;
+      }
+      cum_cnt += (double)set_cnt;
+      cum_re += set_re;
+      cum_im += set_im;
       if (have_prev && prev_r == hr && prev_i == hi) break;  // clusters_ == tempClusters (kmeans.cc:47-56)
       prev_r = hr;
       prev_i = hi;
       have_prev = true;
-      const float inv = __fdividef(1.0f, (float)cum_cnt);  // cluster 0 is never empty: the anchor sample sits on c_0
-      const float mr = (float)cum_re * inv, mi = (float)cum_im * inv;
-      hr = mr * is0r - mi * is0i;
-      hi = mr * is0i + mi * is0r;
+      const double inv = km_rcp_count(cum_cnt);  // cluster 0 is never empty: the anchor sample sits on c_0
+      const double mr = cum_re * inv, mi = cum_im * inv;
+      hr = mr * kc.is0r - mi * kc.is0i;
+      hi = mr * kc.is0i + mi * kc.is0r;
     }
     if (lane == 0) {
-      hhat_out[f] = make_float2(hr, hi);
+      hhat_out[f] = make_float2((float)hr, (float)hi);
+      if (hhat64_out) hhat64_out[f] = make_double2(hr, hi);
       if (passes_out) passes_out[f] = passes;
     }
   }
@@ -768,6 +906,80 @@ __global__ void syndrome_weight_kernel(int F, const uint32_t *bits, int words_n,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ soft-syndrome chain
+// The soft metric (kmcodec.cc:146-155) sums ln(syndrom_soft_[r]) AFTER Decoder(metric_iter) — but the decoder writes
+// syndrom_soft_ only in its check-node phase (binaryldpccodec.cc:274), so a decode that leaves at iteration 0
+// (binaryldpccodec.cc:231-232) leaves the array as the PREVIOUS Decoder call left it: the previous candidate of the
+// frame, or the previous frame's final decode, or whatever that one inherited.  Only the sum is ever read, so the state
+// is one number per codec.  This kernel walks that chain for a batch: frame f's candidate 0 needs the state after
+// frame f-1, which needs f-1's final decode, which needs f-1's choice …  Frames whose candidate 0 wrote its own value
+// depend on nothing and resolve at once; the rest resolve as their predecessor's state becomes known — immediately
+// when that final decode leaves at iteration 0 too, else after the host has run it (one round per link of a chain of
+// consecutive dependent frames).  One CTA; flags[f]: bit 0 = state known, bits 8.. = 1 + round the frame was queued in.
+__global__ void __launch_bounds__(1024) soft_chain_kernel(SoftChainParams p, int round) {
+  __shared__ int s_q, s_left;
+  const int tid = threadIdx.x;
+  if (tid == 0) { s_q = 0; s_left = 0; }
+  __syncthreads();
+  volatile int32_t *flags = p.flags;
+  volatile double *state = p.state;
+  volatile int32_t *kstar = p.kstar;
+  for (bool again = true; again;) {
+    int progress = 0;
+    for (int f = tid; f < p.B; f += blockDim.x) {
+      const int fl = flags[f];
+      if (fl & 1) continue;
+      if (kstar[f] >= 0) {  // chosen in an earlier round: its final decode has run by now
+        if ((fl >> 8) != 0 && (fl >> 8) <= round) {
+          if (p.fret[f] != 1) state[f] = p.fown[f];  // (else: the value after the fourth candidate, already there)
+          __threadfence_block();
+          flags[f] = fl | 1;
+          progress = 1;
+        }
+        continue;
+      }
+      const int32_t *mr = p.mret + 4 * (size_t)f;
+      double m[4];
+      if (mr[0] == 1) {  // candidate 0 left at t = 0: inherits the state the previous frame left
+        if (f == 0) m[0] = *p.carry;
+        else if (flags[f - 1] & 1) { __threadfence_block(); m[0] = state[f - 1]; }
+        else continue;
+      } else {
+        m[0] = p.own[4 * (size_t)f];
+      }
+      int best = 0;
+#pragma unroll
+      for (int c = 1; c < 4; c++) m[c] = mr[c] == 1 ? m[c - 1] : p.own[4 * (size_t)f + c];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        p.metric[4 * (size_t)f + c] = (float)fabs(m[c]);  // kmcodec.cc:137
+        if (fabs(m[c]) < fabs(m[best])) best = c;          // first minimum (kmcodec.cc:61-65)
+      }
+      state[f] = m[3];
+      kstar[f] = best;
+      int nf = fl;
+      if (p.final_decode) {
+        p.queue[atomicAdd(&s_q, 1)] = f;
+        nf |= (round + 1) << 8;
+      }
+      __threadfence_block();
+      if (!p.final_decode || mr[best] == 1) nf |= 1;  // no final decode, or it will leave at t = 0 as well
+      flags[f] = nf;
+      progress = 1;
+    }
+    again = __syncthreads_or(progress) != 0;
+  }
+  int left = 0;
+  for (int f = tid; f < p.B; f += blockDim.x) left += (flags[f] & 1) ? 0 : 1;
+  if (left) atomicAdd(&s_left, left);
+  __syncthreads();
+  if (tid == 0) {
+    p.counts[0] = s_q;
+    p.counts[1] = s_left;
+    if (s_left == 0 && p.B > 0) *p.carry = state[p.B - 1];
+  }
+}
+
 __global__ void abs_kernel(int n, float *v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = fabsf(v[i]);
@@ -897,31 +1109,69 @@ cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const f
   return cudaGetLastError();
 }
 
-cudaError_t launch_kmeans(int B, const float2 *y, int n_sym, const float2 *points, int q, const int *nb, int n_nb,
-                          int iters, float2 *hhat, int32_t *passes, int num_sms, cudaStream_t s) {
-  if (B < 1) return cudaSuccess;
-  if (nb && n_nb >= 1 && n_nb <= 8 && n_sym <= 32 * 64) {  // warp per frame, Voronoi-neighbour half-plane tests
-    const int spl = (n_sym + 31) / 32;
-    const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
-#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, points, nb, n_nb, iters, hhat, passes)
-    if (n_nb <= 2) {
-      if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
-    } else if (n_nb <= 4) {
-      if (spl <= 16) KMW(16, 4); else if (spl <= 24) KMW(24, 4); else if (spl <= 36) KMW(36, 4); else if (spl <= 48) KMW(48, 4); else KMW(64, 4);
-    } else {
-      if (spl <= 16) KMW(16, 8); else if (spl <= 24) KMW(24, 8); else if (spl <= 36) KMW(36, 8); else if (spl <= 48) KMW(48, 8); else KMW(64, 8);
-    }
-#undef KMW
-    return cudaGetLastError();
+// the reference decoder's own input — double P(bit = 0) (binaryldpccodec.cc:165) — to the kernels' likelihood ratio
+__global__ void p0_to_lr_kernel(size_t n, const double *p0, float *lr) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double p = p0[i], r = p / (1.0 - p);
+    lr[i] = (float)fmin(fmax(r, 1.0e-12), 1.0e12);
   }
-  // general fallback: one CTA per frame, full distance comparison against every constellation point
+}
+cudaError_t launch_p0_to_lr(size_t n, const double *p0, float *lr, cudaStream_t s) {
+  if (n < 1) return cudaSuccess;
+  p0_to_lr_kernel<<<grid_for((long long)n, 256), 256, 0, s>>>(n, p0, lr);
+  return cudaGetLastError();
+}
+
+__global__ void f64_to_f32_kernel(size_t n, const double *in, float *out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream_t s) {
+  if (n < 1) return cudaSuccess;
+  f64_to_f32_kernel<<<grid_for((long long)n, 256), 256, 0, s>>>(n, in, out);
+  return cudaGetLastError();
+}
+
+template <bool F64IN>
+static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmConst &kc, int iters, float2 *hhat,
+                                      double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms, cudaStream_t s) {
+  const int spl = (n_sym + 31) / 32;
+  const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
+#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out)
+  if (kc.n_nb <= 2) {
+    if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
+  } else if (kc.n_nb <= 4) {
+    if (spl <= 16) KMW(16, 4); else if (spl <= 24) KMW(24, 4); else if (spl <= 36) KMW(36, 4); else if (spl <= 48) KMW(48, 4); else KMW(64, 4);
+  } else {
+    if (spl <= 16) KMW(16, 8); else if (spl <= 24) KMW(24, 8); else if (spl <= 36) KMW(36, 8); else if (spl <= 48) KMW(48, 8); else KMW(64, 8);
+  }
+#undef KMW
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms,
+                          cudaStream_t s) {
+  if (B < 1) return cudaSuccess;
+  if (kc.n_nb >= 1 && kc.n_nb <= 8 && n_sym <= 32 * 64) {  // warp per frame, Voronoi-neighbour half-plane tests
+    return y_is_f64 ? launch_kmeans_warp<true>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, num_sms, s)
+                    : launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, num_sms, s);
+  }
+  // general fallback (constellations whose first point has more than 8 Voronoi neighbours, very long frames): one CTA
+  // per frame, full distance comparison in fp32 against every constellation point
+  const float2 *y32 = reinterpret_cast<const float2 *>(y);
+  if (y_is_f64) {
+    if (!y32_out) return cudaErrorInvalidValue;
+    cudaError_t e = launch_f64_to_f32((size_t)B * n_sym * 2, reinterpret_cast<const double *>(y), reinterpret_cast<float *>(y32_out), s);
+    if (e != cudaSuccess) return e;
+    y32 = y32_out;
+  }
   const int spt = (n_sym + KM_THREADS - 1) / KM_THREADS;
   const int grid = B < num_sms * 8 ? B : num_sms * 8;
   const int smem = q * (int)sizeof(float2);
-  if (spt <= 4) kmeans_kernel<4><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
-  else if (spt <= 9) kmeans_kernel<9><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
-  else if (spt <= 16) kmeans_kernel<16><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
-  else if (spt <= 64) kmeans_kernel<64><<<grid, KM_THREADS, smem, s>>>(B, y, n_sym, points, q, iters, hhat, passes);
+  if (spt <= 4) kmeans_kernel<4><<<grid, KM_THREADS, smem, s>>>(B, y32, n_sym, points, q, iters, hhat, hhat64, passes);
+  else if (spt <= 9) kmeans_kernel<9><<<grid, KM_THREADS, smem, s>>>(B, y32, n_sym, points, q, iters, hhat, hhat64, passes);
+  else if (spt <= 16) kmeans_kernel<16><<<grid, KM_THREADS, smem, s>>>(B, y32, n_sym, points, q, iters, hhat, hhat64, passes);
+  else if (spt <= 64) kmeans_kernel<64><<<grid, KM_THREADS, smem, s>>>(B, y32, n_sym, points, q, iters, hhat, hhat64, passes);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -961,6 +1211,11 @@ cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int
                                    const int32_t *col_idx, float *metric, cudaStream_t s) {
   if (F < 1) return cudaSuccess;
   syndrome_weight_kernel<<<F < 148 * 8 ? F : 148 * 8, 256, 0, s>>>(F, bits, words_n, m_rows, row_ptr, col_idx, metric);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_soft_chain(const SoftChainParams &p, int round, cudaStream_t s) {
+  soft_chain_kernel<<<1, 1024, 0, s>>>(p, round);
   return cudaGetLastError();
 }
 

@@ -181,6 +181,16 @@ class Link:
                     "kml_kmeans")
         return hhat.view(np.complex64).reshape(B), passes
 
+    def kmeans_f64(self, y: np.ndarray):
+        """The reference's types: y complex128 [B, n_sym] → hhat complex128 [B] (the estimate as carried in fp64)."""
+        y = np.ascontiguousarray(np.asarray(y, np.complex128).reshape(-1, self.n_sym))
+        B = y.shape[0]
+        hhat = np.empty((B, 2), np.float64)
+        passes = np.empty(B, np.int32)
+        self._check(self._lib.kml_kmeans_f64(self._h, B, _ptr(y.view(np.float64), C.c_double), _ptr(hhat, C.c_double),
+                                             _ptr(passes, C.c_int32)), "kml_kmeans_f64")
+        return hhat.view(np.complex128).reshape(B), passes
+
     def demap(self, y: np.ndarray, h: np.ndarray, var: float) -> np.ndarray:
         y, yf = self._y(y)
         B = y.shape[0]
@@ -209,6 +219,46 @@ class Link:
         self._check(self._lib.kml_decode(self._h, B, _ptr(llr, C.c_float), iter_count or self.max_iter,
                                          _ptr(cc, C.c_int32), _ptr(uu, C.c_int32), _ptr(ret, C.c_int32)), "kml_decode")
         return cc, uu, ret
+
+    def decode_p0(self, p0: np.ndarray, iter_count: int | None = None):
+        """BinaryLDPCCodec::Decoder's own input: P(bit = 0) in double [B, n_tx]."""
+        p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, self.code.N_tx)
+        B = p0.shape[0]
+        cc = np.empty((B, self.code.N), np.int32)
+        uu = np.empty((B, self.code.K), np.int32)
+        ret = np.empty(B, np.int32)
+        self._check(self._lib.kml_decode_p0(self._h, B, _ptr(p0, C.c_double), iter_count or self.max_iter,
+                                            _ptr(cc, C.c_int32), _ptr(uu, C.c_int32), _ptr(ret, C.c_int32)), "kml_decode_p0")
+        return cc, uu, ret
+
+    def receive_f64(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None):
+        """kml_receive on the reference's types: y complex128 [B, n_sym], true_h complex128 [B].
+        Returns uu_hat_packed, hhat (complex128), kstar, ret."""
+        y = np.ascontiguousarray(np.asarray(y, np.complex128).reshape(-1, self.n_sym))
+        B = y.shape[0]
+        th = None
+        if true_h is not None:
+            th = np.ascontiguousarray(np.asarray(true_h, np.complex128).reshape(B)).view(np.float64)
+        uu = np.empty((B, self.k_words), np.uint32)
+        hhat = np.zeros((B, 2), np.float64)
+        kstar = np.zeros(B, np.int32)
+        ret = np.empty(B, np.int32)
+        self._check(self._lib.kml_receive_f64(self._h, B, _ptr(y.view(np.float64), C.c_double), _ptr(th, C.c_double), var,
+                                              _ptr(uu, C.c_uint32), _ptr(hhat, C.c_double), _ptr(kstar, C.c_int32),
+                                              _ptr(ret, C.c_int32)), "kml_receive_f64")
+        return uu, hhat.view(np.complex128).reshape(B), kstar, ret
+
+    @property
+    def soft_state(self) -> float:
+        """Sum of ln(syndrom_soft_) as the context's last Decoder call left it (soft-syndrome metric's stale-value chain)."""
+        v = C.c_double(0.0)
+        self._check(self._lib.kml_soft_syndrome_state(self._h, 0, C.byref(v)), "kml_soft_syndrome_state")
+        return float(v.value)
+
+    @soft_state.setter
+    def soft_state(self, value: float):
+        v = C.c_double(float(value))
+        self._check(self._lib.kml_soft_syndrome_state(self._h, 1, C.byref(v)), "kml_soft_syndrome_state")
 
     def receive(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None, out=None):
         """y: complex64 [B, n_sym] (or a float32 view).  Returns uu_hat_packed, hhat, kstar, ret."""
@@ -263,6 +313,20 @@ class Link:
         self._check(self._lib.kml_histogram(self._h, snr_db, seed, frame_begin, frames, _ptr(met, C.c_float),
                                             _ptr(cnt, C.c_uint64)), "kml_histogram")
         return met, cnt
+
+    def histogram_rx(self, y: np.ndarray, var: float, u_packed: np.ndarray):
+        """KmCodec::GetHistogramData + CntErr on given frames: metrics[B,4], kstar, uu_hat_packed (what CntErr saw), counters."""
+        y, yf = self._y(y)
+        B = y.shape[0]
+        u = np.ascontiguousarray(u_packed, np.uint32).reshape(B, self.k_words)
+        met = np.empty((B, 4), np.float32)
+        kstar = np.empty(B, np.int32)
+        uh = np.empty((B, self.k_words), np.uint32)
+        cnt = np.zeros(4, np.uint64)
+        self._check(self._lib.kml_histogram_rx(self._h, B, _ptr(yf, C.c_float), var, _ptr(u, C.c_uint32), _ptr(met, C.c_float),
+                                               _ptr(kstar, C.c_int32), _ptr(uh, C.c_uint32), _ptr(cnt, C.c_uint64)),
+                    "kml_histogram_rx")
+        return met, kstar, uh, cnt
 
     # ---- device-pointer variants (pointers as ints, stream as int)
     def generate_dev(self, B, snr_db, seed, frame0, u_packed_ptr, h_ptr, y_ptr, stream=0):

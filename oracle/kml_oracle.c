@@ -528,7 +528,8 @@ int kmo_kmeans(const double *yy, int n, const double *cons, int q, int max_iter,
 
 /* ------------------------------------------------------------------------------------------------ frame */
 void kmo_receive(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, const double *yy, const double *true_h,
-                 double var, kmo_frame_out *out, double *clusters, double *p0, int *cc_hat, int *uu_hat) {
+                 double var, kmo_frame_out *out, double *clusters, double *p0, int *cc_hat, int *uu_hat,
+                 double *soft_state) {
   const int n_sym = c->n_tx / m->bits;
   double complex hh[4];
   int n_hat;
@@ -536,8 +537,11 @@ void kmo_receive(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, const
   double *pp = p0 ? p0 : malloc(sizeof(double) * c->n_tx);
   int *cch = cc_hat ? cc_hat : malloc(sizeof(int) * c->n);
   int *rr = malloc(sizeof(int) * c->n_tx);
-  double *soft = malloc(sizeof(double) * c->m);
-  for (int r = 0; r < c->m; r++) soft[r] = 1.0;
+  /* syndrom_soft_ is a MEMBER of the codec (binaryldpccodec.h:50): it survives from one Decoder call to the next and is
+   * only overwritten by a check-node phase (binaryldpccodec.cc:274).  soft_state is that member; without one the frame
+   * starts from all ones (the reference's array starts uninitialised, binaryldpccodec.cc:88). */
+  double *soft = soft_state ? soft_state : malloc(sizeof(double) * c->m);
+  if (!soft_state) for (int r = 0; r < c->m; r++) soft[r] = 1.0;
   out->hhat[0] = out->hhat[1] = 0;
   for (int k = 0; k < 4; k++) out->metric[k] = 0;
   if (o->known_h) { /* simulator.cc:132-133 */
@@ -573,17 +577,22 @@ void kmo_receive(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, const
     for (int k = 1; k < 4; k++) if (out->metric[k] < out->metric[kstar]) kstar = k; /* first argmin */
   }
   out->kstar = kstar;
-  kmo_demap(m, yy, n_sym, creal(hh[kstar]), cimag(hh[kstar]), var, pp);
-  out->ret = kmo_decode(c, pp, o->max_iter, o->max_iter, uu_hat, cch, soft);
+  if (o->histogram) { /* simulator.cc:154-162: the metrics are the product; nothing is decoded after them */
+    out->ret = 0;
+    if (!(n_hat > 1 && (o->metric_type || o->is_5g))) for (int t = 0; t < c->k; t++) uu_hat[t] = 0;
+  } else {
+    kmo_demap(m, yy, n_sym, creal(hh[kstar]), cimag(hh[kstar]), var, pp);
+    out->ret = kmo_decode(c, pp, o->max_iter, o->max_iter, uu_hat, cch, soft);
+  }
   if (!clusters) free(cl);
   if (!p0) free(pp);
   if (!cc_hat) free(cch);
   free(rr);
-  free(soft);
+  if (!soft_state) free(soft);
 }
 
 void kmo_frame(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, kmo_lcg *g, double snr_db, kmo_frame_out *out,
-               int *uu, int *cc, double *yy, double *clusters, double *p0, int *cc_hat, int *uu_hat) {
+               int *uu, int *cc, double *yy, double *clusters, double *p0, int *cc_hat, int *uu_hat, double *soft_state) {
   const int n_sym = c->n_tx / m->bits;
   const double var = pow(10.0, -0.1 * snr_db), sigma = sqrt(var); /* simulator.cc:74-77 */
   int *u = uu ? uu : malloc(sizeof(int) * c->k);
@@ -599,7 +608,7 @@ void kmo_frame(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, kmo_lcg
   out->h[1] = hn[1] * sqrt(0.5);
   kmo_map(m, cw, n_sym, xx);
   kmo_channel(g, xx, n_sym, out->h[0], out->h[1], sigma, y);
-  kmo_receive(c, m, o, y, out->h, var, out, clusters, p0, cc_hat, uh);
+  kmo_receive(c, m, o, y, out->h, var, out, clusters, p0, cc_hat, uh, soft_state);
   int ne = 0;
   for (int t = 0; t < c->k; t++) ne += (u[t] != uh[t]);                     /* sourcesink.cc:29-47 */
   out->nerr = ne;
@@ -620,15 +629,18 @@ static void *run_thread(void *p) {
   run_arg *a = p;
   kmo_lcg g;
   kmo_lcg_seed(&g, a->seed);
+  double *soft = malloc(sizeof(double) * a->c->m); /* this worker's codec copy (simulator.cc:93-97) */
+  for (int r = 0; r < a->c->m; r++) soft[r] = 1.0;
   for (long f = 0; f < a->frames; f++) {
     kmo_frame_out fo;
-    kmo_frame(a->c, a->m, a->o, &g, a->snr, &fo, 0, 0, 0, 0, 0, 0, 0);
+    kmo_frame(a->c, a->m, a->o, &g, a->snr, &fo, 0, 0, 0, 0, 0, 0, 0, soft);
     a->cnt[0] += 1;
     a->cnt[1] += (fo.nerr > 0);
     a->cnt[2] += (uint64_t)a->c->k;
     a->cnt[3] += (uint64_t)fo.nerr;
     a->iters += fo.ret > a->o->max_iter ? a->o->max_iter : fo.ret;
   }
+  free(soft);
   return NULL;
 }
 
@@ -656,7 +668,7 @@ int64_t kmo_run(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double
 
 typedef struct {
   const kmo_code *c; const kmo_modem *m; const kmo_opts *o;
-  double snr; long frame0, frames; int tid, threads;
+  double snr; long frame0, frames; int tid, threads; long chain_block;
   double *yy, *h, *hhat; int32_t *kstar, *ret, *nerr; uint8_t *converged, *uu, *uu_hat;
 } bulk_arg;
 
@@ -665,11 +677,17 @@ static void *bulk_thread(void *p) {
   const int n_sym = a->c->n_tx / a->m->bits, k = a->c->k;
   int *u = malloc(sizeof(int) * k), *uh = malloc(sizeof(int) * k), *cch = malloc(sizeof(int) * a->c->n);
   double *y = malloc(sizeof(double) * 2 * n_sym);
-  for (long f = a->tid; f < a->frames; f += a->threads) {
+  double *soft = malloc(sizeof(double) * a->c->m);
+  const long blk = a->chain_block > 0 ? a->chain_block : 1;
+  /* blocks of `blk` consecutive frames go through ONE codec state in frame order (a block = one reference worker task,
+   * simulator.cc:86-97); blocks are dealt out to the threads, so the result does not depend on the thread count */
+  for (long b0 = (long)a->tid * blk; b0 < a->frames; b0 += (long)a->threads * blk)
+  for (long f = b0; f < a->frames && f < b0 + blk; f++) {
+    if (f == b0) for (int r = 0; r < a->c->m; r++) soft[r] = 1.0;
     kmo_lcg g;
     kmo_lcg_seed(&g, (17 + 1000003L * (f + a->frame0)) % (LCG_M - 1) + 1);
     kmo_frame_out fo;
-    kmo_frame(a->c, a->m, a->o, &g, a->snr, &fo, u, 0, y, 0, 0, cch, uh);
+    kmo_frame(a->c, a->m, a->o, &g, a->snr, &fo, u, 0, y, 0, 0, cch, uh, soft);
     if (a->yy) memcpy(a->yy + (size_t)f * 2 * n_sym, y, sizeof(double) * 2 * n_sym);
     if (a->h) { a->h[2 * f] = fo.h[0]; a->h[2 * f + 1] = fo.h[1]; }
     if (a->hhat) { a->hhat[2 * f] = fo.hhat[0]; a->hhat[2 * f + 1] = fo.hhat[1]; }
@@ -680,18 +698,18 @@ static void *bulk_thread(void *p) {
     if (a->uu) for (int t = 0; t < k; t++) a->uu[(size_t)f * k + t] = (uint8_t)u[t];
     if (a->uu_hat) for (int t = 0; t < k; t++) a->uu_hat[(size_t)f * k + t] = (uint8_t)uh[t];
   }
-  free(u); free(uh); free(cch); free(y);
+  free(u); free(uh); free(cch); free(y); free(soft);
   return NULL;
 }
 
 void kmo_bulk(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double snr_db, long frame0, long frames, int threads,
-              double *yy, double *h, double *hhat, int32_t *kstar, int32_t *ret, int32_t *nerr, uint8_t *converged,
-              uint8_t *uu, uint8_t *uu_hat) {
+              long chain_block, double *yy, double *h, double *hhat, int32_t *kstar, int32_t *ret, int32_t *nerr,
+              uint8_t *converged, uint8_t *uu, uint8_t *uu_hat) {
   if (threads < 1) threads = 1;
   pthread_t *th = malloc(sizeof(pthread_t) * threads);
   bulk_arg *ar = calloc(threads, sizeof(bulk_arg));
   for (int t = 0; t < threads; t++) {
-    ar[t] = (bulk_arg){c, m, o, snr_db, frame0, frames, t, threads, yy, h, hhat, kstar, ret, nerr, converged, uu, uu_hat};
+    ar[t] = (bulk_arg){c, m, o, snr_db, frame0, frames, t, threads, chain_block, yy, h, hhat, kstar, ret, nerr, converged, uu, uu_hat};
     pthread_create(&th[t], NULL, bulk_thread, &ar[t]);
   }
   for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);

@@ -30,7 +30,7 @@ def build(force: bool = False) -> str:
 
 class _Opts(C.Structure):
     _fields_ = [("known_h", C.c_int), ("is_5g", C.c_int), ("metric_type", C.c_int), ("metric_iter", C.c_int),
-                ("max_iter", C.c_int), ("kmeans_iter", C.c_int)]
+                ("max_iter", C.c_int), ("kmeans_iter", C.c_int), ("histogram", C.c_int)]
 
 
 class _FrameOut(C.Structure):
@@ -199,11 +199,16 @@ class Link:
     """One (code, modem, options) triple — the oracle's view of Simulator + KmCodec."""
 
     def __init__(self, matrix: str, modem: str, *, is_5g=False, active=True, known_h=False, metric_type=False,
-                 metric_iter=5, max_iter=50, kmeans_iter=20):
+                 metric_iter=5, max_iter=50, kmeans_iter=20, histogram=False):
         self.code = Code(matrix, is_5g, active)
         self.modem = Modem(modem)
-        self.opts = _Opts(int(known_h), int(is_5g), int(metric_type), metric_iter, max_iter, kmeans_iter)
+        self.opts = _Opts(int(known_h), int(is_5g), int(metric_type), metric_iter, max_iter, kmeans_iter, int(histogram))
         self.n_sym = self.code.N_tx // self.modem.bits
+        # the codec's syndrom_soft_ member: survives from frame to frame (binaryldpccodec.cc:274 is its only writer)
+        self.soft_state = np.ones(self.code.M, np.float64)
+
+    def reset_soft_state(self):
+        self.soft_state[:] = 1.0
 
     def frame(self, lcg: Lcg, snr_db: float, full: bool = True) -> FrameResult:
         c, m = self.code, self.modem
@@ -216,7 +221,7 @@ class Link:
             u = cw = y = cl = p0 = cch = uh = None
         lib().kmo_frame(C.c_void_p(c._h), C.c_void_p(m._h), C.byref(self.opts), C.byref(lcg._g), C.c_double(snr_db),
                         C.byref(fo), _p(u, C.c_int), _p(cw, C.c_int), _p(y, C.c_double), _p(cl, C.c_double),
-                        _p(p0, C.c_double), _p(cch, C.c_int), _p(uh, C.c_int))
+                        _p(p0, C.c_double), _p(cch, C.c_int), _p(uh, C.c_int), _p(self.soft_state, C.c_double))
         return FrameResult(complex(*fo.h), complex(*fo.hhat), np.array(fo.metric), fo.kstar, fo.ret, fo.nerr,
                            u, cw, None if y is None else y.view(np.complex128),
                            None if cl is None else cl.view(np.complex128), p0, cch, uh)
@@ -230,12 +235,13 @@ class Link:
         cch = np.empty(c.N, np.int32); uh = np.empty(c.K, np.int32)
         lib().kmo_receive(C.c_void_p(c._h), C.c_void_p(m._h), C.byref(self.opts), _p(y.view(np.float64), C.c_double),
                           _p(th, C.c_double), C.c_double(var), C.byref(fo), _p(cl, C.c_double), _p(p0, C.c_double),
-                          _p(cch, C.c_int), _p(uh, C.c_int))
+                          _p(cch, C.c_int), _p(uh, C.c_int), _p(self.soft_state, C.c_double))
         return FrameResult(true_h, complex(*fo.hhat), np.array(fo.metric), fo.kstar, fo.ret, -1,
                            None, None, y, cl.view(np.complex128), p0, cch, uh)
 
-    def bulk(self, snr_db: float, frames: int, threads: int | None = None, frame0: int = 0) -> dict:
-        """`frames` independent reference frames (frame f has its own LCG), computed on `threads` host threads."""
+    def bulk(self, snr_db: float, frames: int, threads: int | None = None, frame0: int = 0, chain_block: int = 1) -> dict:
+        """`frames` reference frames (frame f has its own LCG), computed on `threads` host threads.  Blocks of
+        `chain_block` consecutive frames share one syndrom_soft_ state in frame order (soft metric only)."""
         c, m = self.code, self.modem
         threads = threads or (os.cpu_count() or 1)
         out = dict(y=np.empty((frames, self.n_sym, 2), np.float64), h=np.empty((frames, 2), np.float64),
@@ -243,7 +249,7 @@ class Link:
                    nerr=np.empty(frames, np.int32), converged=np.empty(frames, np.uint8),
                    u=np.empty((frames, c.K), np.uint8), uu_hat=np.empty((frames, c.K), np.uint8))
         lib().kmo_bulk(C.c_void_p(c._h), C.c_void_p(m._h), C.byref(self.opts), C.c_double(snr_db), C.c_long(frame0),
-                       C.c_long(frames), C.c_int(threads), _p(out["y"], C.c_double), _p(out["h"], C.c_double),
+                       C.c_long(frames), C.c_int(threads), C.c_long(chain_block), _p(out["y"], C.c_double), _p(out["h"], C.c_double),
                        _p(out["hhat"], C.c_double), _p(out["kstar"], C.c_int32), _p(out["ret"], C.c_int32),
                        _p(out["nerr"], C.c_int32), _p(out["converged"], C.c_uint8), _p(out["u"], C.c_uint8),
                        _p(out["uu_hat"], C.c_uint8))

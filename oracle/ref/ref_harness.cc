@@ -171,6 +171,7 @@ main(int argc, char **argv) {
   const double snr = a.d("snr", 10.0);
   const long frames = a.i("frames", 8);
   const long skip = a.i("skip", 0);
+  const bool hist = a.i("hist", 0) != 0;  // [histogram] enable = true: KmCodec::GetHistogramData instead of Decoder
   std::string outdir = a.s("out", "");
   if (!outdir.empty() && outdir[0] != '/') {
     char cwd[4096];
@@ -271,6 +272,12 @@ main(int argc, char **argv) {
   long iters_total = 0;
   long mismatch_kmcodec = 0;
 
+  // syndrom_soft_ is `new double[...]`, never initialised (binaryldpccodec.cc:88), and only the check-node phase writes it
+  // (binaryldpccodec.cc:274): the soft metric of a decode that leaves at iteration 0 reads whatever the previous Decoder
+  // call left — for the very first call that is heap garbage.  Give it a defined start (all ones) through the public
+  // accessor; from then on the reference's own stale-value chain runs unchanged.
+  for (int j = 0; j < codec->num_row(); j++) codec->syndrom_soft()[j] = 1.0;
+
   for (long f = 0; f < skip + frames; f++) {
     const bool rec = dump && f >= skip;
     double t0 = now();
@@ -297,6 +304,28 @@ main(int argc, char **argv) {
       for (size_t j = 0; j < 4; j++) h_hats.push_back(h_hat * exp(cplx(0, (lab::kPi / 2) * j)));
     }
     double t3 = now();
+    if (hist) {  // simulator.cc:154-167 through the reference's own KmCodec::GetHistogramData (kmcodec.cc:74-79)
+      if (f == 0) std::fill(uu_hat.begin(), uu_hat.end(), 0);  // cdata.uu_hat_ is never initialised (simulator.h:30-37)
+      std::vector<double> met = kmcodec.GetHistogramData(mls, h_hats, uu_hat.data());
+      const int lo = (int)(std::min_element(met.begin(), met.end()) - met.begin());
+      double line[4];
+      for (int j = 0; j < 4; j++) line[j] = met[(lo + j) % 4];  // the rotated line of histogram_<snr>.txt (:157-160)
+      ssink.CntErr(uu.data(), uu_hat.data(), k, 1);
+      if (rec) {
+        put(out.get("h.f64"), (const double *)&true_h, 2);
+        put(out.get("hhat.f64"), (const double *)&h_hat, 2);
+        put(out.get("metric.f64"), met.data(), 4);
+        put(out.get("hist_line.f64"), line, 4);
+        int32_t ks = lo;
+        put(out.get("kstar.i32"), &ks, 1);
+        put_bits(out.get("uu_hat.i8"), uu_hat.data(), k);
+        int nerr = 0;
+        for (int t = 0; t < k; t++) nerr += (uu[t] != uu_hat[t]);
+        int32_t ne = nerr;
+        put(out.get("nerr.i32"), &ne, 1);
+      }
+      continue;
+    }
     // ---- mirror of KmCodec::Decoder / GetMetrics / Metric / GetParityCheck (kmcodec.cc:54-163)
     double metrics[4] = {0, 0, 0, 0};
     int kstar = 0;

@@ -39,8 +39,19 @@ CASES = [
     ("5g_16qam_gray_10db", G5, "4bit_16QAM_Gray.txt", 10.0, 100, 4, {"g5": 1, "metric_iter": 5}),
     ("peg8064_64qam_20db", PEG8, "6bits_64QAM_Gray.txt", 20.0, 12, 2, {}),
     ("peg2304_4psk_soft_6db", PEG, "2bits_4PSK.txt", 6.0, 40, 2, {"metric_type": 1, "metric_iter": 5}),
+    # soft metric where most correct candidates leave at iteration 0: their metric is the STALE syndrom_soft_ of the
+    # previous Decoder call (binaryldpccodec.cc:231-232,274), carried from candidate to candidate and frame to frame
+    ("peg2304_4psk_soft_18db", PEG, "2bits_4PSK.txt", 18.0, 120, 2, {"metric_type": 1, "metric_iter": 5}),
     ("peg2304_4psk_inactive_6db", PEG, "2bits_4PSK.txt", 6.0, 40, 2, {"active": 0}),
     ("peg2304_16qam_gray_i5_15db", PEG, "4bit_16QAM_Gray.txt", 15.0, 100, 2, {"max_iter": 5}),
+]
+
+
+# histogram mode ([histogram] enable = true) through the reference's own KmCodec::GetHistogramData: same LCG frames as
+# the case of the same name without the prefix; name, matrix, modem, snr, frames, extra
+HIST_CASES = [
+    ("hist_peg2304_4psk_6db", PEG, "2bits_4PSK.txt", 6.0, 100, {}),
+    ("hist_5g_16qam_gray_10db", G5, "4bit_16QAM_Gray.txt", 10.0, 60, {"g5": 1, "metric_iter": 5}),
 ]
 
 
@@ -108,6 +119,27 @@ def run_case(name, matrix, modem, snr, frames, full, extra):
               f"-> {os.path.getsize(os.path.join(HERE, name + '.npz')) / 1024:.0f} KiB")
 
 
+def run_hist_case(name, matrix, modem, snr, frames, extra):
+    with tempfile.TemporaryDirectory() as d:
+        args = dict(cfgdir=CFG, matrix=matrix, modem=modem, snr=snr, frames=frames, out=d, g5=0, active=1,
+                    known_h=0, metric_type=0, metric_iter=5, max_iter=50, hist=1)
+        args.update(extra)
+        out = subprocess.check_output([HARNESS, "dump"] + [f"{k}={v}" for k, v in args.items()], text=True)
+        summ = json.loads(out.strip().splitlines()[-1])
+        n_tx, n_graph, k, m, q, n_sym, two_z, _ = rd(d, "run_meta.i32", np.int32)
+        F = frames
+        fixture = dict(
+            params=json.dumps(dict(name=name, matrix=matrix, modem=modem, snr=snr, frames=F, histogram=1, **{
+                kk: args[kk] for kk in ("g5", "active", "known_h", "metric_type", "metric_iter", "max_iter")},
+                n_tx=int(n_tx), k=int(k), tot_blk=summ["tot_blk"], err_blk=summ["err_blk"], ber=summ["ber"], fer=summ["fer"])),
+            h=rd(d, "h.f64", np.float64, (F, 2)), hhat=rd(d, "hhat.f64", np.float64, (F, 2)),
+            metric=rd(d, "metric.f64", np.float64, (F, 4)), hist_line=rd(d, "hist_line.f64", np.float64, (F, 4)),
+            kstar=rd(d, "kstar.i32", np.int32), nerr=rd(d, "nerr.i32", np.int32),
+            uu_hat_packed=pack(rd(d, "uu_hat.i8", np.int8, (F, k))))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **fixture)
+        print(f"{name}: histogram mode, FER {summ['fer']:.3f} BER {summ['ber']:.4f}")
+
+
 if __name__ == "__main__":
     if not os.path.exists(HARNESS):
         sys.exit("build oracle/_ref first: make -C oracle ref   (needs /root/reference)")
@@ -116,3 +148,7 @@ if __name__ == "__main__":
         if only and case[0] not in only:
             continue
         run_case(*case)
+    for case in HIST_CASES:
+        if only and case[0] not in only:
+            continue
+        run_hist_case(*case)
