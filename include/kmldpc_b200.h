@@ -27,6 +27,7 @@ typedef enum {
   KML_ERR_IO = -2,      /* file could not be opened or parsed */
   KML_ERR_CUDA = -3,    /* CUDA runtime error or no usable device */
   KML_ERR_STATE = -4,   /* call order / capacity problem */
+  KML_ERR_NCCL = -5,    /* NCCL could not be loaded / initialised, or a collective failed */
 } kml_status;
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -241,7 +242,9 @@ typedef struct kml_sweep_cfg {
   uint64_t max_err_blk, max_num_blk;                 /* [range] maximum_error_number / maximum_block_number */
   int32_t known_h, is_5g, metric_type, metric_iter;  /* [decoder] / [xcodec] */
   int32_t max_iter, encoder_active;                  /* [ldpc] */
-  int32_t histogram_enable, reserved;                /* [histogram] enable: writes histogram_<snr>.txt */
+  int32_t histogram_enable;                          /* [histogram] enable: writes histogram_<snr>.txt */
+  int32_t reduce_on_host;                            /* [gpu] reduce = "host": sum the per-GPU counters on the host
+                                                        instead of one ncclAllReduce per point (default 0 = NCCL) */
   char matrix_file[512];                             /* [ldpc] matrix_file */
   char modem_file[512];                              /* [modem] modem_file */
   /* optional [gpu] table (ignored by the reference binary) */
@@ -253,12 +256,25 @@ typedef struct kml_sweep_cfg {
 int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg);
 /* Runs the sweep on n_gpus devices (one host thread per GPU, frame ranges of every SNR point sharded; with n_gpus > 1 the
  * per-GPU counters of a point are summed by one ncclAllReduce of 4 x uint64 over NVLink — libnccl.so.2 is opened at run
- * time, a process without it sums on the host and says so on stderr) and fills ber[n_points], fer[n_points],
- * counters[n_points][4].  data_dir is prepended to relative file names.
+ * time; if it cannot be had the call FAILS with KML_ERR_NCCL unless cfg->reduce_on_host asks for the host sum) and fills
+ * ber[n_points], fer[n_points], counters[n_points][4].  data_dir is prepended to relative file names.
+ * maximum_error_number = 0 runs no frame at all, like the reference (simulator.cc:117: err_blk >= 0 holds at once).
  * log_cb (may be NULL) receives the reference-format lines ("SNR = … Total blk = …", "BER Result", …). */
 int kml_sweep_points(const kml_sweep_cfg *cfg);
 int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
                   void (*log_cb)(const char *line, void *user), void *user);
+
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU counter reduction (SURVEY 8(b) "comm_init / reduce_counters"; the reference sums under a mutex in
+ * threadsafe_sourcesink.cc).  One process, GPUs 0 .. n_gpus-1, ncclCommInitAll; kml_sweep_run uses the same code.
+ * per_gpu[n_gpus][count] uint64 host words are copied to the GPUs, summed by ONE ncclAllReduce over NVLink and the
+ * result read back from GPU 0 into total[count] (count <= 1024).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct kml_comm kml_comm;
+int kml_comm_init(int n_gpus, kml_comm **out);
+int kml_reduce_counters(kml_comm *comm, const uint64_t *per_gpu, int count, uint64_t *total);
+void kml_comm_destroy(kml_comm *comm);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,7 @@ class KmlSweepCfg(C.Structure):
                 ("max_err_blk", C.c_uint64), ("max_num_blk", C.c_uint64),
                 ("known_h", C.c_int32), ("is_5g", C.c_int32), ("metric_type", C.c_int32), ("metric_iter", C.c_int32),
                 ("max_iter", C.c_int32), ("encoder_active", C.c_int32),
-                ("histogram_enable", C.c_int32), ("reserved", C.c_int32),
+                ("histogram_enable", C.c_int32), ("reduce_on_host", C.c_int32),
                 ("matrix_file", C.c_char * 512), ("modem_file", C.c_char * 512),
                 ("seed", C.c_uint64),
                 ("n_gpus", C.c_int32), ("max_batch", C.c_int32), ("early_exit", C.c_int32), ("algorithm", C.c_int32)]
@@ -85,6 +85,9 @@ SYMBOLS = {
     "kml_demap_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "kml_decode_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kml_count_errors_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kml_comm_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "kml_reduce_counters": (C.c_int, [C.c_void_p, c_u64p, C.c_int, c_u64p]),
+    "kml_comm_destroy": (None, [C.c_void_p]),
     "kml_sweep_cfg_load": (C.c_int, [C.c_char_p, C.POINTER(KmlSweepCfg)]),
     "kml_sweep_points": (C.c_int, [C.POINTER(KmlSweepCfg)]),
     "kml_sweep_run": (C.c_int, [C.POINTER(KmlSweepCfg), C.c_char_p, c_f64p, c_f64p, c_u64p, LOG_CB, C.c_void_p]),

@@ -94,7 +94,9 @@ __device__ __forceinline__ float c2v_ratio(float s, uint32_t x, uint32_t w) {
 // hard bits have odd parity, 1 - s otherwise — taken as log1p(-s) so that rows the decoder is sure of still contribute
 // their ~ -s (the reference sums them in fp64)
 __device__ __forceinline__ float soft_log(uint32_t odd, float s) {
-  if (odd) return __logf(s);
+  // (graphs with variable degree above 3 can still underflow s to 0 in fp32 where the reference's fp64 holds 1e-40…:
+  //  such a row counts as ln(1.2e-38) = -87.3 instead of -inf)
+  if (odd) return __logf(fmaxf(s, 1.18e-38f));
   return s < 0.01f ? -s * fmaf(s, fmaf(s, 0.33333334f, 0.5f), 1.0f) : __logf(1.0f - s);
 }
 
@@ -811,57 +813,67 @@ __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p
   }
 }
 
-// Resolved once per context (dec_prepare): the A/B knobs below are read when a context is created, never on the launch
-// path.  `threads` = the CTA size the tables were built for.
+// Resolved once per context (dec_prepare), never on the launch path.  `threads` = the CTA size the tables were built
+// for.  The shipped library picks between kernels that all reproduce the reference (run-time knobs KML_DEC_PLANAR,
+// KML_DEC_NO_QC, KML_DEC_T8064 choose the fallback layouts / tilings and announce themselves on stderr, kml_internal.h);
+// the A/B and timing-ablation variants exist only in a -DKML_TUNING build.
 dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan, int threads) {
   if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;  // (fp16 x 2 frames exists for regular codes only)
   if (alg != 0) return minsum_kernel_of(k, alg);
   if (qc_plan == 1 && !soft) {
-    const char *e = getenv("KML_DEC_QC_MINB");  // A/B knob
-    return (e && atoi(e) == 2) ? bp_qc_kernel<QcPlanBg2R12, 2, 0> : bp_qc_kernel<QcPlanBg2R12, 3, 0>;
+#ifdef KML_TUNING
+    const char *e = tuning_knob("KML_DEC_QC_MINB");
+    if (e && atoi(e) == 2) return bp_qc_kernel<QcPlanBg2R12, 2, 0>;
+#endif
+    return bp_qc_kernel<QcPlanBg2R12, 3, 0>;
   }
-  if (soft && k == DEC_REG_6_3)
-    return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 2, true, true> : bp_regular_kernel<6, 3, 384, 3, true, 2, false, true>;
-  if (soft && k == DEC_REG_12_6)
-    return !rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 2, false, true>
-                     : threads == 1024 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, true, 8064>
-                                                      : bp_regular_kernel<12, 6, 672, 1, true, 2, true, true>;
+  // Soft-syndrome output of the (3,6)-regular codes: the scalar (PACK = false) planar kernel.  Its variable nodes form
+  // the three extrinsic ratios directly (each a product of the channel ratio and two clipped messages, within 1e+-36),
+  // so the small probabilities never leave the fp32 range — the packed kernels go through post = ch x0 x1 x2 (up to
+  // 1e+-48), whose overflow is harmless for the messages (everything below 1e-12 is clipped alike) but would turn
+  // ln(syndrom_soft) of a confidently violated check into -inf where the reference sums a finite ~ -83.
+  if (soft && k == DEC_REG_6_3) return bp_regular_kernel<6, 3, 384, 3, false, 2, false, true>;
+  if (soft && k == DEC_REG_12_6) return bp_regular_kernel<12, 6, 672, 1, false, 2, false, true>;
   switch (k) {
     case DEC_REG_6_3: {
-      const char *e = getenv("KML_DEC_MINB");  // tuning knob: CTAs per SM the register allocation targets
+#ifdef KML_TUNING
+      const char *e = tuning_knob("KML_DEC_MINB");   // CTAs per SM the register allocation targets
       const int b = e ? atoi(e) : 3;
-      const char *re = getenv("KML_DEC_RATIO");  // A/B knob: how check outputs with hard bit 1 are inverted
+      const char *re = tuning_knob("KML_DEC_RATIO");  // how check outputs with hard bit 1 are inverted
       const int r = re ? atoi(re) : 1;
       if (!rowmajor) {
-        const char *pe = getenv("KML_DEC_NOPACK");  // A/B knob: scalar fp32 instead of FMUL2/FADD2/FFMA2
+        const char *pe = tuning_knob("KML_DEC_NOPACK");  // scalar fp32 instead of FMUL2/FADD2/FFMA2
         if (pe && atoi(pe)) return bp_regular_kernel<6, 3, 384, 3, false>;
         if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0>;
-        if (r == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1>;
         if (b == 2) return bp_regular_kernel<6, 3, 384, 2>;
         if (b == 4) return bp_regular_kernel<6, 3, 384, 4>;
-        return bp_regular_kernel<6, 3, 384, 3>;
+        if (r == 2) return bp_regular_kernel<6, 3, 384, 3>;
+      } else {
+        if (const char *de = tuning_knob("KML_DEC_DIAG")) {  // timing ablations, WRONG results (see the kernel's header)
+          const int dg = atoi(de);
+          if (dg == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 1>;
+          if (dg == 2) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 2>;
+          if (dg == 3) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 3>;
+        }
+        if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0, true>;
+        if (r == 3) return bp_regular_kernel<6, 3, 384, 3, true, 3, true>;
+        if (b == 2) return bp_regular_kernel<6, 3, 384, 2, true, 2, true>;
+        if (b == 4) return bp_regular_kernel<6, 3, 384, 4, true, 2, true>;
+        if (r == 2) return bp_regular_kernel<6, 3, 384, 3, true, 2, true>;
       }
-      if (const char *de = getenv("KML_DEC_DIAG")) {  // timing ablations, wrong results (see the kernel's header)
-        const int dg = atoi(de);
-        if (dg == 1) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 1>;
-        if (dg == 2) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 2>;
-        if (dg == 3) return bp_regular_kernel<6, 3, 384, 3, true, 1, true, false, 2304, 3>;
-      }
-      if (r == 0) return bp_regular_kernel<6, 3, 384, 3, true, 0, true>;
-      if (r == 3) return bp_regular_kernel<6, 3, 384, 3, true, 3, true>;
-      if (b == 2) return bp_regular_kernel<6, 3, 384, 2, true, 2, true>;
-      if (b == 4) return bp_regular_kernel<6, 3, 384, 4, true, 2, true>;
-      if (r == 2) return bp_regular_kernel<6, 3, 384, 3, true, 2, true>;
-      return bp_regular_kernel<6, 3, 384, 3, true, 1, true>;
+#endif
+      return rowmajor ? bp_regular_kernel<6, 3, 384, 3, true, 1, true> : bp_regular_kernel<6, 3, 384, 3, true, 1>;
     }
     case DEC_REG_12_6: {
-      const char *re = getenv("KML_DEC_RATIO");
-      const int r8 = re ? atoi(re) : 1;
-      if (rowmajor && threads == 1024)
-        return r8 == 2 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, false, 8064>
-                       : bp_regular_kernel<8, 4, 1024, 1, true, 1, true, false, 8064>;
-      return rowmajor ? (r8 == 2 ? bp_regular_kernel<12, 6, 672, 1, true, 2, true> : bp_regular_kernel<12, 6, 672, 1, true, 1, true>)
-                      : bp_regular_kernel<12, 6, 672, 1>;
+#ifdef KML_TUNING
+      const char *re = tuning_knob("KML_DEC_RATIO");
+      if (re && atoi(re) == 2)
+        return rowmajor && threads == 1024 ? bp_regular_kernel<8, 4, 1024, 1, true, 2, true, false, 8064>
+               : rowmajor                  ? bp_regular_kernel<12, 6, 672, 1, true, 2, true>
+                                           : bp_regular_kernel<12, 6, 672, 1>;
+#endif
+      if (rowmajor && threads == 1024) return bp_regular_kernel<8, 4, 1024, 1, true, 1, true, false, 8064>;
+      return rowmajor ? bp_regular_kernel<12, 6, 672, 1, true, 1, true> : bp_regular_kernel<12, 6, 672, 1, true, 1>;
     }
     case DEC_GEN_4_8: return soft ? bp_generic_kernel<4, 8, true> : bp_generic_kernel<4, 8, false>;
     case DEC_GEN_9_10: return soft ? bp_generic_kernel<9, 10, true> : bp_generic_kernel<9, 10, false>;
@@ -878,7 +890,7 @@ int dec_generic_max_threads() { return kGenericThreads; }
 // quasi-cyclic plan?  Returns the plan id (1 = QcPlanBg2R12) or 0.
 int dec_match_qc_plan(int n, int m_pad, const uint8_t *vdeg, const uint8_t *cndeg, int dv_max, int row_stride) {
   using P = QcPlanBg2R12;
-  const char *e = getenv("KML_DEC_NO_QC");  // A/B knob: run the generic kernel instead
+  const char *e = knob("KML_DEC_NO_QC");  // run the run-time-graph kernel instead (shipped fallback; announced on stderr)
   if (e && atoi(e)) return 0;
   if (n != 22 * P::Z || m_pad != 12 * P::Z || dv_max != P::DVM || row_stride != P::RS) return 0;
   int seen_v[22] = {0}, seen_c[12] = {0};
@@ -908,7 +920,7 @@ int dec_regular_threads(DecKernelKind k) {
     // 1024 threads x (8 variables, 4 checks; the last round is empty for the top 128 threads): 32 warps on the SM's
     // single CTA instead of 21; KML_DEC_T8064=672 is the A/B knob for the exact 672 x (12, 6) tiling, which the planar
     // layout also uses
-    const char *e = getenv("KML_DEC_T8064");
+    const char *e = knob("KML_DEC_T8064");
     return (!(e && atoi(e) == 672) && dec_wants_rowmajor(k, 0)) ? 1024 : 672;
   }
   return 384;  // (576 threads x (4 variables, 2 checks), 2 CTAs per SM measured 7 % slower)
@@ -917,7 +929,7 @@ int dec_regular_threads(DecKernelKind k) {
 bool dec_wants_rowmajor(DecKernelKind k, int alg) {
   if (alg != 0) return false;
   if (k != DEC_REG_6_3 && k != DEC_REG_12_6) return true;  // generic sum-product kernel: always its own row-major tables
-  const char *e = getenv("KML_DEC_PLANAR");  // A/B knob: the planar layout for the regular sum-product kernels too
+  const char *e = knob("KML_DEC_PLANAR");  // the planar layout for the regular sum-product kernels too (shipped fallback)
   return !(e && atoi(e));
 }
 
@@ -927,18 +939,13 @@ bool dec_has_synd_output(const DecLaunch &l, bool soft) {
 }
 
 cudaError_t dec_prepare(DecLaunch &l) {
-  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, false, l.qc_plan, l.threads);
+  // l.soft: the launch record of the kernel that also produces DecParams::out_soft (sum-product only; a plan kernel hands
+  // over to the run-time-graph kernel)
+  dec_kernel_t k = kernel_of(l.kind, l.alg, l.rowmajor, l.soft != 0, l.soft ? 0 : l.qc_plan, l.threads);
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
   if (e != cudaSuccess) return e;
-  // the soft-syndrome twin (sum-product only; a plan kernel hands over to the run-time-graph kernel), same launch shape
-  dec_kernel_t ks = l.alg == 0 ? kernel_of(l.kind, l.alg, l.rowmajor, true, 0, l.threads) : k;
   l.fn = k;
-  l.fn_soft = ks;
-  if (ks != k) {
-    e = cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem_bytes);
-    if (e != cudaSuccess) return e;
-  }
   int n = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, l.threads, l.smem_bytes);
   if (e != cudaSuccess) return e;
@@ -954,7 +961,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
-  (p.out_soft ? l.fn_soft : l.fn)<<<grid, l.threads, l.smem_bytes, s>>>(p);
+  l.fn<<<grid, l.threads, l.smem_bytes, s>>>(p);
   return cudaGetLastError();
 }
 

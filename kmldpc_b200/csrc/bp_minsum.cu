@@ -270,9 +270,13 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
 
 dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg) {
   if (alg == 2) {  // fp16 x 2 frames per word: regular codes only, otherwise the fp32 min-sum kernels below
-    const char *e = getenv("KML_DEC_MINB");
+#ifdef KML_TUNING
+    const char *e = tuning_knob("KML_DEC_MINB");
     const int b = e ? atoi(e) : 3;
-    if (k == DEC_REG_6_3) return b == 4 ? ms2_regular_kernel<6, 3, 384, 4> : (b == 2 ? ms2_regular_kernel<6, 3, 384, 2> : ms2_regular_kernel<6, 3, 384, 3>);
+    if (k == DEC_REG_6_3 && b == 4) return ms2_regular_kernel<6, 3, 384, 4>;
+    if (k == DEC_REG_6_3 && b == 2) return ms2_regular_kernel<6, 3, 384, 2>;
+#endif
+    if (k == DEC_REG_6_3) return ms2_regular_kernel<6, 3, 384, 3>;
     if (k == DEC_REG_12_6) return ms2_regular_kernel<12, 6, 672, 1>;
   }
   switch (k) {

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -184,6 +186,19 @@ extern "C" int kml_code_load(const char *h_file, int is_5g, int encoder_active, 
   *out = &o->pub;  // pub is the first member: the owner is recovered by a cast in kml_code_free
   return KML_OK;
 }
+
+namespace kml {
+const char *knob(const char *name) {
+  const char *v = getenv(name);
+  if (!v || !*v) return nullptr;
+  static std::mutex mu;
+  static std::set<std::string> said;
+  std::lock_guard<std::mutex> lk(mu);
+  if (said.insert(std::string(name) + "=" + v).second)
+    fprintf(stderr, "kmldpc_b200: environment knob %s=%s is active (selects a non-default kernel variant)\n", name, v);
+  return v;
+}
+}  // namespace kml
 
 extern "C" void kml_code_free(kml_code *code) {
   if (code) delete reinterpret_cast<CodeOwner *>(code);

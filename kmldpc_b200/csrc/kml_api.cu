@@ -72,6 +72,7 @@ struct kml_ctx {
   DevBuf<uint8_t> vn_deg, cn_deg, cn_deg_rm;
   DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
   DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
+  DecLaunch dl_soft{};          // sum-product kernel that also produces the soft-syndrome sums (metric_type = true)
   float alpha = 0.8f;
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
@@ -371,13 +372,25 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     c->dl_alg[alg] = dl;
   }
   c->dl = c->dl_alg[c->opts.algorithm];
+  {  // soft-syndrome twin: regular codes → scalar planar kernel on the planar tables; other graphs → run-time-graph kernel
+    DecLaunch ds = c->dl_alg[0];
+    ds.soft = 1;
+    ds.qc_plan = 0;
+    if (regular_kind) {
+      ds.rowmajor = 0;
+      ds.threads = dl.kind == DEC_REG_12_6 ? 672 : 384;
+      ds.smem_bytes = planar_smem;
+    }
+    KML_CUDA(c, dec_prepare(ds));
+    c->dl_soft = ds;
+  }
   return KML_OK;
 }
 
 DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t *sel, int n_cand, int in_is_lr, int iters,
                      uint32_t *out_bits, int32_t *out_ret, double *out_soft) {
   DecParams p{};
-  p.t = c->dl.rowmajor ? c->dt_rm : c->dt;
+  p.t = (out_soft ? c->dl_soft.rowmajor : c->dl.rowmajor) ? c->dt_rm : c->dt;
   p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
   p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
   p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
@@ -394,7 +407,7 @@ int metric_decodes(kml_ctx *c, Lane &l, cudaStream_t s, int B) {
   DecParams p = dec_params(c, l, 4 * B, l.lr.p, nullptr, 1, 1, c->opts.metric_iter, l.cc_hat_packed.p, l.mret.p, soft ? l.soft.p : nullptr);
   p.early_exit = 1;
   if (!soft && dec_has_synd_output(c->dl, false)) p.out_synd = l.metric.p;  // syndrome weight straight from the decoder
-  KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+  KML_LAUNCH(c, dec_launch(soft ? c->dl_soft : c->dl, p, c->num_sms, s));
   if (soft) return KML_OK;
   if (!p.out_synd)
     KML_LAUNCH(c, launch_syndrome_weight(4 * B, l.cc_hat_packed.p, c->words_n, c->M, c->row_ptr.p, c->col_idx.p, l.metric.p, s));
@@ -424,7 +437,7 @@ int soft_chain(kml_ctx *c, Lane &l, cudaStream_t s, int B, bool final_decode) {
     if (queued > 0) {  // the frames chosen in this round: final Decoder(max_iter) on the chosen candidate (kmcodec.cc:70-71)
       DecParams p = dec_params(c, l, queued, l.lr.p, l.kstar.p, 4, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, l.fsoft.p);
       p.frame_idx = l.chain_queue.p;
-      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      KML_LAUNCH(c, dec_launch(c->dl_soft, p, c->num_sms, s));
     }
     if (left == 0) return KML_OK;
     if (queued == 0) break;  // no progress: cannot happen (frame 0 never waits)
@@ -466,7 +479,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
       KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
       return KML_OK;
     }
-    KML_RC(metric_decodes(c, l, s, B));  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
+    if (decode_metric) KML_RC(metric_decodes(c, l, s, B));  // Metric(): Decoder(metric_iter) on every candidate (kmcodec.cc:146-160)
     if (c->opts.metric_type) {          // soft metric: choice and final decodes are interleaved (stale syndrom_soft_ chain)
       KML_RC(soft_chain(c, l, s, B, true));
       KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
@@ -905,8 +918,8 @@ int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *tru
   if (B > 2 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, std::min(2048, (B + 1) / 2)));
   int slow = 2;
 #ifdef KML_TUNING
-  if (const char *e = getenv("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));
-  if (const char *e = getenv("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));
+  if (const char *e = tuning_knob("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));
+  if (const char *e = tuning_knob("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));
 #endif
   // the soft metric's syndrom_soft_ chain runs through the frames in order: one lane, one batch at a time
   const bool sequential = c->opts.metric_type && !c->opts.known_h;

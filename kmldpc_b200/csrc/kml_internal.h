@@ -24,6 +24,19 @@ enum : uint32_t { STREAM_BITS = 0x5eed0001u, STREAM_FADE = 0x5eed0002u, STREAM_N
 
 // host_code.cpp
 std::vector<int> voronoi_neighbours_of_first(const double *pts, int q);
+// Environment knobs.  knob() = a run-time switch between kernels that are all SHIPPED and all reproduce the reference
+// (the fallback layouts / tilings the tests exercise): when one is set, the library says so on stderr — a stray
+// variable must not change the kernel silently.  tuning_knob() = A/B and timing-ablation variants (some with knowingly
+// WRONG results): compiled in only with -DKML_TUNING, otherwise the variable is ignored.
+const char *knob(const char *name);
+inline const char *tuning_knob(const char *name) {
+#ifdef KML_TUNING
+  return knob(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 // layout_opt.cpp
 int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_stride, const int32_t *row_ptr,

@@ -67,7 +67,8 @@ struct DecLaunch {
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
-  dec_kernel_t fn, fn_soft;  // filled by dec_prepare: the kernel, and its twin that also produces DecParams::out_soft
+  dec_kernel_t fn;  // filled by dec_prepare
+  int soft;         // this record launches the kernel that also produces DecParams::out_soft
   int qc_plan;      // != 0: the graph matches a compiled quasi-cyclic plan (bp_qc_kernel); sum-product, no soft output
   int rowmajor;     // sum-product kernels: messages at row_stride * slot + k (their own DecTables) instead of planar
 };

@@ -41,12 +41,16 @@ struct Rng {
 };
 
 struct Cached {
+  // the full key: the hash only finds the bucket, a hit needs these to compare equal
+  std::vector<int32_t> row_ptr, col_idx;
+  std::vector<int> group_of_var;
+  int par[5];
   std::vector<int> slot, pos;
   std::vector<std::vector<int>> order;
   int residual, excess;
 };
 std::mutex g_mu;
-std::map<uint64_t, Cached> g_cache;
+std::multimap<uint64_t, Cached> g_cache;
 
 uint64_t fnv(uint64_t h, const void *p, size_t n) {
   const unsigned char *b = (const unsigned char *)p;
@@ -75,8 +79,13 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_strid
   key = fnv(key, par, sizeof par);
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_cache.find(key);
-    if (it != g_cache.end()) {
+    auto range = g_cache.equal_range(key);
+    for (auto it = range.first; it != range.second; ++it) {
+      const Cached &cd = it->second;
+      if (!std::equal(par, par + 5, cd.par) || cd.row_ptr.size() != (size_t)M + 1 || cd.col_idx.size() != (size_t)E ||
+          !std::equal(cd.row_ptr.begin(), cd.row_ptr.end(), row_ptr) || !std::equal(cd.col_idx.begin(), cd.col_idx.end(), col_idx) ||
+          cd.group_of_var != group_of_var)
+        continue;  // a different graph behind the same 64-bit hash
       slot_of_row = it->second.slot;
       pos_of_edge = it->second.pos;
       edge_order = it->second.order;
@@ -245,7 +254,13 @@ int optimize_decoder_layout(int M, int N, int n_slots, int plane, int slot_strid
   if (excess_wavefronts) *excess_wavefronts = excess;
   {
     std::lock_guard<std::mutex> lk(g_mu);
-    g_cache[key] = Cached{slot_of_row, pos_of_edge, edge_order, (int)cost, excess};
+    Cached cd;
+    cd.row_ptr.assign(row_ptr, row_ptr + M + 1);
+    cd.col_idx.assign(col_idx, col_idx + E);
+    cd.group_of_var = group_of_var;
+    std::copy(par, par + 5, cd.par);
+    cd.slot = slot_of_row; cd.pos = pos_of_edge; cd.order = edge_order; cd.residual = (int)cost; cd.excess = excess;
+    g_cache.emplace(key, std::move(cd));
   }
   return (int)cost;
 }

@@ -369,12 +369,14 @@ __device__ __forceinline__ double km_rcp_count(double c) {
   r = fma(r, fma(-c, r, 1.0), r);
   return r;
 }
-// The exact input value of a sample for the rare fp64 blocks: re-read from memory (an L1 / L2 hit) through a volatile
-// asm, so that the compiler cannot hoist 2 x SPL conversions to fp64 out of those blocks into the hot loop's registers.
-__device__ __forceinline__ double2 km_exact_load(const float2 *p) {
-  float x, y;
-  asm volatile("ld.global.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "l"(p));
-  return make_double2((double)x, (double)y);
+// The exact input value of a sample for the rare fp64 blocks.  fp32 input: widened from the register through a volatile
+// asm, so that the compiler cannot hoist 2 x SPL conversions out of those blocks into the hot loop's registers.
+// fp64 input: re-read from memory (an L1 / L2 hit), again not hoistable.
+__device__ __forceinline__ double2 km_widen(float2 v) {
+  double x, y;
+  asm volatile("cvt.f64.f32 %0, %1;" : "=d"(x) : "f"(v.x));
+  asm volatile("cvt.f64.f32 %0, %1;" : "=d"(y) : "f"(v.y));
+  return make_double2(x, y);
 }
 __device__ __forceinline__ double2 km_exact_load(const double2 *p) {
   double x, y;
@@ -416,8 +418,8 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
   for (int f = wglobal; f < B; f += wstride) {
     const float2 *yf = reinterpret_cast<const float2 *>(y_in) + (size_t)f * n;
     const double2 *yd = reinterpret_cast<const double2 *>(y_in) + (size_t)f * n;
-    auto exact = [&](int j) -> double2 {  // the input value itself, as the reference sees it
-      return F64IN ? km_exact_load(yd + j * 32 + lane) : km_exact_load(yf + j * 32 + lane);
+    auto exact = [&](int j, float2 v) -> double2 {  // the input value itself, as the reference sees it
+      return F64IN ? km_exact_load(yd + j * 32 + lane) : km_widen(v);
     };
     float2 ys[SPL];
     unsigned long long best = 0ull;
@@ -461,7 +463,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
 #pragma unroll
         for (int j = 0; j < SPL; j++)
           if (valid.get(j) && fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x) >= thr) {
-            const double2 v = exact(j);
+            const double2 v = exact(j, ys[j]);
             const double d2 = fma(v.y, v.y, v.x * v.x);
             if (d2 > bd) { bd = d2; bi = j * 32 + lane; }  // ascending index within the lane: first maximum kept
           }
@@ -537,7 +539,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
 #pragma unroll
         for (int j = 0; j < SPL; j++) {
           if (!valid.get(j)) continue;
-          const double2 v = exact(j);
+          const double2 v = exact(j, ys[j]);
           bool in0 = true;
 #pragma unroll
           for (int t = 0; t < MAXNB; t++)
@@ -553,16 +555,26 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
       if (__any_sync(FULL, chg.any())) {  // samples that entered / left cluster 0 since the last pass
         double dr = 0.0, di = 0.0;
         int dc = 0;
+        constexpr int G = 6;  // samples per group: their (fp64-input: global) reads are in flight together
 #pragma unroll
-        for (int j = 0; j < SPL; j++) {
-          if (!__any_sync(FULL, chg.get(j))) continue;
-          if (chg.get(j)) {
-            const double2 v = exact(j);
-            const bool in = now.get(j);
-            dr += in ? v.x : -v.x;
-            di += in ? v.y : -v.y;
-            dc += in ? 1 : -1;
-          }
+        for (int j0 = 0; j0 < SPL; j0 += G) {
+          bool any = false;
+#pragma unroll
+          for (int t = 0; t < G; t++)
+            if (j0 + t < SPL) any = any || chg.get(j0 + t);
+          if (!__any_sync(FULL, any)) continue;
+          double2 v[G];
+#pragma unroll
+          for (int t = 0; t < G; t++)
+            if (j0 + t < SPL) v[t] = valid.get(j0 + t) ? exact(j0 + t, ys[j0 + t]) : make_double2(0.0, 0.0);
+#pragma unroll
+          for (int t = 0; t < G; t++)
+            if (j0 + t < SPL && chg.get(j0 + t)) {
+              const bool in = now.get(j0 + t);
+              dr += in ? v[t].x : -v[t].x;
+              di += in ? v[t].y : -v[t].y;
+              dc += in ? 1 : -1;
+            }
         }
         set_re += km_warp_sum(dr);
         set_im += km_warp_sum(di);

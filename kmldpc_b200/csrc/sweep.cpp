@@ -32,7 +32,7 @@ namespace {
 // carries an NCCL (torch bundles its own) keeps exactly one copy, and a single-GPU run never touches it.
 class CounterReducer {
  public:
-  // returns false (with `why`) when NCCL cannot be used; the caller then sums on the host and says so on stderr
+  // returns false (with `why`) when NCCL cannot be used
   bool init(int n_gpus, std::string &why) {
     G_ = n_gpus;
     for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
@@ -64,7 +64,7 @@ class CounterReducer {
     dbuf_.assign(G_, nullptr);
     st_.assign(G_, nullptr);
     for (int g = 0; g < G_; g++) {
-      if (cudaSetDevice(g) != cudaSuccess || cudaMalloc(&dbuf_[g], 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      if (cudaSetDevice(g) != cudaSuccess || cudaMalloc(&dbuf_[g], kMaxWords * sizeof(unsigned long long)) != cudaSuccess ||
           cudaStreamCreateWithFlags(&st_[g], cudaStreamNonBlocking) != cudaSuccess) {
         why = "device buffers for the counter reduction";
         return false;
@@ -74,18 +74,22 @@ class CounterReducer {
     return true;
   }
   bool ok() const { return ok_; }
-  // mine[g][0..3] = counters GPU g accumulated for this point; tot = their sum (read back from GPU 0)
-  bool reduce(const std::vector<std::array<uint64_t, 4>> &mine, uint64_t tot[4], std::string &why) {
+  // mine[g * count .. g * count + count) = counters GPU g accumulated; tot[count] = their sum (read back from GPU 0)
+  bool reduce(const uint64_t *mine, int count, uint64_t *tot, std::string &why) {
+    if (count < 1 || count > kMaxWords) {
+      why = "counter block size";
+      return false;
+    }
     for (int g = 0; g < G_; g++) {
       cudaSetDevice(g);
-      if (cudaMemcpyAsync(dbuf_[g], mine[g].data(), 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st_[g]) != cudaSuccess) {
+      if (cudaMemcpyAsync(dbuf_[g], mine + (size_t)g * count, count * sizeof(uint64_t), cudaMemcpyHostToDevice, st_[g]) != cudaSuccess) {
         why = "cudaMemcpyAsync (counters)";
         return false;
       }
     }
     ncclGroupStart_();
     for (int g = 0; g < G_; g++) {
-      ncclResult_t r = ncclAllReduce_(dbuf_[g], dbuf_[g], 4, ncclUint64, ncclSum, comms_[g], st_[g]);
+      ncclResult_t r = ncclAllReduce_(dbuf_[g], dbuf_[g], count, ncclUint64, ncclSum, comms_[g], st_[g]);
       if (r != ncclSuccess) {
         ncclGroupEnd_();
         why = std::string("ncclAllReduce: ") + ncclGetErrorString_(r);
@@ -99,7 +103,7 @@ class CounterReducer {
     }
     for (int g = 0; g < G_; g++) {
       cudaSetDevice(g);
-      if (g == 0) cudaMemcpyAsync(tot, dbuf_[0], 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_[0]);
+      if (g == 0) cudaMemcpyAsync(tot, dbuf_[0], count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st_[0]);
       if (cudaStreamSynchronize(st_[g]) != cudaSuccess) {
         why = "stream sync after the counter reduction";
         return false;
@@ -118,6 +122,9 @@ class CounterReducer {
         if (c) ncclCommDestroy_(c);
     // the library stays open: other users of the process (torch) may share it
   }
+
+  int gpus() const { return G_; }
+  static constexpr int kMaxWords = 1024;
 
  private:
   int G_ = 0;
@@ -286,6 +293,7 @@ extern "C" int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg) {
   if (get_num(t, "gpu.batch", d, err, false) && t.has("gpu.batch")) cfg->max_batch = (int)d;
   if (get_bool(t, "gpu.early_exit", b, err, false) && t.has("gpu.early_exit")) cfg->early_exit = b;
   if (get_num(t, "gpu.algorithm", d, err, false) && t.has("gpu.algorithm")) cfg->algorithm = (int)d;
+  if (t.has("gpu.reduce")) cfg->reduce_on_host = t.kv["gpu.reduce"] == "host";
   return KML_OK;
 }
 
@@ -355,33 +363,45 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
         set_global_error(errs[g]);
       }
   }
+  // The counters of the G GPUs are summed by ONE ncclAllReduce per SNR point.  A host-side sum is used
+  // only when the configuration asks for it ([gpu] reduce = "host"); NCCL failing is an error, not a silent fallback.
   CounterReducer reducer;
-  if (rc == KML_OK && G > 1) {
-    const char *force = getenv("KML_SWEEP_REDUCE");  // "host": sum on the host (A/B and test knob)
-    std::string why = "KML_SWEEP_REDUCE=host";
-    if ((force && std::string(force) == "host") || !reducer.init(G, why))
-      fprintf(stderr, "kmldpc_b200: counters of the %d GPUs are summed on the host (%s)\n", G, why.c_str());
+  if (rc == KML_OK && G > 1 && !cfg->reduce_on_host) {
+    std::string why;
+    if (!reducer.init(G, why)) {
+      set_global_error("counter reduction over NCCL unavailable (" + why + "); set [gpu] reduce = \"host\" to sum on the host");
+      rc = KML_ERR_NCCL;
+    }
   }
   if (rc == KML_OK) {
     int32_t info[8];
     kml_info(ctx[0], info);
-    const uint64_t chunk = (uint64_t)info[7];
+    // frames are handed out in chunks of several batches, so that kml_simulate's two lanes overlap inside a call and its
+    // own (lagged, per-batch) stop rule applies; the chunk shrinks for short runs so every GPU still gets work
+    uint64_t chunk = 4 * (uint64_t)info[7];
+    while (chunk > (uint64_t)info[7] && chunk * (uint64_t)G * 2 > cfg->max_num_blk) chunk -= (uint64_t)info[7];
     for (int i = 0; i < n_pts && rc == KML_OK; i++) {
       const double snr = cfg->min_snr + cfg->step_snr * i;
+      const uint64_t point_seed = cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;  // disjoint Philox streams per point
       std::atomic<uint64_t> cursor{0}, err_blk{0};
       uint64_t tot[4] = {0, 0, 0, 0};
-      std::vector<std::array<uint64_t, 4>> mine(G, std::array<uint64_t, 4>{0, 0, 0, 0});  // per GPU, this point
+      std::vector<uint64_t> mine((size_t)G * 4, 0);  // per GPU, this point
       std::atomic<int> failed{KML_OK};
+      std::mutex err_mu;
+      std::string err_msg;  // kml_last_error() of a failing worker (its thread-local copy dies with the thread)
+      // simulator.cc:117 leaves before the first frame when err_blk >= maximum_error_number — with 0 that is at once
+      const bool no_frames = cfg->max_err_blk == 0;
       // histogram mode (simulator.cc:81-84,154-162): "histogram_<snr>.txt" in the working directory, one line per frame
       // with the four metrics rotated to start at the (first) minimum; frames in index order on GPU 0.
-      if (cfg->histogram_enable) {
+      if (cfg->histogram_enable && !no_frames) {
         const std::string fname = "histogram_" + std::to_string(snr) + ".txt";
         std::ofstream hout(fname);
-        std::vector<float> met((size_t)chunk * 4);
-        for (uint64_t begin = 0; begin < cfg->max_num_blk && rc == KML_OK; begin += chunk) {
-          if (cfg->max_err_blk && tot[1] >= cfg->max_err_blk) break;
-          const uint64_t count = std::min<uint64_t>(chunk, cfg->max_num_blk - begin);
-          rc = kml_histogram(ctx[0], snr, cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull, begin, count, met.data(), tot);
+        const uint64_t hchunk = (uint64_t)info[7];
+        std::vector<float> met((size_t)hchunk * 4);
+        for (uint64_t begin = 0; begin < cfg->max_num_blk && rc == KML_OK; begin += hchunk) {
+          if (tot[1] >= cfg->max_err_blk) break;
+          const uint64_t count = std::min<uint64_t>(hchunk, cfg->max_num_blk - begin);
+          rc = kml_histogram(ctx[0], snr, point_seed, begin, count, met.data(), tot);
           if (rc != KML_OK) set_global_error(kml_last_error(ctx[0]));
           for (uint64_t f = 0; rc == KML_OK && f < count; f++) {
             const float *m = &met[f * 4];
@@ -394,40 +414,46 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
         }
       }
       auto worker = [&](int g) {
-        while (!cfg->histogram_enable && failed.load() == KML_OK) {
-          if (cfg->max_err_blk && err_blk.load() >= cfg->max_err_blk) break;  // simulator.cc:117
+        while (!cfg->histogram_enable && !no_frames && failed.load() == KML_OK) {
+          const uint64_t seen = err_blk.load();
+          if (seen >= cfg->max_err_blk) break;  // simulator.cc:117
           const uint64_t begin = cursor.fetch_add(chunk);
           if (begin >= cfg->max_num_blk) break;
           const uint64_t count = std::min<uint64_t>(chunk, cfg->max_num_blk - begin);
           uint64_t cnt[4] = {0, 0, 0, 0};
-          // the frame index space of a point is offset by the point index so that points use disjoint Philox streams
-          const int r = kml_simulate(ctx[g], snr, cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull, begin, count, 0, cnt, nullptr);
+          // what is left of the error budget goes down with the call: kml_simulate stops between its batches
+          const int r = kml_simulate(ctx[g], snr, point_seed, begin, count, cfg->max_err_blk - seen, cnt, nullptr);
           if (r != KML_OK) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (failed.load() == KML_OK) err_msg = kml_last_error(ctx[g]);
             failed.store(r);
-            set_global_error(kml_last_error(ctx[g]));
             break;
           }
           err_blk.fetch_add(cnt[1]);  // (the stop rule polls this host-side total while frames are in flight)
-          for (int k = 0; k < 4; k++) mine[g][k] += cnt[k];
+          for (int k = 0; k < 4; k++) mine[(size_t)g * 4 + k] += cnt[k];
         }
       };
       std::vector<std::thread> th;
       for (int g = 0; g < G; g++) th.emplace_back(worker, g);
       for (auto &t : th) t.join();
-      if (rc == KML_OK) rc = failed.load();
+      if (rc == KML_OK && failed.load() != KML_OK) {
+        rc = failed.load();
+        set_global_error(err_msg);  // on the CALLER's thread
+      }
       if (!cfg->histogram_enable) {
         std::string why;
         if (reducer.ok() && rc == KML_OK) {  // the path's one collective: 4 x uint64 per point over NCCL / NVLink
-          if (!reducer.reduce(mine, tot, why)) {
+          if (!reducer.reduce(mine.data(), 4, tot, why)) {
             set_global_error("counter reduction: " + why);
-            rc = KML_ERR_CUDA;
+            rc = KML_ERR_NCCL;
           }
         } else {
           for (int g = 0; g < G; g++)
-            for (int k = 0; k < 4; k++) tot[k] += mine[g][k];
+            for (int k = 0; k < 4; k++) tot[k] += mine[(size_t)g * 4 + k];
         }
       }
-      const double b = tot[2] ? (double)tot[3] / (double)tot[2] : 0.0, f = tot[0] ? (double)tot[1] / (double)tot[0] : 0.0;
+      // (0 / 0 like the reference's SourceSink::ber()/fer() when nothing ran)
+      const double b = (double)tot[3] / (double)tot[2], f = (double)tot[1] / (double)tot[0];
       ber_v[i] = b;
       fer_v[i] = f;
       if (ber) ber[i] = b;
@@ -448,3 +474,36 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
   kml_code_free(code);
   return rc;
 }
+
+// ---- comm_init / reduce_counters as entry points of their own (kml_sweep_run uses the same class)
+struct kml_comm {
+  CounterReducer r;
+  std::string err;
+};
+
+extern "C" int kml_comm_init(int n_gpus, kml_comm **out) {
+  if (!out || n_gpus < 1) return KML_ERR_ARG;
+  *out = nullptr;
+  auto *c = new kml_comm();
+  std::string why;
+  if (!c->r.init(n_gpus, why)) {
+    set_global_error("kml_comm_init: " + why);
+    delete c;
+    return KML_ERR_NCCL;
+  }
+  *out = c;
+  return KML_OK;
+}
+
+extern "C" int kml_reduce_counters(kml_comm *comm, const uint64_t *per_gpu, int count, uint64_t *total) {
+  if (!comm || !per_gpu || !total) return KML_ERR_ARG;
+  std::string why;
+  if (!comm->r.reduce(per_gpu, count, total, why)) {
+    comm->err = why;
+    set_global_error("kml_reduce_counters: " + why);
+    return KML_ERR_NCCL;
+  }
+  return KML_OK;
+}
+
+extern "C" void kml_comm_destroy(kml_comm *comm) { delete comm; }
