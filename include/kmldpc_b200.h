@@ -165,15 +165,17 @@ int kml_decode_p0(kml_ctx *ctx, int B, const double *p0, int iter_count, int32_t
 
 /* KmCodec::Decoder (kmcodec.cc:54-72) preceded by the k-means block of Simulator::run_blocks (simulator.cc:131-148):
  *     the whole receiver for B frames.  y[B][n_sym][2]; true_h[B][2] is read only when opts.known_h.
- *     Outputs (any may be NULL): uu_hat_packed[B][ceil(k/32)], hhat[B][2], kstar[B], ret[B]. */
+ *     Outputs (any may be NULL): uu_hat_packed[B][ceil(k/32)], hhat[B][2], kstar[B], ret[B], metric[B][4] = the four
+ *     candidate metrics GetMetrics returned (kmcodec.cc:122-139; blind detection only) — with hhat and kstar, everything
+ *     the reference's per-frame debug lines print ("Hhat = … Metric = …", "hatIndex = …", kmcodec.cc:64,132-136). */
 int kml_receive(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
-                float *hhat, int32_t *kstar, int32_t *ret);
+                float *hhat, int32_t *kstar, int32_t *ret, float *metric);
 
 /*     The same seam on the reference's types (the arguments of KmCodec::Decoder, kmcodec.cc:54-72, batched):
  *     y[B][n_sym][2] and true_h[B][2] are std::complex<double> as double pairs; hhat[B][2] double.  The conversion to the
  *     kernels' fp32 happens on the device, inside this call. */
 int kml_receive_f64(kml_ctx *ctx, int B, const double *y, const double *true_h, double var, uint32_t *uu_hat_packed,
-                    double *hhat, int32_t *kstar, int32_t *ret);
+                    double *hhat, int32_t *kstar, int32_t *ret, float *metric);
 
 /* Soft-syndrome metric ([xcodec] metric_type = true) only: the reference's syndrom_soft_ array is written by the
  * decoder's check-node phase alone (binaryldpccodec.cc:274), so a Decoder call that leaves at iteration 0
@@ -263,6 +265,9 @@ int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg);
 int kml_sweep_points(const kml_sweep_cfg *cfg);
 int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
                   void (*log_cb)(const char *line, void *user), void *user);
+/* seconds[0] = setup (files, contexts, NCCL), seconds[1] = the SNR points, of this process's last kml_sweep_run
+ * (the reference prints one "Total time cost" for both, kmldpc.cpp:44-53). */
+void kml_sweep_last_timing(double seconds[2]);
 
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -70,9 +70,9 @@ SYMBOLS = {
     "kml_resolve": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_f32p, c_i32p]),
     "kml_decode": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_int, c_i32p, c_i32p, c_i32p]),
     "kml_decode_p0": (C.c_int, [C.c_void_p, C.c_int, c_f64p, C.c_int, c_i32p, c_i32p, c_i32p]),
-    "kml_receive_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, C.c_double, c_u32p, c_f64p, c_i32p, c_i32p]),
+    "kml_receive_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, C.c_double, c_u32p, c_f64p, c_i32p, c_i32p, c_f32p]),
     "kml_soft_syndrome_state": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
-    "kml_receive": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p]),
+    "kml_receive": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p, c_f32p]),
     "kml_count_errors": (C.c_int, [C.c_void_p, C.c_int, c_u32p, c_u32p, c_u64p]),
     "kml_simulate": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, c_u64p, c_u64p]),
     "kml_histogram": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, c_f32p, c_u64p]),
@@ -85,6 +85,7 @@ SYMBOLS = {
     "kml_demap_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "kml_decode_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kml_count_errors_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kml_sweep_last_timing": (None, [c_f64p]),
     "kml_comm_init": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "kml_reduce_counters": (C.c_int, [C.c_void_p, c_u64p, C.c_int, c_u64p]),
     "kml_comm_destroy": (None, [C.c_void_p]),

@@ -910,7 +910,7 @@ namespace {
 // Host-buffer receiver: batches alternate between the two lanes so the H2D copy of batch i+1 and the D2H copy of batch
 // i-1 overlap the kernels of batch i (true overlap needs pinned host buffers; pageable ones still work).
 int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *true_h, double var, uint32_t *uu_hat_packed,
-                 float *hhat, double *hhat64, int32_t *kstar, int32_t *ret) {
+                 float *hhat, double *hhat64, int32_t *kstar, int32_t *ret, float *metric) {
   KML_CUDA(c, cudaSetDevice(c->device));
   // sub-batches of ~2048 frames (measured best on B200: the first H2D and the last D2H are the only exposed copies,
   // and the other lane's kernels fill the tail of each decoder launch); never fewer than ~1 frame per resident CTA
@@ -958,6 +958,8 @@ int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *tru
     if (kstar && !c->opts.known_h)
       KML_CUDA(c, cudaMemcpyAsync(kstar + b0, l.kstar.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
     if (ret) KML_CUDA(c, cudaMemcpyAsync(ret + b0, l.ret.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, s));
+    if (metric && !c->opts.known_h)
+      KML_CUDA(c, cudaMemcpyAsync(metric + (size_t)b0 * 4, l.metric.p, sizeof(float) * 4 * nb, cudaMemcpyDeviceToHost, s));
     KML_RC(lane_release(c, l, s));
     if (sequential) KML_CUDA(c, cudaStreamSynchronize(s));
   }
@@ -968,17 +970,17 @@ int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *tru
 }  // namespace
 
 extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
-                           float *hhat, int32_t *kstar, int32_t *ret) {
+                           float *hhat, int32_t *kstar, int32_t *ret, float *metric) {
   KML_RC(check_batch(c, B));
   if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive: bad argument");
-  return receive_host(c, B, y, 0, true_h, var, uu_hat_packed, hhat, nullptr, kstar, ret);
+  return receive_host(c, B, y, 0, true_h, var, uu_hat_packed, hhat, nullptr, kstar, ret, metric);
 }
 
 extern "C" int kml_receive_f64(kml_ctx *c, int B, const double *y, const double *true_h, double var, uint32_t *uu_hat_packed,
-                               double *hhat, int32_t *kstar, int32_t *ret) {
+                               double *hhat, int32_t *kstar, int32_t *ret, float *metric) {
   KML_RC(check_batch(c, B));
   if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive_f64: bad argument");
-  return receive_host(c, B, y, 1, true_h, var, uu_hat_packed, nullptr, hhat, kstar, ret);
+  return receive_host(c, B, y, 1, true_h, var, uu_hat_packed, nullptr, hhat, kstar, ret, metric);
 }
 
 extern "C" int kml_soft_syndrome_state(kml_ctx *c, int set, double *value) {

@@ -7,6 +7,7 @@
 #include <array>
 #include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -302,9 +303,23 @@ extern "C" int kml_sweep_points(const kml_sweep_cfg *cfg) {
   return (int)(unsigned long)((cfg->max_snr - cfg->min_snr) / cfg->step_snr + 1);  // simulator.cc:27
 }
 
+namespace {
+std::mutex g_timing_mu;
+double g_timing[2] = {0.0, 0.0};
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+extern "C" void kml_sweep_last_timing(double seconds[2]) {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  seconds[0] = g_timing[0];
+  seconds[1] = g_timing[1];
+}
+
 extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, double *ber, double *fer, uint64_t *counters,
                              void (*log_cb)(const char *, void *), void *user) {
   if (!cfg) return KML_ERR_ARG;
+  const double t_begin = now_s();
+  double t_points = t_begin;
   if (cfg->histogram_enable && cfg->known_h) {
     set_global_error("[histogram] enable = true needs blind detection (true_h_arg = false): one candidate has no histogram");
     return KML_ERR_ARG;
@@ -380,6 +395,11 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     // own (lagged, per-batch) stop rule applies; the chunk shrinks for short runs so every GPU still gets work
     uint64_t chunk = 4 * (uint64_t)info[7];
     while (chunk > (uint64_t)info[7] && chunk * (uint64_t)G * 2 > cfg->max_num_blk) chunk -= (uint64_t)info[7];
+    for (int g = 0; g < G; g++) {  // setup ends when every device is idle
+      cudaSetDevice(g);
+      cudaDeviceSynchronize();
+    }
+    t_points = now_s();
     for (int i = 0; i < n_pts && rc == KML_OK; i++) {
       const double snr = cfg->min_snr + cfg->step_snr * i;
       const uint64_t point_seed = cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;  // disjoint Philox streams per point
@@ -468,6 +488,11 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
       log("FER Result");
       for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, fer_v[i]));
     }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_timing[0] = t_points - t_begin;
+    g_timing[1] = now_s() - t_points;
   }
   for (auto *c : ctx) kml_destroy(c);
   kml_modem_free(modem);

@@ -231,9 +231,9 @@ class Link:
                                             _ptr(cc, C.c_int32), _ptr(uu, C.c_int32), _ptr(ret, C.c_int32)), "kml_decode_p0")
         return cc, uu, ret
 
-    def receive_f64(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None):
+    def receive_f64(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None, with_metric: bool = False):
         """kml_receive on the reference's types: y complex128 [B, n_sym], true_h complex128 [B].
-        Returns uu_hat_packed, hhat (complex128), kstar, ret."""
+        Returns uu_hat_packed, hhat (complex128), kstar, ret[, metric[B, 4]]."""
         y = np.ascontiguousarray(np.asarray(y, np.complex128).reshape(-1, self.n_sym))
         B = y.shape[0]
         th = None
@@ -243,10 +243,12 @@ class Link:
         hhat = np.zeros((B, 2), np.float64)
         kstar = np.zeros(B, np.int32)
         ret = np.empty(B, np.int32)
+        met = np.zeros((B, 4), np.float32) if with_metric else None
         self._check(self._lib.kml_receive_f64(self._h, B, _ptr(y.view(np.float64), C.c_double), _ptr(th, C.c_double), var,
                                               _ptr(uu, C.c_uint32), _ptr(hhat, C.c_double), _ptr(kstar, C.c_int32),
-                                              _ptr(ret, C.c_int32)), "kml_receive_f64")
-        return uu, hhat.view(np.complex128).reshape(B), kstar, ret
+                                              _ptr(ret, C.c_int32), _ptr(met, C.c_float)), "kml_receive_f64")
+        out = (uu, hhat.view(np.complex128).reshape(B), kstar, ret)
+        return out + (met,) if with_metric else out
 
     @property
     def soft_state(self) -> float:
@@ -260,8 +262,8 @@ class Link:
         v = C.c_double(float(value))
         self._check(self._lib.kml_soft_syndrome_state(self._h, 1, C.byref(v)), "kml_soft_syndrome_state")
 
-    def receive(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None, out=None):
-        """y: complex64 [B, n_sym] (or a float32 view).  Returns uu_hat_packed, hhat, kstar, ret."""
+    def receive(self, y: np.ndarray, var: float, true_h: np.ndarray | None = None, out=None, with_metric: bool = False):
+        """y: complex64 [B, n_sym] (or a float32 view).  Returns uu_hat_packed, hhat, kstar, ret[, metric[B, 4]]."""
         y, yf = self._y(y)
         B = y.shape[0]
         th = None
@@ -271,16 +273,18 @@ class Link:
         hhat = np.zeros((B, 2), np.float32)
         kstar = np.zeros(B, np.int32)
         ret = np.empty(B, np.int32)
+        met = np.zeros((B, 4), np.float32) if with_metric else None
         self._check(self._lib.kml_receive(self._h, B, _ptr(yf, C.c_float), _ptr(th, C.c_float), var,
                                           _ptr(uu, C.c_uint32), _ptr(hhat, C.c_float), _ptr(kstar, C.c_int32),
-                                          _ptr(ret, C.c_int32)), "kml_receive")
-        return uu, hhat.view(np.complex64).reshape(B), kstar, ret
+                                          _ptr(ret, C.c_int32), _ptr(met, C.c_float)), "kml_receive")
+        res = (uu, hhat.view(np.complex64).reshape(B), kstar, ret)
+        return res + (met,) if with_metric else res
 
     def receive_raw(self, B: int, y_ptr: int, var: float, uu_ptr: int, ret_ptr: int = 0, true_h_ptr: int = 0):
         """Host pointers given as integers (e.g. pinned torch tensors): no numpy wrapping, no allocation."""
         f = self._lib.kml_receive
         self._check(f(self._h, B, C.cast(y_ptr, capi.c_f32p), C.cast(true_h_ptr, capi.c_f32p) if true_h_ptr else None, var,
-                      C.cast(uu_ptr, capi.c_u32p), None, None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None),
+                      C.cast(uu_ptr, capi.c_u32p), None, None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None, None),
                     "kml_receive")
 
     def count_errors(self, u_packed: np.ndarray, uu_hat_packed: np.ndarray):

@@ -28,6 +28,13 @@ class Simulator:
             setattr(self.cfg, k, v)
         self.lines: list[str] = []
 
+    def last_timing(self) -> tuple[float, float]:
+        """(setup seconds, sweep seconds) of the last kml_sweep_run of this process: code / constellation loading, context
+        creation and NCCL initialisation, then the SNR points themselves."""
+        t = (C.c_double * 2)()
+        self._lib.kml_sweep_last_timing(t)
+        return float(t[0]), float(t[1])
+
     @property
     def n_points(self) -> int:
         return self._lib.kml_sweep_points(C.byref(self.cfg))

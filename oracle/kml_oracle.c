@@ -669,7 +669,7 @@ int64_t kmo_run(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double
 typedef struct {
   const kmo_code *c; const kmo_modem *m; const kmo_opts *o;
   double snr; long frame0, frames; int tid, threads; long chain_block;
-  double *yy, *h, *hhat; int32_t *kstar, *ret, *nerr; uint8_t *converged, *uu, *uu_hat;
+  double *yy, *h, *hhat; int32_t *kstar, *ret, *nerr; uint8_t *converged, *uu, *uu_hat; double *metric;
 } bulk_arg;
 
 static void *bulk_thread(void *p) {
@@ -692,6 +692,7 @@ static void *bulk_thread(void *p) {
     if (a->h) { a->h[2 * f] = fo.h[0]; a->h[2 * f + 1] = fo.h[1]; }
     if (a->hhat) { a->hhat[2 * f] = fo.hhat[0]; a->hhat[2 * f + 1] = fo.hhat[1]; }
     if (a->kstar) a->kstar[f] = fo.kstar;
+    if (a->metric) for (int k = 0; k < 4; k++) a->metric[4 * f + k] = fo.metric[k];
     if (a->ret) a->ret[f] = fo.ret;
     if (a->nerr) a->nerr[f] = fo.nerr;
     if (a->converged) a->converged[f] = (uint8_t)(kmo_parity_check(a->c, cch) == 0);
@@ -704,12 +705,12 @@ static void *bulk_thread(void *p) {
 
 void kmo_bulk(const kmo_code *c, const kmo_modem *m, const kmo_opts *o, double snr_db, long frame0, long frames, int threads,
               long chain_block, double *yy, double *h, double *hhat, int32_t *kstar, int32_t *ret, int32_t *nerr,
-              uint8_t *converged, uint8_t *uu, uint8_t *uu_hat) {
+              uint8_t *converged, uint8_t *uu, uint8_t *uu_hat, double *metric) {
   if (threads < 1) threads = 1;
   pthread_t *th = malloc(sizeof(pthread_t) * threads);
   bulk_arg *ar = calloc(threads, sizeof(bulk_arg));
   for (int t = 0; t < threads; t++) {
-    ar[t] = (bulk_arg){c, m, o, snr_db, frame0, frames, t, threads, chain_block, yy, h, hhat, kstar, ret, nerr, converged, uu, uu_hat};
+    ar[t] = (bulk_arg){c, m, o, snr_db, frame0, frames, t, threads, chain_block, yy, h, hhat, kstar, ret, nerr, converged, uu, uu_hat, metric};
     pthread_create(&th[t], NULL, bulk_thread, &ar[t]);
   }
   for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);

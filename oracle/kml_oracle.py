@@ -247,12 +247,13 @@ class Link:
         out = dict(y=np.empty((frames, self.n_sym, 2), np.float64), h=np.empty((frames, 2), np.float64),
                    hhat=np.empty((frames, 2), np.float64), kstar=np.empty(frames, np.int32), ret=np.empty(frames, np.int32),
                    nerr=np.empty(frames, np.int32), converged=np.empty(frames, np.uint8),
-                   u=np.empty((frames, c.K), np.uint8), uu_hat=np.empty((frames, c.K), np.uint8))
+                   u=np.empty((frames, c.K), np.uint8), uu_hat=np.empty((frames, c.K), np.uint8),
+                   metric=np.zeros((frames, 4), np.float64))
         lib().kmo_bulk(C.c_void_p(c._h), C.c_void_p(m._h), C.byref(self.opts), C.c_double(snr_db), C.c_long(frame0),
                        C.c_long(frames), C.c_int(threads), C.c_long(chain_block), _p(out["y"], C.c_double), _p(out["h"], C.c_double),
                        _p(out["hhat"], C.c_double), _p(out["kstar"], C.c_int32), _p(out["ret"], C.c_int32),
                        _p(out["nerr"], C.c_int32), _p(out["converged"], C.c_uint8), _p(out["u"], C.c_uint8),
-                       _p(out["uu_hat"], C.c_uint8))
+                       _p(out["uu_hat"], C.c_uint8), _p(out["metric"], C.c_double))
         out["y"] = out["y"].view(np.complex128).reshape(frames, self.n_sym)
         out["h"] = out["h"].view(np.complex128).reshape(frames)
         out["hhat"] = out["hhat"].view(np.complex128).reshape(frames)

@@ -571,21 +571,33 @@ def test_parity_statistics_at_scale(name, frames, kb):
         parts = []
         for b0 in range(0, frames, block):
             link.soft_state = 0.0
-            parts.append(link.receive_f64(ref["y"][b0:b0 + block], var))
-        uu_p, hhat, kstar, ret = [np.concatenate([p[i] for p in parts]) for i in range(4)]
+            parts.append(link.receive_f64(ref["y"][b0:b0 + block], var, with_metric=True))
+        uu_p, hhat, kstar, ret, met = [np.concatenate([p[i] for p in parts]) for i in range(5)]
     else:
         uu_p, hhat, kstar, ret = link.receive_f64(ref["y"], var)
     uu = kb.unpack_bits(uu_p, olink.code.K)
     rel = np.abs(hhat - ref["hhat"]) / np.abs(ref["hhat"])
-    k_same = kstar == ref["kstar"]
-    ret_same = ret == ref["ret"]
+    pinned = np.ones(frames, bool)
+    if soft:
+        # A metric that candidate 0 INHERITED from the previous frame's final decode is only as reproducible as that
+        # decode's last check-node phase: after 50 iterations without convergence the messages are chaotic (SURVEY 8(c) —
+        # the reference's own value depends on the element order of its codec copy), so the inherited number agrees
+        # to ~10 % only, and the choice it feeds is scoped out.  Such frames must be explained by exactly that: the
+        # previous frame's final decode ran to max_iter, or was itself scoped out.
+        pinned = (np.abs(met - ref["metric"]) <= 2e-3 * ref["metric"] + 1e-3).all(axis=1)
+        prev_chaotic = np.concatenate([[False], (ref["ret"][:-1] >= olink.opts.max_iter) | ~pinned[:-1]])
+        assert pinned.mean() >= 0.97, pinned.mean()
+        assert (prev_chaotic | pinned).mean() >= 0.999, np.where(~(prev_chaotic | pinned))[0][:10]
+    k_same = (kstar == ref["kstar"])[pinned]
+    ret_same = (ret == ref["ret"])[pinned]
     bits_same = (uu == ref["uu_hat"]).all(axis=1)
     conv = ref["converged"].astype(bool)
     fe = (uu != ref["u"]).any(axis=1)
     ref_fe = ref["nerr"] > 0
-    stats = dict(frames=frames, hhat_rel_p999=float(np.quantile(rel, 0.999)), hhat_rel_max=float(rel.max()),
+    stats = dict(frames=frames, pinned=int(pinned.sum()), hhat_rel_p999=float(np.quantile(rel, 0.999)), hhat_rel_max=float(rel.max()),
                  kstar_same=float(k_same.mean()), ret_same=float(ret_same.mean()), converged=int(conv.sum()),
-                 converged_bits_same=float(bits_same[conv & k_same].mean()), frame_error_same=float((fe == ref_fe).mean()),
+                 converged_bits_same=float(bits_same[conv & pinned & (kstar == ref["kstar"])].mean()),
+                 frame_error_same=float((fe == ref_fe)[pinned].mean()),
                  fer_gpu=float(fe.mean()), fer_ref=float(ref_fe.mean()))
     print(name, stats)
     assert stats["hhat_rel_max"] <= 1e-4, stats          # EVERY frame (measured: ~1e-12)
