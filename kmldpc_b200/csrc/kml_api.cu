@@ -41,6 +41,8 @@ struct Lane {
   DevBuf<float> lr, metric, llr_io;
   DevBuf<double> soft, fsoft, chain_state;   // soft-syndrome metric: own sums of the metric / final decodes, chain values
   DevBuf<int32_t> kstar, ret, mret, passes, bits_io, chain_flags, chain_queue, chain_counts;
+  DevBuf<int32_t> km_redo;                   // [B + 1] frames the fast k-means pass hands to the exact kernel, and their count
+  DevBuf<int32_t> dec_queue, dec_queue_n;    // frames the demapper hands to the decoder (the rest left at iteration 0)
   DevBuf<unsigned int> work_counter;
   DevBuf<unsigned long long> counters;  // 5 x u64: what THIS lane's batches of the current kml_simulate call counted
   // The work space above belongs to ONE stream at a time.  Every entry point calls lane_acquire() before it enqueues
@@ -58,6 +60,7 @@ struct kml_ctx {
   // code / modem
   int M = 0, N = 0, n_tx = 0, K = 0, n_chk = 0, punct = 0, info_offset = 0, E = 0, is_5g = 0, active = 0;
   int k_words = 0, tx_words = 0, words_n = 0, bits = 0, Q = 0, n_sym = 0;
+  int even_rows = 0;  // every check has even degree: a word and its complement have the same syndrome
   kml_opts opts{};
   int max_batch = 0;
   float2 rot[4];
@@ -66,6 +69,7 @@ struct kml_ctx {
   DevBuf<float2> points;
   DevBuf<int32_t> row_ptr, col_idx;
   KmConst km{};  // fp64 constants of the k-means kernel (n_nb = 0: general kernel)
+  int rot_symmetric = 0, rot_perm[3][64];  // s_k e^{j c pi/2} = s_{rot_perm[c-1][k]} for every k (else rot_symmetric = 0)
   DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
   DevBuf<uint32_t> vn_items, cn_items;
   int ell_width = 0;
@@ -148,6 +152,9 @@ int alloc_lane(kml_ctx *c, Lane &l) {
   KML_CUDA(c, l.kstar.alloc(B));
   KML_CUDA(c, l.ret.alloc(B));
   KML_CUDA(c, l.mret.alloc(4 * B));
+  KML_CUDA(c, l.km_redo.alloc(B + 1));
+  KML_CUDA(c, l.dec_queue.alloc(B));
+  KML_CUDA(c, l.dec_queue_n.alloc(1));
   if (c->opts.metric_type) {
     KML_CUDA(c, l.soft.alloc(4 * B));
     KML_CUDA(c, l.fsoft.alloc(B));
@@ -166,7 +173,7 @@ void free_lane(Lane &l) {
   l.u_packed.release(); l.c_packed.release(); l.uu_hat_packed.release(); l.cc_hat_packed.release();
   l.h.release(); l.y.release(); l.hhat.release(); l.noise.release(); l.lr.release(); l.metric.release();
   l.soft.release(); l.fsoft.release(); l.chain_state.release(); l.chain_flags.release(); l.chain_queue.release();
-  l.chain_counts.release(); l.mret.release();
+  l.chain_counts.release(); l.mret.release(); l.dec_queue.release(); l.dec_queue_n.release(); l.km_redo.release();
   l.llr_io.release(); l.kstar.release(); l.ret.release(); l.passes.release(); l.bits_io.release();
   l.work_counter.release(); l.counters.release();
   l.y64.release(); l.hhat64.release(); l.h64.release(); l.p0_io.release();
@@ -458,6 +465,8 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
   for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
   d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p; d.col_ell = c->col_ell.p; d.ell_width = c->ell_width;
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
+  d.symmetric = c->rot_symmetric;
+  std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
   const int32_t *sel = nullptr;
   int n_cand = 1;
   if (c->opts.known_h) {
@@ -466,15 +475,25 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
   } else {
     KML_LAUNCH(c, launch_kmeans(B, y, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
-                               want_h64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, s));
+                               want_h64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, l.km_redo.p, c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
     // hard metric: the four ratio vectors stay in shared memory and only the winner's reaches HBM — as long as that
     // leaves room for >= 4 CTAs per SM (PEG2304: 39 KB); long frames (PEG8064: 137 KB) write all four instead
     d.winner_only = (!decode_metric && 16 * (size_t)c->n_tx + c->n_tx + 64 * (size_t)c->Q <= 56 * 1024) ? 1 : 0;
+    // … and a frame whose winner already satisfies every check is finished by the demapper itself (what the decoder
+    // returns at iteration 0); only the others are queued for the decoder.  Reference semantics unchanged; off in the
+    // fixed-iteration timing mode (early_exit = 0 promises the full iteration count for every frame).
+    d.skip_decode = (d.winner_only && c->opts.early_exit && c->even_rows && c->punct == 0) ? 1 : 0;
+    d.words_n = c->words_n; d.out_bits = l.cc_hat_packed.p; d.out_ret = l.ret.p;
+    if (d.skip_decode) {
+      d.queue = l.dec_queue.p; d.queue_n = l.dec_queue_n.p;
+      KML_CUDA(c, cudaMemsetAsync(l.dec_queue_n.p, 0, sizeof(int32_t), s));
+    }
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
     if (d.winner_only) {
       DecParams p = dec_params(c, l, B, l.lr.p, nullptr, 1, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
+      if (d.skip_decode) { p.frame_idx = l.dec_queue.p; p.n_frames_dev = l.dec_queue_n.p; }
       KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
       KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
       return KML_OK;
@@ -536,6 +555,8 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
   c->punct = code->puncture; c->info_offset = code->info_offset; c->E = code->n_edges; c->is_5g = code->is_5g;
   c->active = code->encoder_active;
   c->k_words = (c->K + 31) / 32; c->tx_words = (c->n_tx + 31) / 32; c->words_n = (c->N + 31) / 32;
+  c->even_rows = 1;
+  for (int r = 0; r < c->M; r++) c->even_rows &= ((code->row_ptr[r + 1] - code->row_ptr[r]) & 1) ? 0 : 1;
   c->bits = modem->bits_per_symbol; c->Q = modem->n_points; c->n_sym = c->n_tx / c->bits;
   c->opts = *opts;
   if (c->opts.kmeans_iter <= 0) c->opts.kmeans_iter = 20;
@@ -569,6 +590,22 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     for (int i = 0; i < c->Q; i++) pts[i] = make_float2((float)modem->points[2 * i], (float)modem->points[2 * i + 1]);
     KML_CUDA(c, c->points.alloc(c->Q));
     KML_CUDA(c, cudaMemcpy(c->points.p, pts.data(), sizeof(float2) * c->Q, cudaMemcpyHostToDevice));
+    {  // quarter-turn symmetry of the constellation (demapper: one set of exponentials serves the four candidates)
+      c->rot_symmetric = c->Q <= 64 ? 1 : 0;
+      for (int cc = 1; cc <= 3 && c->rot_symmetric; cc++) {
+        const double cr = cc == 2 ? -1.0 : 0.0, ci = cc == 1 ? 1.0 : (cc == 3 ? -1.0 : 0.0);  // e^{j cc pi/2}
+        std::vector<char> used(c->Q, 0);
+        for (int k = 0; k < c->Q && c->rot_symmetric; k++) {
+          const double xr = modem->points[2 * k] * cr - modem->points[2 * k + 1] * ci;
+          const double xi = modem->points[2 * k] * ci + modem->points[2 * k + 1] * cr;
+          int hit = -1;
+          for (int m = 0; m < c->Q; m++)
+            if (!used[m] && std::hypot(modem->points[2 * m] - xr, modem->points[2 * m + 1] - xi) < 1e-9) { hit = m; break; }
+          if (hit < 0) c->rot_symmetric = 0;
+          else { used[hit] = 1; c->rot_perm[cc - 1][k] = hit; }
+        }
+      }
+    }
     {  // k-means: only "nearest centroid is cluster 0" matters, decided by the Voronoi neighbours of s_0 (host_code.cpp)
       const std::vector<int> nb = voronoi_neighbours_of_first(modem->points, c->Q);
       const double s0r = modem->points[0], s0i = modem->points[1], s0n = s0r * s0r + s0i * s0i;
@@ -772,7 +809,7 @@ int kmeans_host(kml_ctx *c, int B, const void *y, int y_is_f64, float *hhat, dou
     if (hhat64) KML_RC(ensure(c, l.hhat64, (size_t)c->max_batch));
     KML_CUDA(c, cudaMemcpyAsync(ydev, (const char *)y + (size_t)b0 * c->n_sym * ysz, ysz * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
     KML_LAUNCH(c, launch_kmeans(nb, ydev, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
-                               hhat64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, l.stream));
+                               hhat64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, l.km_redo.p, c->num_sms, l.stream));
     if (hhat) KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
     if (hhat64) KML_CUDA(c, cudaMemcpyAsync(hhat64 + (size_t)b0 * 2, l.hhat64.p, sizeof(double2) * nb, cudaMemcpyDeviceToHost, l.stream));
     if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
@@ -804,6 +841,8 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   for (int k = 0; k < 4; k++) d.rot[k] = c->rot[k];
   d.points = c->points.p; d.row_ptr = c->row_ptr.p; d.col_idx = c->col_idx.p; d.col_ell = c->col_ell.p; d.ell_width = c->ell_width;
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
+  d.symmetric = c->rot_symmetric;
+  std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
   return d;
 }
 
@@ -1048,8 +1087,7 @@ extern "C" int kml_simulate(kml_ctx *c, double snr_db, uint64_t seed, uint64_t f
       }
       const int nb = (int)std::min<uint64_t>((uint64_t)c->max_batch, frame_count - done);
       GenParams g = gen_params(c, nb, snr_db, seed, frame_begin + done);
-      KML_LAUNCH(c, launch_gen_bits(g, l.u_packed.p, l.stream));
-      KML_LAUNCH(c, launch_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
+      KML_LAUNCH(c, launch_gen_encode(g, l.u_packed.p, l.c_packed.p, l.stream));
       KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, l.stream));
       KML_RC(receive_on_lane(c, l, l.stream, nb, l.y.p, 0, l.h.p, var));
       KML_LAUNCH(c, launch_count_errors(nb, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, l.ret.p, c->opts.max_iter,
@@ -1078,7 +1116,7 @@ namespace {
 int histogram_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int nb, double var) {
   const bool decode_metric = c->is_5g || c->opts.metric_type;
   KML_LAUNCH(c, launch_kmeans(nb, l.y.p, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p, nullptr,
-                             l.passes.p, nullptr, c->num_sms, s));
+                             l.passes.p, nullptr, l.km_redo.p, c->num_sms, s));
   KML_RC(resolve_on_lane(c, l, s, nb, var));
   if (decode_metric) {
     // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)
@@ -1179,9 +1217,14 @@ extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed,
 extern "C" int kml_kmeans_dev(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes, void *stream) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat) return fail_arg(c, "kml_kmeans_dev: null buffer");
-  KML_CUDA(c, cudaSetDevice(c->device));  // (no scratch: reads y, writes hhat / passes)
+  if (B > c->max_batch) return fail_arg(c, "kml_kmeans_dev: B exceeds max_batch");
+  Lane &l = c->lane[0];
+  cudaStream_t s = (cudaStream_t)stream;
+  KML_ENTER(c, l, s);  // (the redo list of the two-tier scheme is lane scratch)
   KML_LAUNCH(c, launch_kmeans(B, y, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, (float2 *)hhat, nullptr,
-                             passes, nullptr, c->num_sms, (cudaStream_t)stream));
+                             passes, nullptr, l.km_redo.p, c->num_sms, s));
+  c->launches += 1;
+  KML_LEAVE(c, l, s);
   return KML_OK;
 }
 

@@ -96,6 +96,8 @@ struct GenParams {
 };
 cudaError_t launch_gen_bits(const GenParams &g, uint32_t *u_packed, cudaStream_t s);
 cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s);
+// launch_gen_bits + launch_encode in one kernel (same bits: the Philox stream is a function of the frame index only)
+cudaError_t launch_gen_encode(const GenParams &g, uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s);
 // noise == nullptr → Philox noise and fading (h written to h_out); otherwise h is read from h_in, noise as given
 cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
                            float2 *h_out, float2 *y, cudaStream_t s);
@@ -111,9 +113,11 @@ struct KmConst {
 };
 // y: float2 [B][n_sym], or double2 when y_is_f64 (then y32_out, if given, receives the fp32 copy the demapper reads).
 // hhat64 (optional): the estimate as carried (fp64).
+// redo (optional, int32 [B + 1] device scratch): enables the two-tier scheme for fp32 input — a plain-fp32 pass with a
+// margin test on every frame, the exact kernel only on the frames listed in redo by the first (see kmeans_fast_kernel).
 cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
-                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms,
-                          cudaStream_t s);
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int32_t *redo,
+                          int num_sms, cudaStream_t s);
 cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream_t s);
 cudaError_t launch_p0_to_lr(size_t n, const double *p0, float *lr, cudaStream_t s);
 
@@ -135,6 +139,17 @@ struct DemapParams {
   float *lr;             // [B][n_cand][n_tx] likelihood ratios P0/P1 in [1e-12, 1e12]
   float *metric;         // [B][4] (hard metric only)
   int32_t *kstar;        // [B]     (hard metric only; else untouched)
+  // winner_only + skip_decode: a frame whose chosen candidate has syndrome weight 0 gets its decisions (out_bits[B][words_n],
+  // out_ret = 1) written here — what the decoder would return at iteration 0 — and every OTHER frame is appended to the
+  // decoder's queue (queue[B], *queue_n zeroed by the caller).  Needs punct == 0 and even row degrees (host checks).
+  // 4 candidates: the constellation is invariant under quarter turns, s_k e^{j c pi/2} = s_{perm[c-1][k]} (host_code.cpp):
+  // candidate c's point probabilities are candidate 0's, re-labelled
+  int symmetric;
+  int perm[3][64];
+  int skip_decode, words_n;
+  uint32_t *out_bits;
+  int32_t *out_ret;
+  int32_t *queue, *queue_n;
 };
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s);
 

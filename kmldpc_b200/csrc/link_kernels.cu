@@ -86,7 +86,10 @@ __global__ void gen_bits_kernel(GenParams g, uint32_t *u_packed) {
 // 1 LDG + 4 LDS.128 + 16 LOP3 for 16 frames).
 constexpr int ENC_FT = 16;
 constexpr int ENC_THREADS = 256;
-__global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const uint32_t *u_packed, uint32_t *c_packed) {
+// GEN: the information bits are drawn here (SourceSink::GetBitStr, the Philox stream of gen_bits_kernel) and written to
+// u_packed as well, instead of being read from it — one launch and one HBM round trip less in the fused path.
+template <bool GEN>
+__global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, uint32_t *u_packed, uint32_t *c_packed) {
   extern __shared__ __align__(16) uint32_t sm[];
   const int chk_words = (g.n_chk + 31) / 32;
   uint32_t *su = sm;                                   // [ENC_FT][k_words + 1]
@@ -94,11 +97,35 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_kernel(GenParams g, const 
   uint4 *sut = reinterpret_cast<uint4 *>(sm + (((ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) + 3) & ~3));  // [k_words][ENC_FT]
   const int f0 = blockIdx.x * ENC_FT;
   const int nf = min(ENC_FT, g.B - f0);
-  for (int i = threadIdx.x; i < ENC_FT * (g.k_words + 1); i += blockDim.x) {
-    const int f = i / (g.k_words + 1), w = i % (g.k_words + 1);
-    const uint32_t v = (f < nf && w < g.k_words) ? u_packed[(size_t)(f0 + f) * g.k_words + w] : 0u;
-    su[i] = v;
-    if (w < g.k_words) reinterpret_cast<uint32_t *>(sut)[w * ENC_FT + f] = v;
+  if (GEN) {
+    const int groups = (g.k_words + 3) / 4;
+    for (int i = threadIdx.x; i < ENC_FT * groups; i += blockDim.x) {
+      const int f = i / groups, gr = i % groups;
+      uint32_t v[4] = {0, 0, 0, 0};
+      if (f < nf && g.encoder_active) {  // [ldpc] active = false → all-zero word (binaryldpccodec.cc:156-161)
+        const Philox4 r = philox_at(g.seed, STREAM_BITS, g.frame0 + f0 + f, gr);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int w = gr * 4 + j;
+        if (w < g.k_words) {
+          uint32_t x = v[j];
+          if (w == g.k_words - 1 && (g.k & 31)) x &= (1u << (g.k & 31)) - 1u;
+          su[f * (g.k_words + 1) + w] = x;
+          reinterpret_cast<uint32_t *>(sut)[w * ENC_FT + f] = x;
+          if (f < nf) u_packed[(size_t)(f0 + f) * g.k_words + w] = x;
+        }
+      }
+      if (gr == 0) su[f * (g.k_words + 1) + g.k_words] = 0u;
+    }
+  } else {
+    for (int i = threadIdx.x; i < ENC_FT * (g.k_words + 1); i += blockDim.x) {
+      const int f = i / (g.k_words + 1), w = i % (g.k_words + 1);
+      const uint32_t v = (f < nf && w < g.k_words) ? u_packed[(size_t)(f0 + f) * g.k_words + w] : 0u;
+      su[i] = v;
+      if (w < g.k_words) reinterpret_cast<uint32_t *>(sut)[w * ENC_FT + f] = v;
+    }
   }
   for (int i = threadIdx.x; i < ENC_FT * (chk_words + 1); i += blockDim.x) sp[i] = 0u;
   __syncthreads();
@@ -171,41 +198,50 @@ __global__ void channel_replay_kernel(GenParams g, const uint32_t *c_packed, con
   }
 }
 
-// Philox channel.  The fade is drawn once per frame (fade_kernel); one Philox4x32-10 call feeds the noise of TWO symbols
-// (counter = (symbol pair, frame, stream): independent of batch size, launch shape and GPU count).
-__global__ void fade_kernel(GenParams g, float2 *h_out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= g.B) return;
-  const Philox4 rh = philox_at(g.seed, STREAM_FADE, g.frame0 + f, 0);
-  const float2 gh = gauss_pair(rh.x, rh.y);
-  h_out[f] = make_float2(gh.x * 0.70710678118654752f, gh.y * 0.70710678118654752f);  // CN(0,1)
+// Philox channel.  One CTA per frame (grid-stride): the fade is drawn once per frame, one Philox4x32-10 call feeds the
+// noise of TWO symbols (counter = (symbol pair, frame, stream): independent of batch size, launch shape and GPU count).
+// Box-Muller with the fast intrinsics (lg2 / sin / cos / sqrt on the SFU: ~1e-6 relative, far below the noise itself).
+__device__ __forceinline__ float2 gauss_pair_fast(uint32_t a, uint32_t b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+  const float ang = (float)b * (6.283185307179586f * 2.3283064365386963e-10f);  // [0, 2 pi)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * __logf(u1)));
+  float s, c;
+  __sincosf(ang, &s, &c);
+  return make_float2(r * c, r * s);
 }
 
-__global__ void channel_kernel(GenParams g, const uint32_t *c_packed, const float2 *h, float2 *y) {
+constexpr int CH_THREADS = 192;
+__global__ void __launch_bounds__(CH_THREADS) channel_kernel(GenParams g, const uint32_t *c_packed, float2 *h_out, float2 *y) {
   const int pairs = (g.n_sym + 1) >> 1;
-  const long long total = (long long)g.B * pairs;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int f = (int)(i / pairs), pp = (int)(i % pairs);
+  for (int f = blockIdx.x; f < g.B; f += gridDim.x) {
     const uint32_t *c = c_packed + (size_t)f * g.tx_words;
-    const float2 hf = h[f];
-    const Philox4 rn = philox_at(g.seed, STREAM_NOISE, g.frame0 + f, (uint32_t)pp);
-    const float2 n0 = gauss_pair(rn.x, rn.y), n1 = gauss_pair(rn.z, rn.w);
-    float2 *yo = y + (size_t)f * g.n_sym + 2 * pp;
-    const float2 x0 = map_symbol(g, c, 2 * pp);
-    const float2 o0 = make_float2(hf.x * x0.x - hf.y * x0.y + g.sigma_over_sqrt2 * n0.x,
-                                  hf.x * x0.y + hf.y * x0.x + g.sigma_over_sqrt2 * n0.y);
-    if (2 * pp + 1 < g.n_sym) {
-      const float2 x1 = map_symbol(g, c, 2 * pp + 1);
-      const float2 o1 = make_float2(hf.x * x1.x - hf.y * x1.y + g.sigma_over_sqrt2 * n1.x,
-                                    hf.x * x1.y + hf.y * x1.x + g.sigma_over_sqrt2 * n1.y);
-      if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {  // one 128-bit store for the pair
-        *reinterpret_cast<float4 *>(yo) = make_float4(o0.x, o0.y, o1.x, o1.y);
+    // every thread derives the frame's fade itself (one Philox call; no barrier)
+    const Philox4 rh = philox_at(g.seed, STREAM_FADE, g.frame0 + f, 0);
+    const float2 gh = gauss_pair(rh.x, rh.y);
+    const float2 hf = make_float2(gh.x * 0.70710678118654752f, gh.y * 0.70710678118654752f);  // CN(0,1)
+    if (threadIdx.x == 0) h_out[f] = hf;
+    float2 *yf = y + (size_t)f * g.n_sym;
+    for (int pp = threadIdx.x; pp < pairs; pp += CH_THREADS) {
+      const Philox4 rn = philox_at(g.seed, STREAM_NOISE, g.frame0 + f, (uint32_t)pp);
+      const float2 n0 = gauss_pair_fast(rn.x, rn.y), n1 = gauss_pair_fast(rn.z, rn.w);
+      float2 *yo = yf + 2 * pp;
+      const float2 x0 = map_symbol(g, c, 2 * pp);
+      const float2 o0 = make_float2(hf.x * x0.x - hf.y * x0.y + g.sigma_over_sqrt2 * n0.x,
+                                    hf.x * x0.y + hf.y * x0.x + g.sigma_over_sqrt2 * n0.y);
+      if (2 * pp + 1 < g.n_sym) {
+        const float2 x1 = map_symbol(g, c, 2 * pp + 1);
+        const float2 o1 = make_float2(hf.x * x1.x - hf.y * x1.y + g.sigma_over_sqrt2 * n1.x,
+                                      hf.x * x1.y + hf.y * x1.x + g.sigma_over_sqrt2 * n1.y);
+        if ((reinterpret_cast<uintptr_t>(yo) & 15) == 0) {  // one 128-bit store for the pair
+          *reinterpret_cast<float4 *>(yo) = make_float4(o0.x, o0.y, o1.x, o1.y);
+        } else {
+          yo[0] = o0;
+          yo[1] = o1;
+        }
       } else {
         yo[0] = o0;
-        yo[1] = o1;
       }
-    } else {
-      yo[0] = o0;
     }
   }
 }
@@ -389,6 +425,133 @@ __device__ __forceinline__ double km_warp_sum(double v) {
   return v;
 }
 
+// FIRST TIER (fp32 input).  The same pass in plain fp32 — per-pass sums in fp32, cumulative sums in fp64 — plus ONE
+// extra instruction per sample that tracks the smallest |d| the frame ever saw.  As long as every |d| exceeds the band
+// tau (which covers the fp32 error of the estimate itself and of the test), every assignment equals the exact kernel's,
+// by induction over the passes, and the estimate differs from the exact one by fp32 summation noise only (~1e-7).  A
+// frame that came within the band anywhere is appended to `redo` and recomputed by kmeans_warp_kernel (a few per cent
+// of the frames); everything else never pays for fp64.
+template <int SPL, int MAXNB>
+__global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 24 ? 6 : (SPL <= 36 ? 5 : (SPL <= 48 ? 4 : 3)))
+kmeans_fast_kernel(int B, const float2 *y, int n, const KmConst kc, int iters, float2 *hhat_out, int32_t *passes_out,
+                   int32_t *redo, int32_t *redo_n) {
+  static_assert(MAXNB % 2 == 0, "neighbours are tested in pairs");
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
+  const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
+  const float is0r = (float)kc.is0r, is0i = (float)kc.is0i;
+  float2 snb[MAXNB];
+#pragma unroll
+  for (int t = 0; t < MAXNB; t++)
+    snb[t] = make_float2((float)(kc.s0r + kc.dsr[t < kc.n_nb ? t : 0]), (float)(kc.s0i + kc.dsi[t < kc.n_nb ? t : 0]));
+  for (int f = wglobal; f < B; f += wstride) {
+    const float2 *yf = y + (size_t)f * n;
+    float2 ys[SPL];
+    unsigned long long best = 0ull;
+    float a2top = 0.f, a2next = 0.f;  // the two largest |y|^2 (values only; the key carries the index of the largest)
+    // padded samples are NaN: every d of theirs is NaN, which fails "d <= 0" and drops out of fminf / fmaxf
+    const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int j = 0; j < SPL; j++) {
+      const int i = j * 32 + lane;
+      if (i < n) {
+        ys[j] = yf[i];
+        const float a2 = fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
+        best = key > best ? key : best;
+        a2next = fmaxf(a2next, fminf(a2, a2top));
+        a2top = fmaxf(a2top, a2);
+      } else {
+        ys[j] = make_float2(qnan, qnan);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ob = __shfl_xor_sync(FULL, best, o);
+      best = ob > best ? ob : best;
+      const float ot = __shfl_xor_sync(FULL, a2top, o), on = __shfl_xor_sync(FULL, a2next, o);
+      a2next = fmaxf(fmaxf(a2next, on), fminf(a2top, ot));
+      a2top = fmaxf(a2top, ot);
+    }
+    const float amax2 = a2top;
+    // the anchor must be THE largest sample: if the runner-up is within fp32's resolution of it, let the exact kernel decide
+    bool unsure = a2next >= amax2 * (1.0f - 2.0e-6f);
+    const float ymax_l1 = 1.4142137f * sqrtf(amax2);
+    const float2 ya = yf[0x7fffffff - (int)(uint32_t)(best & 0xffffffffu)];
+    float hr = ya.x * is0r - ya.y * is0i, hi = ya.x * is0i + ya.y * is0r;  // y_a / s_0
+    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0;  // cumulative over passes (never reset: kmeans.cc:33-34 as compiled)
+    float prev_r = 0.f, prev_i = 0.f, margin = 3.0e38f;
+    bool have_prev = false;
+    int passes = 0;
+    for (int it = 0; it < iters; it++) {
+      passes++;
+      const float2 c0 = make_float2(s0f.x * hr - s0f.y * hi, s0f.x * hi + s0f.y * hr);
+      const float n0 = c0.x * c0.x + c0.y * c0.y;
+      float2 ax[MAXNB / 2], ay[MAXNB / 2], nth[MAXNB / 2];
+      float cmax2 = n0;
+#pragma unroll
+      for (int t = 0; t < MAXNB; t++) {
+        const float2 ck = make_float2(snb[t].x * hr - snb[t].y * hi, snb[t].x * hi + snb[t].y * hr);
+        const float nk = ck.x * ck.x + ck.y * ck.y;
+        cmax2 = fmaxf(cmax2, nk);
+        const bool used = t < kc.n_nb;
+        const float axx = used ? ck.x - c0.x : 0.f, ayy = used ? ck.y - c0.y : 0.f;
+        const float nt = used ? -0.5f * (nk - n0) : -3.0e38f;
+        if (t & 1) { ax[t / 2].y = axx; ay[t / 2].y = ayy; nth[t / 2].y = nt; }
+        else { ax[t / 2].x = axx; ay[t / 2].x = ayy; nth[t / 2].x = nt; }
+      }
+      const float cmax = sqrtf(cmax2);
+      // the margin is compared in units of this pass's band, so that one running minimum serves all passes
+      const float inv_tau = __fdividef(1.0f, 4.0e-6f * cmax * (ymax_l1 + cmax));
+      float cnt = 0.f, sr = 0.f, si = 0.f, dmin = 3.0e38f;
+#pragma unroll
+      for (int j = 0; j < SPL; j++) {
+        float dmax = 0.f;
+#pragma unroll
+        for (int t = 0; t < MAXNB / 2; t++) {
+          const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_fma2(ay[t], make_float2(ys[j].y, ys[j].y), nth[t]));
+          dmax = t == 0 ? fmaxf(v.x, v.y) : fmaxf(dmax, fmaxf(v.x, v.y));  // (a padded sample: NaN throughout)
+        }
+        dmin = fminf(dmin, fabsf(dmax));  // fminf drops the NaN of a padded sample
+        if (dmax <= 0.0f) {
+          cnt += 1.f;
+          sr += ys[j].x;
+          si += ys[j].y;
+        }
+      }
+      margin = fminf(margin, dmin * inv_tau);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+        sr += __shfl_xor_sync(FULL, sr, o);
+        si += __shfl_xor_sync(FULL, si, o);
+      }
+      cum_cnt += (double)cnt;
+      cum_re += (double)sr;
+      cum_im += (double)si;
+      if (have_prev && prev_r == hr && prev_i == hi) break;  // clusters_ == tempClusters (kmeans.cc:47-56)
+      prev_r = hr;
+      prev_i = hi;
+      have_prev = true;
+      const float inv = __fdividef(1.0f, (float)cum_cnt);  // cluster 0 is never empty: the anchor sample sits on c_0
+      const float mr = (float)cum_re * inv, mi = (float)cum_im * inv;
+      hr = mr * is0r - mi * is0i;
+      hi = mr * is0i + mi * is0r;
+    }
+    unsure = unsure || margin <= 1.0f;
+    // (the bitwise early exit above compares fp32 estimates: a frame that left early is re-done too, the exact kernel's
+    //  fp64 estimate may not have repeated yet)
+    unsure = unsure || passes < iters;
+    if (__any_sync(FULL, unsure)) {
+      if (lane == 0) redo[atomicAdd(redo_n, 1)] = f;
+    } else if (lane == 0) {
+      hhat_out[f] = make_float2(hr, hi);
+      if (passes_out) passes_out[f] = passes;
+    }
+  }
+}
+
 template <int SPL>
 struct KmMask {  // one membership bit per sample of the lane
   uint32_t lo = 0, hi = 0;
@@ -405,17 +568,19 @@ struct KmMask {  // one membership bit per sample of the lane
 template <int SPL, int MAXNB, bool F64IN>
 __global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 16 ? 6 : (SPL <= 24 ? 5 : (SPL <= 36 ? 4 : (SPL <= 48 ? 3 : 2))))
 kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, float2 *hhat_out, double2 *hhat64_out,
-                   int32_t *passes_out, float2 *y32_out) {
+                   int32_t *passes_out, float2 *y32_out, const int32_t *queue, const int32_t *queue_n) {
   static_assert(MAXNB % 2 == 0 && SPL <= 64, "neighbours are tested in pairs; one mask bit per sample");
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
+  if (queue) B = min(B, __ldg(queue_n));  // second tier: only the frames the fast kernel could not vouch for
   const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
   float2 snb[MAXNB];
 #pragma unroll
   for (int t = 0; t < MAXNB; t++)
     snb[t] = make_float2((float)(kc.s0r + kc.dsr[t < kc.n_nb ? t : 0]), (float)(kc.s0i + kc.dsi[t < kc.n_nb ? t : 0]));
-  for (int f = wglobal; f < B; f += wstride) {
+  for (int fi = wglobal; fi < B; fi += wstride) {
+    const int f = queue ? __ldg(queue + fi) : fi;
     const float2 *yf = reinterpret_cast<const float2 *>(y_in) + (size_t)f * n;
     const double2 *yd = reinterpret_cast<const double2 *>(y_in) + (size_t)f * n;
     auto exact = [&](int j, float2 v) -> double2 {  // the input value itself, as the reference sees it
@@ -636,32 +801,48 @@ __device__ __forceinline__ float dm_dist2(const float2 s, const float2 ny) {
 // One symbol against NC candidates: per-point softmax with the reference's clip, bit marginals, ratio P0/P1; returns in
 // rr[j] the candidates' inverted hard decisions of bit j (bit c = candidate c).  lr_base already points at element
 // i * BITS of candidate 0; consecutive candidates are lr_stride floats apart.
-template <int BITS, int NC>
+// SYM: every shipped constellation is mapped onto itself by a 90-degree turn (QPSK, 4PSK, square QAM), so the points of
+// candidate c — s_k h e^{j c pi/2} — are the points of candidate 0 in another order: s_k e^{j c pi/2} = s_{perm_c(k)}.  The Q
+// clipped probabilities are then the SAME numbers for all four candidates, only attached to other labels: they are
+// computed once (Q exponentials instead of 4 Q), parked in this thread's column of a shared-memory stage and re-read
+// through perm_c for candidates 1..3.  (The reference's rotation uses a truncated pi: its candidates differ from exact
+// quarter turns by 1.6e-15 rad — nine orders below fp32.)  The host finds perm (kml_api.cu) and keeps the plain path for
+// a constellation without the symmetry.
+template <int BITS, int NC, bool SYM>
 __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pts, float rscale, float *lr_base,
-                                             size_t lr_stride, unsigned int (&rr)[BITS]) {
+                                             size_t lr_stride, unsigned int (&rr)[BITS], float *stage, const DemapParams &d) {
   constexpr int Q = 1 << BITS;
   const float2 ny = make_float2(-yy.x * rscale, -yy.y * rscale);
 #pragma unroll
   for (int j = 0; j < BITS; j++) rr[j] = 0;
+  float p[Q];
 #pragma unroll
   for (int c = 0; c < NC; c++) {
-    float p[Q];
-    float mx = -3.0e38f;
+    if (!SYM || c == 0) {
+      float mx = -3.0e38f;
 #pragma unroll
-    for (int k = 0; k < Q; k++) {
-      p[k] = -dm_dist2(s_pts[c * Q + k], ny);  // points and symbol are pre-scaled by sqrt(log2(e) / var)
-      mx = fmaxf(mx, p[k]);
+      for (int k = 0; k < Q; k++) {
+        p[k] = -dm_dist2(s_pts[c * Q + k], ny);  // points and symbol are pre-scaled by sqrt(log2(e) / var)
+        mx = fmaxf(mx, p[k]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < Q; k++) {
+        p[k] = dm_ex2(p[k] - mx);
+        sum += p[k];
+      }
+      const float inv = dm_rcp(sum);
+#pragma unroll
+      for (int k = 0; k < Q; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
+      // (the second normalisation, modem.cc:47-57, cancels in the ratio z0 / z1)
+      if (SYM && NC > 1) {
+#pragma unroll
+        for (int k = 0; k < Q; k++) stage[k * DM_THREADS] = p[k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < Q; k++) p[k] = stage[d.perm[c - 1][k] * DM_THREADS];
     }
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < Q; k++) {
-      p[k] = dm_ex2(p[k] - mx);
-      sum += p[k];
-    }
-    const float inv = dm_rcp(sum);
-#pragma unroll
-    for (int k = 0; k < Q; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);  // the upper clip 1-1e-12 is 1.0f in fp32
-    // (the second normalisation, modem.cc:47-57, cancels in the ratio z0 / z1)
 #pragma unroll
     for (int j = 0; j < BITS; j++) {
       float z0 = 0.f, z1 = 0.f;
@@ -670,8 +851,11 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
         if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
         else z1 += p[k];
       }
-      lr_base[c * lr_stride + j] = fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax);
-      rr[j] |= (z0 > z1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
+      const float ratio = fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax);
+      lr_base[c * lr_stride + j] = ratio;
+      // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115); taken from the ratio as stored, so that it
+      // is exactly the complement of the decision the decoder makes from that ratio at iteration 0 (post > 1 ? 0 : 1)
+      rr[j] |= (ratio > 1.0f ? 1u : 0u) << c;
     }
   }
 }
@@ -749,17 +933,18 @@ __device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float
     if (t == 1) { a0 = z0[1]; a1 = z1[1]; b0 = z0[5]; b1 = z1[5]; }
     if (t == 2) { a0 = z0[2]; a1 = z1[2]; }
     if (t == 3) { a0 = z0[3]; a1 = z1[3]; }
+    const float ra = fminf(fmaxf(a0 * dm_rcp(a1), kLrMin), kLrMax), rb = fminf(fmaxf(b0 * dm_rcp(b1), kLrMin), kLrMax);
     if (valid) {
-      lr_base[c * lr_stride + t] = fminf(fmaxf(a0 * dm_rcp(a1), kLrMin), kLrMax);
-      if (t < 2) lr_base[c * lr_stride + t + 4] = fminf(fmaxf(b0 * dm_rcp(b1), kLrMin), kLrMax);
+      lr_base[c * lr_stride + t] = ra;
+      if (t < 2) lr_base[c * lr_stride + t + 4] = rb;
     }
-    rr_a |= (a0 > a1 ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115)
-    rr_b |= (b0 > b1 ? 1u : 0u) << c;
+    rr_a |= (ra > 1.0f ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115), see demap_symbol
+    rr_b |= (rb > 1.0f ? 1u : 0u) << c;
   }
 }
 
-template <int BITS, int NC>
-__global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
+template <int BITS, int NC, bool SYM>
+__global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) {
   constexpr int Q = 1 << BITS;
   constexpr int MAXS = 6;  // symbols a thread keeps in flight (n_sym <= MAXS * DM_THREADS on the fast path)
   extern __shared__ unsigned char dsm[];
@@ -767,6 +952,9 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
   float2 *s_pts = reinterpret_cast<float2 *>(dsm);                          // [NC][PTS] s_k * h_cand
   float *s_lr = reinterpret_cast<float *>(dsm + sizeof(float2) * PTS * 4);   // [NC][n_tx]   (winner_only)
   unsigned char *s_rr = dsm + sizeof(float2) * PTS * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0);
+  // SYM: [Q][DM_THREADS] probabilities of candidate 0, one column per thread (16-byte aligned behind the decision bytes)
+  float *stage = reinterpret_cast<float *>(dsm + ((sizeof(float2) * PTS * 4 + (d.winner_only ? sizeof(float) * 4 * (size_t)d.n_tx : 0) +
+                                                   d.n_tx + d.punct + 32 + 15) & ~(size_t)15)) + threadIdx.x;
   __shared__ int s_cnt[4], s_best;
   const int tid = threadIdx.x;
   // exp(-|s - y|^2 / var) = 2^(-|r s - r y|^2) with r = sqrt(log2(e) / var): the candidate tables and the symbols are
@@ -818,7 +1006,7 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
       const int i = u * DM_THREADS + tid;
       if (i < d.n_sym) {
         unsigned int rr[BITS];
-        demap_symbol<BITS, NC>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
+        demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
         if (d.hard_metric) {
 #pragma unroll
           for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -827,7 +1015,7 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
     }
     for (int i = MAXS * DM_THREADS + tid; BITS != 6 && i < d.n_sym; i += DM_THREADS) {  // very long frames
       unsigned int rr[BITS];
-      demap_symbol<BITS, NC>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
+      demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
       if (d.hard_metric) {
 #pragma unroll
         for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -883,9 +1071,25 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(DemapParams d) {
       }
       if (d.winner_only) {
         __syncthreads();
-        const float *w = s_lr + (size_t)s_best * d.n_tx;
-        float *out = d.lr + (size_t)f * d.n_tx;
-        for (int i = tid; i < d.n_tx; i += DM_THREADS) out[i] = w[i];
+        const int best = s_best;
+        if (d.skip_decode && s_cnt[best] == 0) {
+          // The chosen candidate's hard decisions already satisfy every check: the decoder would make exactly these
+          // decisions in its first variable phase (all messages neutral → posterior = channel ratio), find a zero
+          // syndrome and return 0 + (0 < max_iter) = 1 (binaryldpccodec.cc:175-232).  Its answer is written here and the
+          // frame never enters the decoder's queue — nor do its ratios travel through HBM.  (All row degrees are even,
+          // so the inverted decisions of the metric and their complements have the same syndrome.)
+          for (int v = tid; v < d.words_n * 32; v += DM_THREADS) {
+            const unsigned bit = v < d.n_tx ? (((unsigned)s_rr[v] >> best) & 1u) ^ 1u : 0u;
+            const unsigned word = __ballot_sync(0xffffffffu, bit);
+            if ((tid & 31) == 0) d.out_bits[(size_t)f * d.words_n + (v >> 5)] = word;
+          }
+          if (tid == 0) d.out_ret[f] = 1;
+        } else {
+          const float *w = s_lr + (size_t)best * d.n_tx;
+          float *out = d.lr + (size_t)f * d.n_tx;
+          for (int i = tid; i < d.n_tx; i += DM_THREADS) out[i] = w[i];
+          if (tid == 0 && d.queue) d.queue[atomicAdd(d.queue_n, 1)] = f;
+        }
       }
     }
     __syncthreads();
@@ -1098,15 +1302,24 @@ cudaError_t launch_gen_bits(const GenParams &g, uint32_t *u_packed, cudaStream_t
   return cudaGetLastError();
 }
 
-cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s) {
+static cudaError_t launch_encode_impl(const GenParams &g, uint32_t *u_packed, uint32_t *c_packed, bool gen, cudaStream_t s) {
   const int chk_words = (g.n_chk + 31) / 32;
   const int smem = ((((ENC_FT * (g.k_words + 1) + ENC_FT * (chk_words + 1)) + 3) & ~3) + ENC_FT * g.k_words) * (int)sizeof(uint32_t);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = gen ? cudaFuncSetAttribute(encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                        : cudaFuncSetAttribute(encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
   }
-  encode_kernel<<<(g.B + ENC_FT - 1) / ENC_FT, ENC_THREADS, smem, s>>>(g, u_packed, c_packed);
+  if (g.B < 1) return cudaSuccess;
+  if (gen) encode_kernel<true><<<(g.B + ENC_FT - 1) / ENC_FT, ENC_THREADS, smem, s>>>(g, u_packed, c_packed);
+  else encode_kernel<false><<<(g.B + ENC_FT - 1) / ENC_FT, ENC_THREADS, smem, s>>>(g, u_packed, c_packed);
   return cudaGetLastError();
+}
+cudaError_t launch_encode(const GenParams &g, const uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s) {
+  return launch_encode_impl(g, const_cast<uint32_t *>(u_packed), c_packed, false, s);
+}
+cudaError_t launch_gen_encode(const GenParams &g, uint32_t *u_packed, uint32_t *c_packed, cudaStream_t s) {
+  return launch_encode_impl(g, u_packed, c_packed, true, s);
 }
 
 cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const float2 *h_in, const float2 *noise,
@@ -1116,8 +1329,7 @@ cudaError_t launch_channel(const GenParams &g, const uint32_t *c_packed, const f
     return cudaGetLastError();
   }
   if (!h_out) return cudaErrorInvalidValue;  // the Philox channel always reports its fades
-  fade_kernel<<<(g.B + 255) / 256, 256, 0, s>>>(g, h_out);
-  channel_kernel<<<grid_for((long long)g.B * ((g.n_sym + 1) / 2), 256), 256, 0, s>>>(g, c_packed, h_out, y);
+  channel_kernel<<<g.B < 148 * 10 ? g.B : 148 * 10, CH_THREADS, 0, s>>>(g, c_packed, h_out, y);
   return cudaGetLastError();
 }
 
@@ -1145,10 +1357,11 @@ cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream
 
 template <bool F64IN>
 static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmConst &kc, int iters, float2 *hhat,
-                                      double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms, cudaStream_t s) {
+                                      double2 *hhat64, int32_t *passes, float2 *y32_out, const int32_t *queue,
+                                      const int32_t *queue_n, int num_sms, cudaStream_t s) {
   const int spl = (n_sym + 31) / 32;
   const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
-#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out)
+#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, queue, queue_n)
   if (kc.n_nb <= 2) {
     if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
   } else if (kc.n_nb <= 4) {
@@ -1160,13 +1373,37 @@ static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmC
   return cudaGetLastError();
 }
 
+static cudaError_t launch_kmeans_fast(int B, const float2 *y, int n_sym, const KmConst &kc, int iters, float2 *hhat,
+                                      int32_t *passes, int32_t *redo, int32_t *redo_n, int num_sms, cudaStream_t s) {
+  const int spl = (n_sym + 31) / 32;
+  const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
+#define KMF(SPL, NB) kmeans_fast_kernel<SPL, NB><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, passes, redo, redo_n)
+  if (kc.n_nb <= 2) {
+    if (spl <= 16) KMF(16, 2); else if (spl <= 24) KMF(24, 2); else if (spl <= 36) KMF(36, 2); else if (spl <= 48) KMF(48, 2); else KMF(64, 2);
+  } else if (kc.n_nb <= 4) {
+    if (spl <= 16) KMF(16, 4); else if (spl <= 24) KMF(24, 4); else if (spl <= 36) KMF(36, 4); else if (spl <= 48) KMF(48, 4); else KMF(64, 4);
+  } else {
+    if (spl <= 16) KMF(16, 8); else if (spl <= 24) KMF(24, 8); else if (spl <= 36) KMF(36, 8); else if (spl <= 48) KMF(48, 8); else KMF(64, 8);
+  }
+#undef KMF
+  return cudaGetLastError();
+}
+
 cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
-                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms,
-                          cudaStream_t s) {
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int32_t *redo,
+                          int num_sms, cudaStream_t s) {
   if (B < 1) return cudaSuccess;
   if (kc.n_nb >= 1 && kc.n_nb <= 8 && n_sym <= 32 * 64) {  // warp per frame, Voronoi-neighbour half-plane tests
-    return y_is_f64 ? launch_kmeans_warp<true>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, num_sms, s)
-                    : launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, num_sms, s);
+    if (y_is_f64)
+      return launch_kmeans_warp<true>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, nullptr, nullptr, num_sms, s);
+    if (!redo || hhat64)  // no scratch for the two-tier scheme (or the fp64 estimate is wanted): exact kernel on every frame
+      return launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, hhat64, passes, nullptr, nullptr, nullptr, num_sms, s);
+    // two tiers: plain fp32 with a margin test on every frame, then the exact kernel on the frames that came within the band
+    cudaError_t e = cudaMemsetAsync(redo + B, 0, sizeof(int32_t), s);  // redo[0..B) = list, redo[B] = its length
+    if (e != cudaSuccess) return e;
+    e = launch_kmeans_fast(B, reinterpret_cast<const float2 *>(y), n_sym, kc, iters, hhat, passes, redo, redo + B, num_sms, s);
+    if (e != cudaSuccess) return e;
+    return launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, nullptr, passes, nullptr, redo, redo + B, num_sms, s);
   }
   // general fallback (constellations whose first point has more than 8 Voronoi neighbours, very long frames): one CTA
   // per frame, full distance comparison in fp32 against every constellation point
@@ -1191,13 +1428,17 @@ cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const f
 template <int BITS>
 static cudaError_t launch_demap_bits(const DemapParams &d, int grid, int smem, cudaStream_t s) {
   if (d.n_cand == 4) {
+    constexpr bool kCanSym = BITS <= 5;  // (64 points: the quad-of-lanes path keeps its own exponentials)
+    const bool sym = kCanSym && d.symmetric;
+    if (sym) smem = ((smem + 15) & ~15) + (int)sizeof(float) * (1 << BITS) * DM_THREADS;
+    auto k = sym ? demap_kernel<BITS, 4, kCanSym> : demap_kernel<BITS, 4, false>;
     if (smem > 48 * 1024) {  // per device: set on every large launch
-      cudaError_t e = cudaFuncSetAttribute(demap_kernel<BITS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
     }
-    demap_kernel<BITS, 4><<<grid, DM_THREADS, smem, s>>>(d);
+    k<<<grid, DM_THREADS, smem, s>>>(d);
   } else if (d.n_cand == 1) {
-    demap_kernel<BITS, 1><<<grid, DM_THREADS, smem, s>>>(d);
+    demap_kernel<BITS, 1, false><<<grid, DM_THREADS, smem, s>>>(d);
   } else {
     return cudaErrorInvalidValue;
   }
