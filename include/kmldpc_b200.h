@@ -203,6 +203,13 @@ int kml_count_errors(kml_ctx *ctx, int B, const uint32_t *u_packed, const uint32
 int kml_simulate(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, uint64_t frame_count,
                  uint64_t max_err_blk, uint64_t counters[4], uint64_t *iters_sum);
 
+/* The same for ONE batch (count <= max_batch) with the per-frame values the reference writes to its log file for every
+ * frame — "Generated H = …" (simulator.cc:124-126), "Hhat = … Metric = …" per candidate (kmcodec.cc:132-136),
+ * "hatIndex = …" (kmcodec.cc:64): h[count][2] the fade drawn, hhat[count][2], metric[count][4], kstar[count] (blind
+ * detection only) and ret[count]; any may be NULL.  kml_sweep_run prints those lines from it when [gpu] debug = true. */
+int kml_simulate_frames(kml_ctx *ctx, double snr_db, uint64_t seed, uint64_t frame_begin, int count, uint64_t counters[4],
+                        float *h, float *hhat, float *metric, int32_t *kstar, int32_t *ret);
+
 /* Histogram mode of Simulator::run_blocks (simulator.cc:154-162) + KmCodec::GetHistogramData (kmcodec.cc:74-79): frames
  * [frame_begin, frame_begin+frame_count) are generated and detected but NOT finally decoded; metrics[frame][4] receives
  * the four candidate metrics (in candidate order 0°, 90°, 180°, 270°; the caller rotates them to start at the minimum
@@ -252,6 +259,9 @@ typedef struct kml_sweep_cfg {
   /* optional [gpu] table (ignored by the reference binary) */
   uint64_t seed;
   int32_t n_gpus, max_batch, early_exit, algorithm;  /* [gpu] gpus / batch / early_exit / algorithm (0 SPA, 1 min-sum) */
+  int32_t debug_frames, reserved2;                   /* [gpu] debug = true: the reference's per-frame log lines ("Generated H",
+                                                        "Current Block Number", "Hhat … Metric", "hatIndex") through log_cb, frames
+                                                        in index order on GPU 0 — a debugging mode, orders of magnitude slower */
 } kml_sweep_cfg;
 
 /* Minimal TOML reader for exactly the keys above (the reference parses the same file with toml11, kmldpc.cpp:29-31). */

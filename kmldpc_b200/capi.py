@@ -41,7 +41,8 @@ class KmlSweepCfg(C.Structure):
                 ("histogram_enable", C.c_int32), ("reduce_on_host", C.c_int32),
                 ("matrix_file", C.c_char * 512), ("modem_file", C.c_char * 512),
                 ("seed", C.c_uint64),
-                ("n_gpus", C.c_int32), ("max_batch", C.c_int32), ("early_exit", C.c_int32), ("algorithm", C.c_int32)]
+                ("n_gpus", C.c_int32), ("max_batch", C.c_int32), ("early_exit", C.c_int32), ("algorithm", C.c_int32),
+                ("debug_frames", C.c_int32), ("reserved2", C.c_int32)]
 
 
 LOG_CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
@@ -75,6 +76,8 @@ SYMBOLS = {
     "kml_receive": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p, c_f32p]),
     "kml_count_errors": (C.c_int, [C.c_void_p, C.c_int, c_u32p, c_u32p, c_u64p]),
     "kml_simulate": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, c_u64p, c_u64p]),
+    "kml_simulate_frames": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_int, c_u64p, c_f32p, c_f32p, c_f32p,
+                                      c_i32p, c_i32p]),
     "kml_histogram": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, c_f32p, c_u64p]),
     "kml_histogram_rx": (C.c_int, [C.c_void_p, C.c_int, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_u32p, c_u64p]),
     "kml_generate_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,

@@ -1110,6 +1110,36 @@ extern "C" int kml_simulate(kml_ctx *c, double snr_db, uint64_t seed, uint64_t f
   return KML_OK;
 }
 
+// Per-frame view of the fused path (the reference's per-frame log lines, simulator.cc:124-126,149-152, kmcodec.cc:64,132-136)
+extern "C" int kml_simulate_frames(kml_ctx *c, double snr_db, uint64_t seed, uint64_t frame_begin, int count,
+                                   uint64_t counters[4], float *h, float *hhat, float *metric, int32_t *kstar, int32_t *ret) {
+  KML_RC(check_batch(c, count));
+  if (!counters) return fail_arg(c, "kml_simulate_frames: null counters");
+  if (count > c->max_batch) return fail_arg(c, "kml_simulate_frames: count exceeds max_batch");
+  const double var = std::pow(10.0, -0.1 * snr_db);
+  Lane &l = c->lane[0];
+  cudaStream_t s = l.stream;
+  KML_ENTER(c, l, s);
+  KML_CUDA(c, cudaMemsetAsync(l.counters.p, 0, 5 * sizeof(unsigned long long), s));
+  GenParams g = gen_params(c, count, snr_db, seed, frame_begin);
+  KML_LAUNCH(c, launch_gen_encode(g, l.u_packed.p, l.c_packed.p, s));
+  KML_LAUNCH(c, launch_channel(g, l.c_packed.p, nullptr, nullptr, l.h.p, l.y.p, s));
+  KML_RC(receive_on_lane(c, l, s, count, l.y.p, 0, l.h.p, var));
+  KML_LAUNCH(c, launch_count_errors(count, c->K, c->k_words, l.u_packed.p, l.uu_hat_packed.p, l.ret.p, c->opts.max_iter, l.counters.p, s));
+  if (h) KML_CUDA(c, cudaMemcpyAsync(h, l.h.p, sizeof(float2) * count, cudaMemcpyDeviceToHost, s));
+  if (ret) KML_CUDA(c, cudaMemcpyAsync(ret, l.ret.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, s));
+  if (!c->opts.known_h) {
+    if (hhat) KML_CUDA(c, cudaMemcpyAsync(hhat, l.hhat.p, sizeof(float2) * count, cudaMemcpyDeviceToHost, s));
+    if (metric) KML_CUDA(c, cudaMemcpyAsync(metric, l.metric.p, sizeof(float) * 4 * count, cudaMemcpyDeviceToHost, s));
+    if (kstar) KML_CUDA(c, cudaMemcpyAsync(kstar, l.kstar.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, s));
+  }
+  KML_CUDA(c, cudaMemcpyAsync(c->h_counters, l.counters.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  KML_CUDA(c, cudaStreamSynchronize(s));
+  KML_LEAVE(c, l, s);
+  for (int k = 0; k < 4; k++) counters[k] += c->h_counters[k];
+  return KML_OK;
+}
+
 namespace {
 // GetHistogramData + CntErr for nb frames whose symbols and information bits sit in l.y / l.u_packed
 // (kmcodec.cc:74-79, simulator.cc:154-167): l.metric[nb][4], c->counters += CntErr on a uu_hat no final decoder wrote.

@@ -539,10 +539,10 @@ kmeans_fast_kernel(int B, const float2 *y, int n, const KmConst kc, int iters, f
       hr = mr * is0r - mi * is0i;
       hi = mr * is0i + mi * is0r;
     }
-    unsure = unsure || margin <= 1.0f;
-    // (the bitwise early exit above compares fp32 estimates: a frame that left early is re-done too, the exact kernel's
-    //  fp64 estimate may not have repeated yet)
-    unsure = unsure || passes < iters;
+    // A frame that left early (its fp32 estimate repeated: every pass since has had the same member set and the cumulative
+    // mean has stopped moving at fp32 resolution) skipped passes in which the exact estimate would still have crept by up
+    // to ~1e-6: it is vouched for only with twice the band to spare.
+    unsure = unsure || margin <= (passes < iters ? 2.0f : 1.0f);
     if (__any_sync(FULL, unsure)) {
       if (lane == 0) redo[atomicAdd(redo_n, 1)] = f;
     } else if (lane == 0) {

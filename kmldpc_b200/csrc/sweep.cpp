@@ -9,6 +9,7 @@
 #include <cctype>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -295,6 +296,7 @@ extern "C" int kml_sweep_cfg_load(const char *config_toml, kml_sweep_cfg *cfg) {
   if (get_bool(t, "gpu.early_exit", b, err, false) && t.has("gpu.early_exit")) cfg->early_exit = b;
   if (get_num(t, "gpu.algorithm", d, err, false) && t.has("gpu.algorithm")) cfg->algorithm = (int)d;
   if (t.has("gpu.reduce")) cfg->reduce_on_host = t.kv["gpu.reduce"] == "host";
+  if (get_bool(t, "gpu.debug", b, err, false) && t.has("gpu.debug")) cfg->debug_frames = b;
   return KML_OK;
 }
 
@@ -433,8 +435,43 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
           }
         }
       }
+      // [gpu] debug = true: the reference's per-frame log lines, frames in index order on GPU 0 (simulator.cc:124-126,
+      // 149-152; kmcodec.cc:64,132-136).  The same frames and counters as the normal path, one batch at a time.
+      const bool debug = cfg->debug_frames && !cfg->histogram_enable && !no_frames;
+      if (debug) {
+        const int nb_max = info[7];
+        std::vector<float> dh(2 * (size_t)nb_max), dhh(2 * (size_t)nb_max), dm(4 * (size_t)nb_max);
+        std::vector<int32_t> dk(nb_max), dr(nb_max);
+        for (uint64_t begin = 0; begin < cfg->max_num_blk && rc == KML_OK; begin += (uint64_t)nb_max) {
+          if (tot[1] >= cfg->max_err_blk) break;
+          const int count = (int)std::min<uint64_t>((uint64_t)nb_max, cfg->max_num_blk - begin);
+          const uint64_t blk0 = tot[0];
+          rc = kml_simulate_frames(ctx[0], snr, point_seed, begin, count, tot, dh.data(), dhh.data(), dm.data(), dk.data(), dr.data());
+          if (rc != KML_OK) { set_global_error(kml_last_error(ctx[0])); break; }
+          for (int f = 0; f < count; f++) {
+            std::stringstream st;
+            st << "Generated H = " << std::complex<double>(dh[2 * f], dh[2 * f + 1]);
+            log(st.str());
+            if (cfg->known_h) continue;
+            st.str("");
+            st << std::fixed << std::setprecision(0) << std::setfill('0') << "Current Block Number = " << std::setw(7) << std::right
+               << (blk0 + (uint64_t)f + 1);
+            log(st.str());
+            const std::complex<double> hh(dhh[2 * f], dhh[2 * f + 1]);
+            for (int k = 0; k < 4; k++) {
+              st.str("");
+              st.clear();
+              const double m = cfg->metric_type ? -(double)dm[4 * f + k] : (double)dm[4 * f + k];  // Metric() before std::abs
+              st << std::fixed << std::setprecision(14) << "Hhat = " << hh * std::exp(std::complex<double>(0, (kml::kRefPi / 2) * k))
+                 << " Metric = " << std::setw(5) << std::right << m;
+              log(st.str());
+            }
+            log("hatIndex = " + std::to_string(dk[f]));
+          }
+        }
+      }
       auto worker = [&](int g) {
-        while (!cfg->histogram_enable && !no_frames && failed.load() == KML_OK) {
+        while (!cfg->histogram_enable && !debug && !no_frames && failed.load() == KML_OK) {
           const uint64_t seen = err_blk.load();
           if (seen >= cfg->max_err_blk) break;  // simulator.cc:117
           const uint64_t begin = cursor.fetch_add(chunk);

@@ -6,7 +6,7 @@
 // src/simulator.cc:3-22, src/kmcodec.cc:20-40, lib/lab/src/binaryldpccodec.cc:62-73 and lib/lab/src/modem.cc:4-9
 // (missing key → toml11 throws, as in the reference); Simulate() hands the sweep to libkmldpc_b200.so
 // (kml_sweep_run) and forwards its lines to the reference's logger, so logs and BER/FER tables look the same.
-// Optional GPU-only knobs live in a [gpu] table the CPU binary ignores: seed, gpus, batch, early_exit, algorithm.
+// Optional GPU-only knobs live in a [gpu] table the CPU binary ignores: seed, gpus, batch, early_exit, algorithm, reduce, debug.
 #ifndef KMLDPC_B200_SIMULATOR_FACADE_H
 #define KMLDPC_B200_SIMULATOR_FACADE_H
 
@@ -52,6 +52,8 @@ class Simulator {
       cfg_.max_batch = (int)toml::find_or<std::int64_t>(gpu, "batch", 0);
       cfg_.early_exit = toml::find_or<bool>(gpu, "early_exit", true) ? 1 : 0;
       cfg_.algorithm = (int)toml::find_or<std::int64_t>(gpu, "algorithm", 0);  // 1 = normalised min-sum (throughput mode)
+      cfg_.reduce_on_host = toml::find_or<std::string>(gpu, "reduce", "nccl") == "host" ? 1 : 0;
+      cfg_.debug_frames = toml::find_or<bool>(gpu, "debug", false) ? 1 : 0;  // the per-frame lines of the reference's log file
     }
   }
   virtual ~Simulator() = default;
@@ -64,7 +66,13 @@ class Simulator {
   }
 
  private:
-  static void on_line(const char *line, void *) { lab::logger::INFO(line, true); }
+  // per-frame lines go to the log file only, like the reference's INFO(…, false) (simulator.cc:126,152; kmcodec.cc:64,136)
+  static void on_line(const char *line, void *) {
+    static const char *const quiet[] = {"Generated H = ", "Current Block Number = ", "Hhat = ", "hatIndex = "};
+    bool both = true;
+    for (const char *q : quiet) both = both && std::strncmp(line, q, std::strlen(q)) != 0;
+    lab::logger::INFO(line, both);
+  }
   const toml::value arguments_;
   kml_sweep_cfg cfg_;
 };

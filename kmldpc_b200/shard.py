@@ -34,3 +34,40 @@ def ber_fer(counters) -> tuple[float, float]:
     """SourceSink::ber / fer (lib/lab/src/sourcesink.cc:43-44) from 64-bit counters."""
     tot_blk, err_blk, tot_bit, err_bit = [int(x) for x in counters[:4]]
     return (err_bit / tot_bit if tot_bit else 0.0, err_blk / tot_blk if tot_blk else 0.0)
+
+
+class CounterComm:
+    """kml_comm_init / kml_reduce_counters: the single-process flavour of the same reduction (GPUs 0 .. n-1 of this
+    process, ncclCommInitAll, ONE ncclAllReduce of uint64 words over NVLink) — what kml_sweep_run uses per SNR point."""
+
+    def __init__(self, n_gpus: int):
+        import ctypes as C
+        from . import capi
+        self._lib = capi.load()
+        self._h = C.c_void_p()
+        rc = self._lib.kml_comm_init(int(n_gpus), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"kml_comm_init: {self._lib.kml_last_error(None).decode()} (rc={rc})")
+        self.n_gpus = int(n_gpus)
+
+    def reduce(self, per_gpu):
+        """per_gpu: uint64 [n_gpus, count] → their sum, uint64 [count]."""
+        import numpy as np
+        from . import capi
+        a = np.ascontiguousarray(per_gpu, np.uint64).reshape(self.n_gpus, -1)
+        out = np.zeros(a.shape[1], np.uint64)
+        rc = self._lib.kml_reduce_counters(self._h, a.ctypes.data_as(capi.c_u64p), a.shape[1], out.ctypes.data_as(capi.c_u64p))
+        if rc != 0:
+            raise RuntimeError(f"kml_reduce_counters: {self._lib.kml_last_error(None).decode()} (rc={rc})")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self._lib.kml_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
