@@ -865,19 +865,19 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
 // kernel then runs at half its own instruction bound); a quad keeps 16, exchanges minimum / sum / the bit marginals
 // with 24 shuffles per candidate, and lets 4x more warps be resident.  Same arithmetic as demap_symbol (the sums of a
 // marginal are taken pairwise instead of sequentially).  Lane t finalises the bits j with j mod 4 == t.
-// SYM (see demap_symbol): the 64 clipped probabilities are computed for candidate 0 only, parked in the quad's row of a
-// shared-memory stage (row stride 65 words) and re-read through perm_c by the lane that owns the label in candidate c.
-template <int NC, bool SYM>
+// (Sharing the exponentials between the candidates, as demap_symbol<…, SYM> does, was measured here too: the permuted
+// re-reads through a shared-memory stage cost more than the 48 exponentials they save — 3.65 ms against 3.34 ms per 16384
+// PEG8064 frames — so the 64-point path keeps one softmax per candidate.)
+template <int NC>
 __device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float2 *s_pts, float rscale, float *lr_base,
                                                     size_t lr_stride, int t, bool valid, unsigned int &rr_a,
-                                                    unsigned int &rr_b, float *row, const DemapParams &d) {
+                                                    unsigned int &rr_b) {
   constexpr unsigned FULL = 0xffffffffu;
   const float2 ny = make_float2(-yy.x * rscale, -yy.y * rscale);
   rr_a = rr_b = 0;
 #pragma unroll
   for (int c = 0; c < NC; c++) {
     float p[16];
-    if (!SYM || c == 0) {
     float mn = 3.0e38f;
 #pragma unroll
     for (int m = 0; m < 16; m++) {
@@ -897,15 +897,6 @@ __device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float
     const float inv = dm_rcp(sum);
 #pragma unroll
     for (int m = 0; m < 16; m++) p[m] = fmaxf(p[m] * inv, kSmallProbF);
-    if (SYM && NC > 1) {
-#pragma unroll
-      for (int m = 0; m < 16; m++) row[16 * t + m] = p[m];
-      __syncwarp();
-    }
-    } else {
-#pragma unroll
-      for (int m = 0; m < 16; m++) p[m] = row[d.perm[c - 1][16 * t + m]];
-    }
     // label bit j of point k = (k >> (5 - j)) & 1 with k = 16 t + m: bits 0, 1 come from t, bits 2..5 from m (MSB first)
     float z0[6], z1[6];
     float q8[8], q4[4], q2[2];
@@ -953,7 +944,6 @@ __device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float
     rr_a |= (ra > 1.0f ? 1u : 0u) << c;  // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115), see demap_symbol
     rr_b |= (rb > 1.0f ? 1u : 0u) << c;
   }
-  if (SYM && NC > 1) __syncwarp();  // the quad's next symbol reuses the row
 }
 
 template <int BITS, int NC, bool SYM>
@@ -1007,8 +997,7 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
         const bool valid = i < d.n_sym;
         const float2 yy = yf[valid ? i : d.n_sym - 1];
         unsigned int rr_a, rr_b;
-        demap_symbol_quad64<NC, SYM>(yy, s_pts, rscale, lr0 + i * BITS, lr_stride, t, valid, rr_a, rr_b,
-                                     stage - threadIdx.x + (tid >> 2) * 65, d);
+        demap_symbol_quad64<NC>(yy, s_pts, rscale, lr0 + i * BITS, lr_stride, t, valid, rr_a, rr_b);
         if (d.hard_metric && valid) {
           s_rr[d.punct + i * BITS + t] = (unsigned char)rr_a;
           if (t < 2) s_rr[d.punct + i * BITS + t + 4] = (unsigned char)rr_b;
@@ -1442,10 +1431,10 @@ cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const f
 template <int BITS>
 static cudaError_t launch_demap_bits(const DemapParams &d, int grid, int smem, cudaStream_t s) {
   if (d.n_cand == 4) {
-    const bool sym = d.symmetric != 0;
-    // stage: one column of Q words per thread, or (64 points, a quad of lanes per symbol) one 65-word row per quad
-    if (sym) smem = ((smem + 15) & ~15) + (int)sizeof(float) * (BITS == 6 ? (DM_THREADS / 4) * 65 : (1 << BITS) * DM_THREADS);
-    auto k = sym ? demap_kernel<BITS, 4, true> : demap_kernel<BITS, 4, false>;
+    constexpr bool kCanSym = BITS <= 5;  // (64 points: the quad-of-lanes path keeps one softmax per candidate, see there)
+    const bool sym = kCanSym && d.symmetric;
+    if (sym) smem = ((smem + 15) & ~15) + (int)sizeof(float) * (1 << BITS) * DM_THREADS;  // one column of Q words per thread
+    auto k = sym ? demap_kernel<BITS, 4, kCanSym> : demap_kernel<BITS, 4, false>;
     if (smem > 48 * 1024) {  // per device: set on every large launch
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
