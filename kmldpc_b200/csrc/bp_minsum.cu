@@ -29,7 +29,7 @@ using namespace msn;
 // ---- (3,6)-regular codes: same thread/frame organisation as bp_regular_kernel
 template <int VPT, int CPT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ms_regular_kernel(const DecParams p) {
-  extern __shared__ __align__(16) uint32_t msg[];
+  extern __shared__ uint32_t msg[];
   __shared__ int s_frame;
   const int tid = threadIdx.x;
   constexpr int plane = CPT * T + 1;
@@ -174,8 +174,8 @@ __device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__
 
 template <int VPT, int CPT, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p) {
-  extern __shared__ __align__(16) uint32_t msg[];
-  __shared__ int s_pair[2][2];  // [parity of the work item][frame a / frame b]
+  extern __shared__ uint32_t msg[];
+  __shared__ int s_pair[2];
   const int tid = threadIdx.x;
   constexpr int plane = CPT * T + 1;
   uint32_t va[VPT][3];
@@ -185,53 +185,33 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
     for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[(j * T + tid) * 3 + k];
   const __half2 alpha2 = __float2half2_rn(p.alpha), clip2 = __float2half2_rn(kLlrClip), zero2 = __float2half2_rn(0.0f);
 
-  // a work item = two consecutive entries of the frame queue (the last one may be single: fb = fa)
-  auto claim = [&](int slot) {
-    const int nB = frame_count(p), fp = (int)atomicAdd(p.work_counter, 1u);
-    const int ia = 2 * fp, ib = min(2 * fp + 1, nB - 1);
-    s_pair[slot][0] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ia) : ia) : -1;
-    s_pair[slot][1] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ib) : ib) : -1;
-  };
-  auto row_of = [&](int f) { return p.in + (size_t)(p.sel ? f * p.n_cand + __ldg(p.sel + f) : f) * p.t.n_tx; };
-  // channel values of a pair travel HBM → shared memory with cp.async (no registers, no waiting thread): stage[2][n_tx]
-  float *stage = reinterpret_cast<float *>(msg + ((6 * plane + 3) & ~3));  // 16-byte aligned for cp.async
-  const int n_tx = p.t.n_tx, quads = n_tx >> 2;  // rows are 16-byte multiples (n_tx % 4 == 0 for the regular codes)
-  auto fetch = [&](int f_a, int f_b) {
-    const float *ina = row_of(f_a), *inb = row_of(f_b);
-    for (int i = tid; i < 2 * quads; i += T) {
-      const float *src = (i < quads ? ina + 4 * i : inb + 4 * (i - quads));
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + 4 * i);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+  while (true) {
+    if (tid == 0) {  // a work item = two consecutive entries of the frame queue (the last one may be single: fb = fa)
+      const int nB = frame_count(p), fp = (int)atomicAdd(p.work_counter, 1u);
+      const int ia = 2 * fp, ib = min(2 * fp + 1, nB - 1);
+      s_pair[0] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ia) : ia) : -1;
+      s_pair[1] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ib) : ib) : -1;
     }
-    asm volatile("cp.async.commit_group;");
-  };
-  if (tid == 0) claim(0);
-  __syncthreads();
-  int fa = s_pair[0][0], fb = s_pair[0][1];
-  if (fa >= 0) fetch(fa, fb);
-  for (int item = 0; fa >= 0; item++) {
-    asm volatile("cp.async.wait_group 0;");
     __syncthreads();
+    const int fa = s_pair[0], fb = s_pair[1];
+    if (fa < 0) break;
+    const float *ina = p.in + (size_t)(p.sel ? fa * p.n_cand + __ldg(p.sel + fa) : fa) * p.t.n_tx;
+    const float *inb = p.in + (size_t)(p.sel ? fb * p.n_cand + __ldg(p.sel + fb) : fb) * p.t.n_tx;
     __half2 ch[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; j++)
-      ch[j] = __floats2half2_rn(channel_llr_of(stage[j * T + tid], p.in_is_lr), channel_llr_of(stage[n_tx + j * T + tid], p.in_is_lr));
-    // the NEXT work item is claimed now and its channel values are requested as soon as the first barrier of this decode has
-    // published the claim (and freed the stage): the HBM latency of a pair hides behind the decode of the pair before it
-    // (at 5 iterations the exposed load was a fifth of a frame's time)
-    if (tid == 0) claim((item + 1) & 1);
-    int na = -1, nb = -1;
+      ch[j] = __floats2half2_rn(load_channel_llr(ina, j * T + tid, p.in_is_lr), load_channel_llr(inb, j * T + tid, p.in_is_lr));
+    for (int i = tid; i < 6 * plane; i += T) msg[i] = 0u;
+    __syncthreads();
     uint32_t bits_a = 0, bits_b = 0, lat_a = 0, lat_b = 0;
     const int ret_full = p.iters + (p.iters < p.max_iter);
     int ret_a = ret_full, ret_b = ret_full;
     bool done_a = false, done_b = false;
     for (int t = 0; t < p.iters; t++) {
       bits_a = bits_b = 0;
-      // iteration 0: every c2v is InitMsg's LLR 0 — nothing is read, every word is written (no initialisation pass)
 #pragma unroll
       for (int j = 0; j < VPT; j++) {
-        __half2 x0 = zero2, x1 = zero2, x2 = zero2;
-        if (t > 0) { x0 = u2h(msg[va[j][0]]); x1 = u2h(msg[va[j][1]]); x2 = u2h(msg[va[j][2]]); }
+        const __half2 x0 = u2h(msg[va[j][0]]), x1 = u2h(msg[va[j][1]]), x2 = u2h(msg[va[j][2]]);
         const __half2 total = __hadd2(__hadd2(__hadd2(ch[j], x0), x1), x2);
         const uint32_t pb = __hle2_mask(total, zero2) & 0x00010001u;  // decision 1 unless total > 0 (tie → 1)
         bits_a |= (pb & 1u) << j;
@@ -241,11 +221,6 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
         msg[va[j][2]] = (h2u(__hsub2(total, x2)) & 0xFFFEFFFEu) | pb;
       }
       __syncthreads();
-      if (t == 0) {  // (every thread has taken its channel values out of the stage before this barrier)
-        na = s_pair[(item + 1) & 1][0];
-        nb = s_pair[(item + 1) & 1][1];
-        if (na >= 0) fetch(na, nb);
-      }
       uint32_t fail = 0;
 #pragma unroll
       for (int j = 0; j < CPT; j++) {
@@ -288,8 +263,6 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
       p.out_ret[fa] = ret_a;
       if (fb != fa) p.out_ret[fb] = ret_b;
     }
-    fa = na;
-    fb = nb;
   }
 }
 

@@ -11,12 +11,10 @@ namespace msn {
 
 constexpr float kLlrClip = 27.631021f;  // ln((1-1e-12)/1e-12)
 
-__device__ __forceinline__ float channel_llr_of(float v, int in_is_lr) {
+__device__ __forceinline__ float load_channel_llr(const float *in, int idx, int in_is_lr) {
+  float v = __ldg(in + idx);
   if (in_is_lr) v = __logf(fminf(fmaxf(v, kLrMin), kLrMax));
   return fminf(fmaxf(v, -kLlrClip), kLlrClip);
-}
-__device__ __forceinline__ float load_channel_llr(const float *in, int idx, int in_is_lr) {
-  return channel_llr_of(__ldg(in + idx), in_is_lr);
 }
 
 template <int D>

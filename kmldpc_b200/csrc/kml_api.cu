@@ -375,7 +375,6 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     dl.rowmajor = ((alg == 0 && rowmajor) || qc_plan) ? 1 : 0;
     if (dl.kind == DEC_REG_12_6) dl.threads = dl.rowmajor ? dec_regular_threads(dl.kind) : 672;
     dl.smem_bytes = dl.rowmajor ? rm_smem : planar_smem;
-    if (dec_two_frames_per_cta(dl.kind, alg)) dl.smem_bytes += 2 * N * 4 + 16;  // cp.async stage of the pair's channel values (16-byte aligned)
     KML_CUDA(c, dec_prepare(dl));
     c->dl_alg[alg] = dl;
   }
