@@ -460,6 +460,21 @@ def gpu_arm(args):
     k1.record()
     torch.cuda.synchronize()
     km_ms = k0.elapsed_time(k1) / reps
+    # … and at config.toml's 15 dB (rank 0): the cell boundaries cross few samples there, so fewer memberships change per pass
+    km15_ms = None
+    if rank == 0:
+        y15 = [torch.empty((B, N_SYM, 2), dtype=torch.float32, device=dev) for _ in range(pool)]
+        for i in range(pool):
+            link.generate_dev(B, 15.0, 23, i * B, us[0].data_ptr(), hs.data_ptr(), y15[i].data_ptr(), stream)
+        link.generate_dev(B, SNR_DB, 17, lo, us[0].data_ptr(), hs.data_ptr(), ys[0].data_ptr(), stream)  # (us[0] restored)
+        link.kmeans_dev(B, y15[0].data_ptr(), hhat.data_ptr(), 0, stream)
+        k0.record()
+        for i in range(reps):
+            link.kmeans_dev(B, y15[i % pool].data_ptr(), hhat.data_ptr(), 0, stream)
+        k1.record()
+        torch.cuda.synchronize()
+        km15_ms = k0.elapsed_time(k1) / reps
+        del y15
     sampler.mark_end()
 
     # ---- secondary: throughput-mode decoders (NOT the reference's algorithm: normalised min-sum, gated by BER/FER tests)
@@ -587,7 +602,9 @@ def gpu_arm(args):
                                      "unit": "GB/s", "frac": hbm_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak,
                                      "note": "LLR in + packed decisions out of the standalone decoder; never binding",
                                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}},
-                "kmeans": {"frames_per_s": world * B / (km_ms * 1e-3), "ms_per_batch": km_ms, "passes": KMEANS_ITER},
+                "kmeans": {"frames_per_s": world * B / (km_ms * 1e-3), "ms_per_batch": km_ms, "passes": KMEANS_ITER, "snr_db": SNR_DB,
+                           "frames_per_s_per_gpu_at_15dB": B / (km15_ms * 1e-3) if km15_ms else None,
+                           "note": "exact-assignment kernel (fp64 estimate and sums, fp32 filter): every frame within 1e-4 of the reference"},
                 "clocks": clocks}
         if cpu:
             line["cpu_baseline"] = cpu

@@ -41,7 +41,6 @@ struct Lane {
   DevBuf<float> lr, metric, llr_io;
   DevBuf<double> soft, fsoft, chain_state;   // soft-syndrome metric: own sums of the metric / final decodes, chain values
   DevBuf<int32_t> kstar, ret, mret, passes, bits_io, chain_flags, chain_queue, chain_counts;
-  DevBuf<int32_t> km_redo;                   // [B + 1] frames the fast k-means pass hands to the exact kernel, and their count
   DevBuf<int32_t> dec_queue, dec_queue_n;    // frames the demapper hands to the decoder (the rest left at iteration 0)
   DevBuf<unsigned int> work_counter;
   DevBuf<unsigned long long> counters;  // 5 x u64: what THIS lane's batches of the current kml_simulate call counted
@@ -152,7 +151,6 @@ int alloc_lane(kml_ctx *c, Lane &l) {
   KML_CUDA(c, l.kstar.alloc(B));
   KML_CUDA(c, l.ret.alloc(B));
   KML_CUDA(c, l.mret.alloc(4 * B));
-  KML_CUDA(c, l.km_redo.alloc(B + 1));
   KML_CUDA(c, l.dec_queue.alloc(B));
   KML_CUDA(c, l.dec_queue_n.alloc(1));
   if (c->opts.metric_type) {
@@ -173,7 +171,7 @@ void free_lane(Lane &l) {
   l.u_packed.release(); l.c_packed.release(); l.uu_hat_packed.release(); l.cc_hat_packed.release();
   l.h.release(); l.y.release(); l.hhat.release(); l.noise.release(); l.lr.release(); l.metric.release();
   l.soft.release(); l.fsoft.release(); l.chain_state.release(); l.chain_flags.release(); l.chain_queue.release();
-  l.chain_counts.release(); l.mret.release(); l.dec_queue.release(); l.dec_queue_n.release(); l.km_redo.release();
+  l.chain_counts.release(); l.mret.release(); l.dec_queue.release(); l.dec_queue_n.release();
   l.llr_io.release(); l.kstar.release(); l.ret.release(); l.passes.release(); l.bits_io.release();
   l.work_counter.release(); l.counters.release();
   l.y64.release(); l.hhat64.release(); l.h64.release(); l.p0_io.release();
@@ -475,7 +473,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
   } else {
     KML_LAUNCH(c, launch_kmeans(B, y, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
-                               want_h64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, l.km_redo.p, c->num_sms, s));
+                               want_h64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, s));
     const bool decode_metric = c->is_5g || c->opts.metric_type;
     d.h = l.hhat.p; d.n_cand = 4; d.hard_metric = decode_metric ? 0 : 1;
     // hard metric: the four ratio vectors stay in shared memory and only the winner's reaches HBM — as long as that
@@ -809,7 +807,7 @@ int kmeans_host(kml_ctx *c, int B, const void *y, int y_is_f64, float *hhat, dou
     if (hhat64) KML_RC(ensure(c, l.hhat64, (size_t)c->max_batch));
     KML_CUDA(c, cudaMemcpyAsync(ydev, (const char *)y + (size_t)b0 * c->n_sym * ysz, ysz * nb * c->n_sym, cudaMemcpyHostToDevice, l.stream));
     KML_LAUNCH(c, launch_kmeans(nb, ydev, y_is_f64, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p,
-                               hhat64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, l.km_redo.p, c->num_sms, l.stream));
+                               hhat64 ? l.hhat64.p : nullptr, l.passes.p, y_is_f64 ? l.y.p : nullptr, c->num_sms, l.stream));
     if (hhat) KML_CUDA(c, cudaMemcpyAsync(hhat + (size_t)b0 * 2, l.hhat.p, sizeof(float2) * nb, cudaMemcpyDeviceToHost, l.stream));
     if (hhat64) KML_CUDA(c, cudaMemcpyAsync(hhat64 + (size_t)b0 * 2, l.hhat64.p, sizeof(double2) * nb, cudaMemcpyDeviceToHost, l.stream));
     if (passes) KML_CUDA(c, cudaMemcpyAsync(passes + b0, l.passes.p, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, l.stream));
@@ -1146,7 +1144,7 @@ namespace {
 int histogram_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int nb, double var) {
   const bool decode_metric = c->is_5g || c->opts.metric_type;
   KML_LAUNCH(c, launch_kmeans(nb, l.y.p, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, l.hhat.p, nullptr,
-                             l.passes.p, nullptr, l.km_redo.p, c->num_sms, s));
+                             l.passes.p, nullptr, c->num_sms, s));
   KML_RC(resolve_on_lane(c, l, s, nb, var));
   if (decode_metric) {
     // uu_hat as the reference leaves it: written by the LAST candidate's metric decode (kmcodec.cc:126-131,148,157)
@@ -1247,14 +1245,9 @@ extern "C" int kml_generate_dev(kml_ctx *c, int B, double snr_db, uint64_t seed,
 extern "C" int kml_kmeans_dev(kml_ctx *c, int B, const float *y, float *hhat, int32_t *passes, void *stream) {
   KML_RC(check_batch(c, B));
   if (!y || !hhat) return fail_arg(c, "kml_kmeans_dev: null buffer");
-  if (B > c->max_batch) return fail_arg(c, "kml_kmeans_dev: B exceeds max_batch");
-  Lane &l = c->lane[0];
-  cudaStream_t s = (cudaStream_t)stream;
-  KML_ENTER(c, l, s);  // (the redo list of the two-tier scheme is lane scratch)
+  KML_CUDA(c, cudaSetDevice(c->device));  // (no scratch: reads y, writes hhat / passes)
   KML_LAUNCH(c, launch_kmeans(B, y, 0, c->n_sym, c->points.p, c->Q, c->km, c->opts.kmeans_iter, (float2 *)hhat, nullptr,
-                             passes, nullptr, l.km_redo.p, c->num_sms, s));
-  c->launches += 1;
-  KML_LEAVE(c, l, s);
+                             passes, nullptr, c->num_sms, (cudaStream_t)stream));
   return KML_OK;
 }
 

@@ -113,10 +113,8 @@ struct KmConst {
 };
 // y: float2 [B][n_sym], or double2 when y_is_f64 (then y32_out, if given, receives the fp32 copy the demapper reads).
 // hhat64 (optional): the estimate as carried (fp64).
-// redo (optional, int32 [B + 1] device scratch): enables the two-tier scheme for fp32 input — a plain-fp32 pass with a
-// margin test on every frame, the exact kernel only on the frames listed in redo by the first (see kmeans_fast_kernel).
 cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
-                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int32_t *redo,
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out,
                           int num_sms, cudaStream_t s);
 cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream_t s);
 cudaError_t launch_p0_to_lr(size_t n, const double *p0, float *lr, cudaStream_t s);

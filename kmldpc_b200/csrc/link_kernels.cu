@@ -425,133 +425,11 @@ __device__ __forceinline__ double km_warp_sum(double v) {
   return v;
 }
 
-// FIRST TIER (fp32 input).  The same pass in plain fp32 — per-pass sums in fp32, cumulative sums in fp64 — plus ONE
-// extra instruction per sample that tracks the smallest |d| the frame ever saw.  As long as every |d| exceeds the band
-// tau (which covers the fp32 error of the estimate itself and of the test), every assignment equals the exact kernel's,
-// by induction over the passes, and the estimate differs from the exact one by fp32 summation noise only (~1e-7).  A
-// frame that came within the band anywhere is appended to `redo` and recomputed by kmeans_warp_kernel (a few per cent
-// of the frames); everything else never pays for fp64.
-template <int SPL, int MAXNB>
-__global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 24 ? 6 : (SPL <= 36 ? 5 : (SPL <= 48 ? 4 : 3)))
-kmeans_fast_kernel(int B, const float2 *y, int n, const KmConst kc, int iters, float2 *hhat_out, int32_t *passes_out,
-                   int32_t *redo, int32_t *redo_n) {
-  static_assert(MAXNB % 2 == 0, "neighbours are tested in pairs");
-  constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
-  const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
-  const float is0r = (float)kc.is0r, is0i = (float)kc.is0i;
-  float2 snb[MAXNB];
-#pragma unroll
-  for (int t = 0; t < MAXNB; t++)
-    snb[t] = make_float2((float)(kc.s0r + kc.dsr[t < kc.n_nb ? t : 0]), (float)(kc.s0i + kc.dsi[t < kc.n_nb ? t : 0]));
-  for (int f = wglobal; f < B; f += wstride) {
-    const float2 *yf = y + (size_t)f * n;
-    float2 ys[SPL];
-    unsigned long long best = 0ull;
-    float a2top = 0.f, a2next = 0.f;  // the two largest |y|^2 (values only; the key carries the index of the largest)
-    // padded samples are NaN: every d of theirs is NaN, which fails "d <= 0" and drops out of fminf / fmaxf
-    const float qnan = __int_as_float(0x7fc00000);
-#pragma unroll
-    for (int j = 0; j < SPL; j++) {
-      const int i = j * 32 + lane;
-      if (i < n) {
-        ys[j] = yf[i];
-        const float a2 = fmaf(ys[j].y, ys[j].y, ys[j].x * ys[j].x);
-        const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
-        best = key > best ? key : best;
-        a2next = fmaxf(a2next, fminf(a2, a2top));
-        a2top = fmaxf(a2top, a2);
-      } else {
-        ys[j] = make_float2(qnan, qnan);
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long ob = __shfl_xor_sync(FULL, best, o);
-      best = ob > best ? ob : best;
-      const float ot = __shfl_xor_sync(FULL, a2top, o), on = __shfl_xor_sync(FULL, a2next, o);
-      a2next = fmaxf(fmaxf(a2next, on), fminf(a2top, ot));
-      a2top = fmaxf(a2top, ot);
-    }
-    const float amax2 = a2top;
-    // the anchor must be THE largest sample: if the runner-up is within fp32's resolution of it, let the exact kernel decide
-    bool unsure = a2next >= amax2 * (1.0f - 2.0e-6f);
-    const float ymax_l1 = 1.4142137f * sqrtf(amax2);
-    const float2 ya = yf[0x7fffffff - (int)(uint32_t)(best & 0xffffffffu)];
-    float hr = ya.x * is0r - ya.y * is0i, hi = ya.x * is0i + ya.y * is0r;  // y_a / s_0
-    double cum_cnt = 0.0, cum_re = 0.0, cum_im = 0.0;  // cumulative over passes (never reset: kmeans.cc:33-34 as compiled)
-    float prev_r = 0.f, prev_i = 0.f, margin = 3.0e38f;
-    bool have_prev = false;
-    int passes = 0;
-    for (int it = 0; it < iters; it++) {
-      passes++;
-      const float2 c0 = make_float2(s0f.x * hr - s0f.y * hi, s0f.x * hi + s0f.y * hr);
-      const float n0 = c0.x * c0.x + c0.y * c0.y;
-      float2 ax[MAXNB / 2], ay[MAXNB / 2], nth[MAXNB / 2];
-      float cmax2 = n0;
-#pragma unroll
-      for (int t = 0; t < MAXNB; t++) {
-        const float2 ck = make_float2(snb[t].x * hr - snb[t].y * hi, snb[t].x * hi + snb[t].y * hr);
-        const float nk = ck.x * ck.x + ck.y * ck.y;
-        cmax2 = fmaxf(cmax2, nk);
-        const bool used = t < kc.n_nb;
-        const float axx = used ? ck.x - c0.x : 0.f, ayy = used ? ck.y - c0.y : 0.f;
-        const float nt = used ? -0.5f * (nk - n0) : -3.0e38f;
-        if (t & 1) { ax[t / 2].y = axx; ay[t / 2].y = ayy; nth[t / 2].y = nt; }
-        else { ax[t / 2].x = axx; ay[t / 2].x = ayy; nth[t / 2].x = nt; }
-      }
-      const float cmax = sqrtf(cmax2);
-      // the margin is compared in units of this pass's band, so that one running minimum serves all passes
-      const float inv_tau = __fdividef(1.0f, 4.0e-6f * cmax * (ymax_l1 + cmax));
-      float cnt = 0.f, sr = 0.f, si = 0.f, dmin = 3.0e38f;
-#pragma unroll
-      for (int j = 0; j < SPL; j++) {
-        float dmax = 0.f;
-#pragma unroll
-        for (int t = 0; t < MAXNB / 2; t++) {
-          const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_fma2(ay[t], make_float2(ys[j].y, ys[j].y), nth[t]));
-          dmax = t == 0 ? fmaxf(v.x, v.y) : fmaxf(dmax, fmaxf(v.x, v.y));  // (a padded sample: NaN throughout)
-        }
-        dmin = fminf(dmin, fabsf(dmax));  // fminf drops the NaN of a padded sample
-        if (dmax <= 0.0f) {
-          cnt += 1.f;
-          sr += ys[j].x;
-          si += ys[j].y;
-        }
-      }
-      margin = fminf(margin, dmin * inv_tau);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(FULL, cnt, o);
-        sr += __shfl_xor_sync(FULL, sr, o);
-        si += __shfl_xor_sync(FULL, si, o);
-      }
-      cum_cnt += (double)cnt;
-      cum_re += (double)sr;
-      cum_im += (double)si;
-      if (have_prev && prev_r == hr && prev_i == hi) break;  // clusters_ == tempClusters (kmeans.cc:47-56)
-      prev_r = hr;
-      prev_i = hi;
-      have_prev = true;
-      const float inv = __fdividef(1.0f, (float)cum_cnt);  // cluster 0 is never empty: the anchor sample sits on c_0
-      const float mr = (float)cum_re * inv, mi = (float)cum_im * inv;
-      hr = mr * is0r - mi * is0i;
-      hi = mr * is0i + mi * is0r;
-    }
-    // A frame that left early (its fp32 estimate repeated: every pass since has had the same member set and the cumulative
-    // mean has stopped moving at fp32 resolution) skipped passes in which the exact estimate would still have crept by up
-    // to ~1e-6: it is vouched for only with twice the band to spare.
-    unsure = unsure || margin <= (passes < iters ? 2.0f : 1.0f);
-    if (__any_sync(FULL, unsure)) {
-      if (lane == 0) redo[atomicAdd(redo_n, 1)] = f;
-    } else if (lane == 0) {
-      hhat_out[f] = make_float2(hr, hi);
-      if (passes_out) passes_out[f] = passes;
-    }
-  }
-}
-
+// (Measured and dropped: a first tier in plain fp32 with a margin test — frames that never came within the band are
+// provably assigned like the exact kernel's — followed by this kernel on the rest.  The fp32 pass alone took 131 us per
+// 16384 PEG2304 frames against 165 us for this kernel on all of them, but the 2.5 % of frames it handed over cost a 46 us
+// tail (one warp per frame, twenty dependent passes: the tail is one frame's latency however few frames there are), and
+// at -5 dB, where 40 % of the frames touch the band, the pair was slower than this kernel alone: 316 us against 277 us.)
 template <int SPL>
 struct KmMask {  // one membership bit per sample of the lane
   uint32_t lo = 0, hi = 0;
@@ -566,21 +444,20 @@ struct KmMask {  // one membership bit per sample of the lane
 };
 
 template <int SPL, int MAXNB, bool F64IN>
+// (CTAs per SM for 36 samples per lane: 4 measured best — 167 us per 16384 frames at 15 dB against 181 with 3 and 183 with 5)
 __global__ void __launch_bounds__(KMW_WARPS * 32, SPL <= 16 ? 6 : (SPL <= 24 ? 5 : (SPL <= 36 ? 4 : (SPL <= 48 ? 3 : 2))))
 kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, float2 *hhat_out, double2 *hhat64_out,
-                   int32_t *passes_out, float2 *y32_out, const int32_t *queue, const int32_t *queue_n) {
+                   int32_t *passes_out, float2 *y32_out) {
   static_assert(MAXNB % 2 == 0 && SPL <= 64, "neighbours are tested in pairs; one mask bit per sample");
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
-  if (queue) B = min(B, __ldg(queue_n));  // second tier: only the frames the fast kernel could not vouch for
   const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
   float2 snb[MAXNB];
 #pragma unroll
   for (int t = 0; t < MAXNB; t++)
     snb[t] = make_float2((float)(kc.s0r + kc.dsr[t < kc.n_nb ? t : 0]), (float)(kc.s0i + kc.dsi[t < kc.n_nb ? t : 0]));
-  for (int fi = wglobal; fi < B; fi += wstride) {
-    const int f = queue ? __ldg(queue + fi) : fi;
+  for (int f = wglobal; f < B; f += wstride) {
     const float2 *yf = reinterpret_cast<const float2 *>(y_in) + (size_t)f * n;
     const double2 *yd = reinterpret_cast<const double2 *>(y_in) + (size_t)f * n;
     auto exact = [&](int j, float2 v) -> double2 {  // the input value itself, as the reference sees it
@@ -1360,11 +1237,10 @@ cudaError_t launch_f64_to_f32(size_t n, const double *in, float *out, cudaStream
 
 template <bool F64IN>
 static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmConst &kc, int iters, float2 *hhat,
-                                      double2 *hhat64, int32_t *passes, float2 *y32_out, const int32_t *queue,
-                                      const int32_t *queue_n, int num_sms, cudaStream_t s) {
+                                      double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms, cudaStream_t s) {
   const int spl = (n_sym + 31) / 32;
   const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
-#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, queue, queue_n)
+#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out)
   if (kc.n_nb <= 2) {
     if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
   } else if (kc.n_nb <= 4) {
@@ -1376,37 +1252,13 @@ static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmC
   return cudaGetLastError();
 }
 
-static cudaError_t launch_kmeans_fast(int B, const float2 *y, int n_sym, const KmConst &kc, int iters, float2 *hhat,
-                                      int32_t *passes, int32_t *redo, int32_t *redo_n, int num_sms, cudaStream_t s) {
-  const int spl = (n_sym + 31) / 32;
-  const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
-#define KMF(SPL, NB) kmeans_fast_kernel<SPL, NB><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, passes, redo, redo_n)
-  if (kc.n_nb <= 2) {
-    if (spl <= 16) KMF(16, 2); else if (spl <= 24) KMF(24, 2); else if (spl <= 36) KMF(36, 2); else if (spl <= 48) KMF(48, 2); else KMF(64, 2);
-  } else if (kc.n_nb <= 4) {
-    if (spl <= 16) KMF(16, 4); else if (spl <= 24) KMF(24, 4); else if (spl <= 36) KMF(36, 4); else if (spl <= 48) KMF(48, 4); else KMF(64, 4);
-  } else {
-    if (spl <= 16) KMF(16, 8); else if (spl <= 24) KMF(24, 8); else if (spl <= 36) KMF(36, 8); else if (spl <= 48) KMF(48, 8); else KMF(64, 8);
-  }
-#undef KMF
-  return cudaGetLastError();
-}
-
 cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const float2 *points, int q, const KmConst &kc,
-                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out, int32_t *redo,
+                          int iters, float2 *hhat, double2 *hhat64, int32_t *passes, float2 *y32_out,
                           int num_sms, cudaStream_t s) {
   if (B < 1) return cudaSuccess;
   if (kc.n_nb >= 1 && kc.n_nb <= 8 && n_sym <= 32 * 64) {  // warp per frame, Voronoi-neighbour half-plane tests
-    if (y_is_f64)
-      return launch_kmeans_warp<true>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, nullptr, nullptr, num_sms, s);
-    if (!redo || hhat64)  // no scratch for the two-tier scheme (or the fp64 estimate is wanted): exact kernel on every frame
-      return launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, hhat64, passes, nullptr, nullptr, nullptr, num_sms, s);
-    // two tiers: plain fp32 with a margin test on every frame, then the exact kernel on the frames that came within the band
-    cudaError_t e = cudaMemsetAsync(redo + B, 0, sizeof(int32_t), s);  // redo[0..B) = list, redo[B] = its length
-    if (e != cudaSuccess) return e;
-    e = launch_kmeans_fast(B, reinterpret_cast<const float2 *>(y), n_sym, kc, iters, hhat, passes, redo, redo + B, num_sms, s);
-    if (e != cudaSuccess) return e;
-    return launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, nullptr, passes, nullptr, redo, redo + B, num_sms, s);
+    return y_is_f64 ? launch_kmeans_warp<true>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out, num_sms, s)
+                    : launch_kmeans_warp<false>(B, y, n_sym, kc, iters, hhat, hhat64, passes, nullptr, num_sms, s);
   }
   // general fallback (constellations whose first point has more than 8 Voronoi neighbours, very long frames): one CTA
   // per frame, full distance comparison in fp32 against every constellation point

@@ -76,7 +76,7 @@ def test_kmeans_channel_estimate(name, frames):
     pts = olink.modem.points
     ref32 = np.array([util.ko.kmeans(yy.astype(np.complex128), pts)[0][0] / pts[0] for yy in y32])
     rel32 = np.abs(h32.astype(np.complex128) - ref32) / np.abs(ref32)
-    assert rel32.max() <= 5e-6, rel32.max()          # identical assignments; what is left is fp32 summation / output rounding
+    assert rel32.max() <= 5e-7, rel32.max()          # identical assignments; what is left is the fp32 rounding of the output
     # … and within the stated 1e-4 of the reference's fp64 run except where rounding the INPUT to fp32 moved a sample
     # across a cell boundary (about one frame in 10^4)
     rel_in = np.abs(h32.astype(np.complex128) - ref) / np.abs(ref)
