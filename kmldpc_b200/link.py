@@ -287,6 +287,11 @@ class Link:
                       C.cast(uu_ptr, capi.c_u32p), None, None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None, None),
                     "kml_receive")
 
+    def receive_f64_raw(self, B: int, y_ptr: int, var: float, uu_ptr: int, ret_ptr: int = 0):
+        """kml_receive_f64 on host pointers given as integers (pinned complex128 symbols): no wrapping, no allocation."""
+        self._check(self._lib.kml_receive_f64(self._h, B, C.cast(y_ptr, capi.c_f64p), None, var, C.cast(uu_ptr, capi.c_u32p), None,
+                                              None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None, None), "kml_receive_f64")
+
     def count_errors(self, u_packed: np.ndarray, uu_hat_packed: np.ndarray):
         u = np.ascontiguousarray(u_packed, np.uint32).reshape(-1, self.k_words)
         uh = np.ascontiguousarray(uu_hat_packed, np.uint32).reshape(-1, self.k_words)

@@ -28,7 +28,7 @@ for r in rows[2:]:
 # mangled-name fragment to find the function in the cubin
 with tempfile.TemporaryDirectory() as d:
     subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, capture_output=True)
-    cub = [f for f in os.listdir(d) if f.startswith(stem + ".") and f.endswith(".cubin")][0]
+    cub = [f for f in os.listdir(d) if f.startswith(stem + ".sm_") and f.endswith(".cubin")][0]
     dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout
 # candidate functions: same instruction count and same opcode sequence as the profiled kernel
 funcs, cur, name, line = {}, None, None, 0
