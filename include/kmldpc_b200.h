@@ -100,6 +100,9 @@ const char *kml_last_error(const kml_ctx *ctx);  /* ctx may be NULL: message of 
 int kml_set_early_exit(kml_ctx *ctx, int early_exit);
 /* Switches the decoder of every later call (also the 5G metric decodes); alpha = min-sum normalisation in (0, 1]. */
 int kml_set_algorithm(kml_ctx *ctx, int algorithm, double alpha);
+/* Check-node rule of the min-sum decoders (algorithm 1 | 2): |c2v| = max(alpha * min - beta, 0).  alpha = 0.8, beta = 0 is
+ * the normalised min-sum kml_set_algorithm selects; alpha = 1, beta = 0.5 the offset min-sum.  Not in the reference. */
+int kml_set_minsum(kml_ctx *ctx, double alpha, double beta);
 /* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
 int kml_info(const kml_ctx *ctx, int32_t info[8]);
 /* Decoder launch facts: info[0..7] = kernel kind (bits 0-7: 0/1 = (3,6)-regular PEG2304 / PEG8064 shapes, 2-4 = run-time

@@ -58,6 +58,7 @@ SYMBOLS = {
     "kml_last_error": (C.c_char_p, [C.c_void_p]),
     "kml_set_early_exit": (C.c_int, [C.c_void_p, C.c_int]),
     "kml_set_algorithm": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "kml_set_minsum": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "kml_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_decoder_info": (C.c_int, [C.c_void_p, c_i32p]),
     "kml_measure_smem_bandwidth": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

@@ -771,7 +771,7 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
         constexpr int j = decltype(jc)::value, D = P::cdeg[Q][j];
         float unused;
         uint32_t *row = msg + (P::cblk[Q][j] * P::Z + z) * P::RS;
-        fail += (int)((ALG == 0 ? cn_node<D, false>(row, &unused) : msn::ms_cn<D>(row, 1, 0, p.alpha)) & 1u);
+        fail += (int)((ALG == 0 ? cn_node<D, false>(row, &unused) : msn::ms_cn<D>(row, 1, 0, p.alpha, p.beta)) & 1u);
       });
       nfail = fail;
       const int any_fail = __syncthreads_or(fail);

@@ -8,7 +8,8 @@
 // by BER/FER against the sum-product decoder (tests/test_gpu_minsum.py).
 //
 //   VN   total = L_ch + sum_e c2v_e ;  v2c_e = total - c2v_e ;  decision = (total > 0) ? 0 : 1      (LLR = ln P0/P1)
-//   CN   c2v_e = alpha * min_{e' != e} |v2c_e'| * prod_{e' != e} sign(v2c_e'), clipped to +-27.63 (the reference's clip)
+//   CN   c2v_e = max(alpha * min_{e' != e} |v2c_e'| - beta, 0) * prod_{e' != e} sign(v2c_e'), clipped to +-27.63 (the
+//        reference's clip): normalised min-sum (alpha = 0.8, beta = 0, the default), offset min-sum (alpha = 1, beta > 0)
 //
 // A v2c word is the float itself with mantissa bit 0 replaced by the variable's posterior decision (an LLR does not need
 // its last bit), so a check node gets sign parity and the syndrome of the current decisions from one XOR chain.
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(T, MINB) ms_regular_kernel(const DecParams p) 
       __syncthreads();
       uint32_t x = 0;
 #pragma unroll
-      for (int j = 0; j < CPT; j++) x |= ms_cn<6>(msg, plane, j * T + tid, p.alpha);
+      for (int j = 0; j < CPT; j++) x |= ms_cn<6>(msg, plane, j * T + tid, p.alpha, p.beta);
       const int any_fail = __syncthreads_or((int)(x & 1u));
       if (!any_fail && !latched) {
         latched = true;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(T, MINB) ms_regular_kernel(const DecParams p) 
     break;
 #define KML_MS_CN_CASE(D)                                           \
   case D:                                                           \
-    if (D <= DC) x = ms_cn<(D <= DC ? D : 1)>(msg, plane, slot, p.alpha); \
+    if (D <= DC) x = ms_cn<(D <= DC ? D : 1)>(msg, plane, slot, p.alpha, p.beta); \
     break;
 
 template <int DV, int DC>
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
 #pragma unroll
     for (int k = 0; k < 3; k++) va[j][k] = p.t.vn_addr[(j * T + tid) * 3 + k];
   const __half2 alpha2 = __float2half2_rn(p.alpha), clip2 = __float2half2_rn(kLlrClip), zero2 = __float2half2_rn(0.0f);
+  const __half2 nbeta2 = __float2half2_rn(-p.beta);
+  const bool has_offset = p.beta != 0.0f;
 
   while (true) {
     if (tid == 0) {  // a work item = two consecutive entries of the frame queue (the last one may be single: fb = fa)
@@ -236,7 +239,10 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
           m1 = __hmin2(m1, a[k]);
         }
         fail |= x;
-        const uint32_t s1 = h2u(__hmin2(__hmul2(alpha2, m1), clip2)), s2 = h2u(__hmin2(__hmul2(alpha2, m2), clip2));
+        // max(alpha m - beta, 0) clipped: one HFMA2 (FMA pipe) + max + min per minimum
+        __half2 t1 = __hfma2(alpha2, m1, nbeta2), t2 = __hfma2(alpha2, m2, nbeta2);
+        if (has_offset) { t1 = __hmax2(t1, zero2); t2 = __hmax2(t2, zero2); }  // (uniform: the normalised rule never goes negative)
+        const uint32_t s1 = h2u(__hmin2(t1, clip2)), s2 = h2u(__hmin2(t2, clip2));
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           const uint32_t eq = __heq2_mask(a[k], m1);

@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t ms_vn(uint32_t *msg, const uint32_t *a, floa
 
 // returns the XOR of the row's words: bit 31 = sign parity, bit 0 = syndrome of the current decisions
 template <int D>
-__device__ __forceinline__ uint32_t ms_cn(uint32_t *msg, int plane, int slot, float alpha) {
+__device__ __forceinline__ uint32_t ms_cn(uint32_t *msg, int plane, int slot, float alpha, float beta = 0.0f) {
   uint32_t w[D], x = 0;
   float m1 = 3.0e38f, m2 = 3.0e38f, a[D];
 #pragma unroll
@@ -44,7 +44,8 @@ __device__ __forceinline__ uint32_t ms_cn(uint32_t *msg, int plane, int slot, fl
     m2 = fminf(m2, fmaxf(m1, a[k]));
     m1 = fminf(m1, a[k]);
   }
-  const float s1 = fminf(alpha * m1, kLlrClip), s2 = fminf(alpha * m2, kLlrClip);
+  // normalised (beta = 0) / offset (alpha = 1) / both: magnitude = max(alpha m - beta, 0), clipped like the reference's messages
+  const float s1 = fminf(fmaxf(fmaf(alpha, m1, -beta), 0.0f), kLlrClip), s2 = fminf(fmaxf(fmaf(alpha, m2, -beta), 0.0f), kLlrClip);
 #pragma unroll
   for (int k = 0; k < D; k++) {
     const float mag = (a[k] == m1) ? s2 : s1;  // ties at the minimum: m2 == m1, either choice gives the same value

@@ -76,7 +76,7 @@ struct kml_ctx {
   DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
   DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
   DecLaunch dl_soft{};          // sum-product kernel that also produces the soft-syndrome sums (metric_type = true)
-  float alpha = 0.8f;
+  float alpha = 0.8f, beta = 0.0f;  // min-sum: normalisation and offset
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
@@ -399,7 +399,7 @@ DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t 
   p.in = in; p.sel = sel; p.n_cand = n_cand; p.in_is_lr = in_is_lr;
   p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
   p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
-  p.work_counter = l.work_counter.p; p.words_n = c->words_n; p.alpha = c->alpha;
+  p.work_counter = l.work_counter.p; p.words_n = c->words_n; p.alpha = c->alpha; p.beta = c->beta;
   return p;
 }
 
@@ -678,8 +678,17 @@ extern "C" int kml_set_algorithm(kml_ctx *c, int algorithm, double alpha) {
   if (algorithm != 0 && c->opts.metric_type) return fail_arg(c, "kml_set_algorithm: soft-syndrome metric needs sum-product");
   if (algorithm != 0 && !(alpha > 0.0 && alpha <= 1.0)) return fail_arg(c, "kml_set_algorithm: alpha must be in (0, 1]");
   c->opts.algorithm = algorithm;
-  if (algorithm != 0) c->alpha = (float)alpha;
+  if (algorithm != 0) { c->alpha = (float)alpha; c->beta = 0.0f; }
   c->dl = c->dl_alg[algorithm];
+  return KML_OK;
+}
+
+extern "C" int kml_set_minsum(kml_ctx *c, double alpha, double beta) {
+  if (!c) return KML_ERR_ARG;
+  if (!(alpha > 0.0 && alpha <= 1.0) || !(beta >= 0.0 && beta < 27.0))
+    return fail_arg(c, "kml_set_minsum: alpha must be in (0, 1], beta in [0, 27)");
+  c->alpha = (float)alpha;
+  c->beta = (float)beta;
   return KML_OK;
 }
 

@@ -39,7 +39,7 @@ struct DecParams {
                             // kernels dec_has_synd_output() names fill it
   unsigned int *work_counter;  // dynamic frame scheduler (zeroed by the launcher)
   int words_n;
-  float alpha;              // min-sum normalisation (algorithm = 1 only)
+  float alpha, beta;        // min-sum: magnitude = max(alpha m - beta, 0) (algorithm = 1 | 2)
   // optional frame queue: entry i of the queue decodes frame frame_idx[i]; the queue length is *n_frames_dev (written by
   // an earlier kernel of the stream; B is then only the upper bound the grid is sized for).  Inputs and outputs stay
   // indexed by the frame number, so a queue is just a subset / an order of the batch.

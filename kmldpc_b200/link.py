@@ -142,6 +142,10 @@ class Link:
         """0 = sum-product (the reference's decoder), 1 = normalised min-sum (throughput mode, not reference-pinned)."""
         self._check(self._lib.kml_set_algorithm(self._h, int(algorithm), float(alpha)), "kml_set_algorithm")
 
+    def set_minsum(self, alpha: float = 0.8, beta: float = 0.0):
+        """Check-node rule of the min-sum decoders: |c2v| = max(alpha * min - beta, 0) (normalised / offset / both)."""
+        self._check(self._lib.kml_set_minsum(self._h, float(alpha), float(beta)), "kml_set_minsum")
+
     # ---- stages (host buffers)
     def encode(self, u: np.ndarray) -> np.ndarray:
         u = np.ascontiguousarray(u, np.int32).reshape(-1, self.code.K)

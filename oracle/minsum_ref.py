@@ -5,7 +5,8 @@ algorithm itself is gated by BER/FER against the sum-product oracle (tests/test_
 
 Schedule, stopping rule and return value are the reference decoder's (binaryldpccodec.cc:175-277); only the node
 updates differ:  VN  total = L_ch + sum c2v,  v2c_e = total - c2v_e,  bit = (total > 0) ? 0 : 1
-                 CN  c2v_e = alpha * min_{e' != e} |v2c_e'| * prod sign,  clipped to +-ln((1-1e-12)/1e-12)."""
+                 CN  c2v_e = max(alpha * min_{e' != e} |v2c_e'| - beta, 0) * prod sign,  clipped to +-ln((1-1e-12)/1e-12)
+                     (normalised: beta = 0; offset: alpha = 1, beta > 0)."""
 from __future__ import annotations
 
 import numpy as np
@@ -14,7 +15,7 @@ f32 = np.float32
 LLR_CLIP = f32(27.631021)
 
 
-def decode(row_ptr, col_idx, n_graph, punct, llr, iters, max_iter, alpha=0.8):
+def decode(row_ptr, col_idx, n_graph, punct, llr, iters, max_iter, alpha=0.8, beta=0.0):
     """llr [B, n_tx] float32 (ln P0/P1).  Returns ret[B], cc_hat[B, n_graph]."""
     rp, ci = np.asarray(row_ptr), np.asarray(col_idx)
     M, E = len(rp) - 1, len(ci)
@@ -26,7 +27,7 @@ def decode(row_ptr, col_idx, n_graph, punct, llr, iters, max_iter, alpha=0.8):
     ret = np.full(B, iters + (1 if iters < max_iter else 0), np.int32)
     done = np.zeros(B, bool)
     out = np.zeros((B, n_graph), np.int8)
-    alpha = f32(alpha)
+    alpha, beta = f32(alpha), f32(beta)
     for t in range(iters):
         total = ch.copy()
         np.add.at(total, (slice(None), ci), c2v)
@@ -49,8 +50,8 @@ def decode(row_ptr, col_idx, n_graph, punct, llr, iters, max_iter, alpha=0.8):
             srt = np.sort(m, axis=1)
             min1, min2 = srt[:, :1], srt[:, 1:2] if b - a > 1 else srt[:, :1]
             par = np.logical_xor.reduce(neg[:, a:b], axis=1, keepdims=True)
-            o = np.where(m == min1, min2, min1) * alpha
-            o = np.minimum(o, LLR_CLIP)
+            o = np.where(m == min1, min2, min1).astype(np.float64) * np.float64(alpha) - np.float64(beta)  # (one rounding, like fmaf)
+            o = np.minimum(np.maximum(o.astype(f32), f32(0)), LLR_CLIP)
             sgn = par ^ neg[:, a:b]
             new[:, a:b] = np.where(sgn, -o, o)
         c2v = np.where(done[:, None], c2v, new).astype(f32)

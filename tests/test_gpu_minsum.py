@@ -50,6 +50,31 @@ def test_minsum_ber_fer_gate_against_sum_product(name, snr, frames):
     link.close()
 
 
+@pytest.mark.parametrize("alg", [1, 2])
+def test_offset_minsum_variant(alg):
+    """|c2v| = max(alpha m - beta, 0) with alpha = 1, beta = 0.5 (offset min-sum): the fp32 kernel against the numpy statement,
+    and both message formats against the sum-product decoder on the same frames (BER/FER gate)."""
+    name, snr, frames = "peg2304_4psk_6db", 6.0, 30000
+    link = util.gpu_link(name, max_batch=8192)
+    spa, _ = link.simulate(snr, frames, seed=41)
+    link.set_algorithm(alg, 0.8)
+    link.set_minsum(1.0, 0.5)
+    ms, _ = link.simulate(snr, frames, seed=41)
+    fer_spa, fer_ms = spa[1] / spa[0], ms[1] / ms[0]
+    sd = np.sqrt(fer_spa * (1 - fer_spa) / frames)
+    assert fer_spa - 3 * sd - 0.005 <= fer_ms <= fer_spa + 3 * sd + 0.015, (fer_ms, fer_spa)
+    if alg == 1:
+        olink, rs = util.oracle_frames(name, 120)
+        ex = olink.code.export(with_enc=False)
+        llr = np.stack([util.llr_of_p0(r.p0) for r in rs]).astype(np.float32)
+        cc, uu, ret = link.decode(llr)
+        rret, rcc = minsum_ref.decode(ex["row_ptr"], ex["col_idx"], olink.code.N, olink.code.two_z, llr, 50, 50, alpha=1.0, beta=0.5)
+        assert (ret == rret).mean() >= 0.95
+        both = (ret == rret) & (rret < 50)
+        assert both.sum() > 0 and np.array_equal(cc[both], rcc[both])
+    link.close()
+
+
 def test_minsum_rejects_soft_metric():
     import kmldpc_b200 as kb
     code, mod = kb.LdpcCode("PEG2304regular0.5.txt"), kb.Modem("2bits_4PSK.txt")
