@@ -720,6 +720,7 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
 #pragma unroll
       for (int k = 0; k < Q; k++) p[k] = stage[d.perm[c - 1][k] * DM_THREADS];
     }
+    float ratio[BITS];
 #pragma unroll
     for (int j = 0; j < BITS; j++) {
       float z0 = 0.f, z1 = 0.f;
@@ -728,11 +729,18 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
         if (((k >> (BITS - 1 - j)) & 1) == 0) z0 += p[k];
         else z1 += p[k];
       }
-      const float ratio = fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax);
-      lr_base[c * lr_stride + j] = ratio;
+      ratio[j] = fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax);
       // rr = (P0 > 0.5) ? 1 : 0 — inverted on purpose (kmcodec.cc:110-115); taken from the ratio as stored, so that it
       // is exactly the complement of the decision the decoder makes from that ratio at iteration 0 (post > 1 ? 0 : 1)
-      rr[j] |= (ratio > 1.0f ? 1u : 0u) << c;
+      rr[j] |= (ratio[j] > 1.0f ? 1u : 0u) << c;
+    }
+    // a symbol's BITS ratios are contiguous and BITS * 4 bytes aligned (rows are n_sym * BITS floats): one wide store
+    float *dst = lr_base + c * lr_stride;
+    if constexpr (BITS == 2) *reinterpret_cast<float2 *>(dst) = make_float2(ratio[0], ratio[1]);
+    else if constexpr (BITS == 4) *reinterpret_cast<float4 *>(dst) = make_float4(ratio[0], ratio[1], ratio[2], ratio[3]);
+    else {
+#pragma unroll
+      for (int j = 0; j < BITS; j++) dst[j] = ratio[j];
     }
   }
 }

@@ -80,6 +80,22 @@ def test_config_toml_parsing_matches_reference_keys(tmp_path):
     # (unsigned long)((max - min) / step + 1), simulator.cc:27
     sim2 = kb.Simulator(os.path.join(ROOT, "config", "config.toml"), min_snr=0.0, max_snr=30.0, step_snr=5.0)
     assert sim2.n_points == 7
+    # the optional [gpu] table (ignored by the reference binary): defaults, then every key
+    assert (c.reduce_on_host, c.debug_frames, c.early_exit, c.algorithm, c.max_batch) == (0, 0, 1, 0, 0)
+    full = tmp_path / "gpu.toml"
+    full.write_text(open(os.path.join(ROOT, "config", "config.toml")).read() +
+                    '\n[gpu]\nseed = 99\ngpus = 4\nbatch = 4096\nearly_exit = false\nalgorithm = 1\nreduce = "host"\ndebug = true\n')
+    g = kb.Simulator(str(full)).cfg
+    assert (g.seed, g.n_gpus, g.max_batch, g.early_exit, g.algorithm, g.reduce_on_host, g.debug_frames) == (99, 4, 4096, 0, 1, 1, 1)
+
+
+@pytest.mark.gpu
+def test_sweep_with_zero_error_budget_runs_nothing_like_the_reference(tmp_path):
+    """maximum_error_number = 0: simulator.cc:117 leaves before the first frame (err_blk >= 0 holds at once)."""
+    cfg = tmp_path / "z.toml"
+    cfg.write_text(open(os.path.join(ROOT, "config", "config.toml")).read().replace("maximum_error_number = 1", "maximum_error_number = 0"))
+    snr, ber, fer, cnt = kb.Simulator(str(cfg), data_dir=os.path.join(ROOT, "config")).simulate(echo=False)
+    assert cnt[0, 0] == 0 and np.isnan(ber[0]) and np.isnan(fer[0])
 
 
 def test_no_cpu_fallback_without_gpu():
