@@ -174,6 +174,16 @@ int kml_decode_p0(kml_ctx *ctx, int B, const double *p0, int iter_count, int32_t
 int kml_receive(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
                 float *hhat, int32_t *kstar, int32_t *ret, float *metric);
 
+/*     Pipelined form of kml_receive for callers that hand over batch after batch: kml_receive_submit enqueues the batch
+ *     (H2D copy of y from the caller's — ideally pinned — buffer, the receiver kernels, D2H copies of the outputs) and
+ *     returns; kml_receive_wait(ctx, n) blocks until at most n submitted batches are still in flight (n = 0: all done).
+ *     Input and output buffers of a batch belong to the library until it has been waited for.  Up to 4 batches may be in
+ *     flight (a fifth submit first waits for the oldest); consecutive batches overlap their copies with each other's
+ *     kernels, which the blocking call can only do inside one batch. */
+int kml_receive_submit(kml_ctx *ctx, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                       float *hhat, int32_t *kstar, int32_t *ret, float *metric);
+int kml_receive_wait(kml_ctx *ctx, int max_outstanding);
+
 /*     The same seam on the reference's types (the arguments of KmCodec::Decoder, kmcodec.cc:54-72, batched):
  *     y[B][n_sym][2] and true_h[B][2] are std::complex<double> as double pairs; hhat[B][2] double.  The conversion to the
  *     kernels' fp32 happens on the device, inside this call. */

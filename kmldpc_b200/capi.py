@@ -75,6 +75,8 @@ SYMBOLS = {
     "kml_receive_f64": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, C.c_double, c_u32p, c_f64p, c_i32p, c_i32p, c_f32p]),
     "kml_soft_syndrome_state": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
     "kml_receive": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p, c_f32p]),
+    "kml_receive_submit": (C.c_int, [C.c_void_p, C.c_int, c_f32p, c_f32p, C.c_double, c_u32p, c_f32p, c_i32p, c_i32p, c_f32p]),
+    "kml_receive_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "kml_count_errors": (C.c_int, [C.c_void_p, C.c_int, c_u32p, c_u32p, c_u64p]),
     "kml_simulate": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, c_u64p, c_u64p]),
     "kml_simulate_frames": (C.c_int, [C.c_void_p, C.c_double, C.c_uint64, C.c_uint64, C.c_int, c_u64p, c_f32p, c_f32p, c_f32p,

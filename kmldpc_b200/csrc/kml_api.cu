@@ -80,6 +80,9 @@ struct kml_ctx {
   Lane lane[2];
   DevBuf<unsigned long long> counters;  // 5 x u64
   unsigned long long *h_counters = nullptr;  // pinned
+  static constexpr int kRxRing = 4;          // kml_receive_submit calls that may be outstanding
+  cudaEvent_t rx_done[kRxRing][2] = {};      // completion of a submit on each lane
+  uint64_t rx_submitted = 0, rx_waited = 0;
   DevBuf<double> soft_carry;  // [1] sum of ln(syndrom_soft_) as the last Decoder call of this context left it
   int32_t *h_chain_counts = nullptr;  // pinned [2]
   uint64_t launches = 0;
@@ -659,6 +662,9 @@ extern "C" void kml_destroy(kml_ctx *c) {
   c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_g.release(); c->vn_items.release(); c->cn_items.release(); c->cn_deg_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_chain_counts) cudaFreeHost(c->h_chain_counts);
+  for (auto &slot : c->rx_done)
+    for (cudaEvent_t e : slot)
+      if (e) cudaEventDestroy(e);
   c->soft_carry.release();
   delete c;
 }
@@ -956,7 +962,7 @@ namespace {
 // Host-buffer receiver: batches alternate between the two lanes so the H2D copy of batch i+1 and the D2H copy of batch
 // i-1 overlap the kernels of batch i (true overlap needs pinned host buffers; pageable ones still work).
 int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *true_h, double var, uint32_t *uu_hat_packed,
-                 float *hhat, double *hhat64, int32_t *kstar, int32_t *ret, float *metric) {
+                 float *hhat, double *hhat64, int32_t *kstar, int32_t *ret, float *metric, bool wait = true) {
   KML_CUDA(c, cudaSetDevice(c->device));
   // sub-batches of ~2048 frames (measured best on B200: the first H2D and the last D2H are the only exposed copies,
   // and the other lane's kernels fill the tail of each decoder launch); never fewer than ~1 frame per resident CTA
@@ -1009,11 +1015,44 @@ int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *tru
     KML_RC(lane_release(c, l, s));
     if (sequential) KML_CUDA(c, cudaStreamSynchronize(s));
   }
+  if (!wait) return KML_OK;
   KML_CUDA(c, cudaStreamSynchronize(c->lane[0].stream));
   KML_CUDA(c, cudaStreamSynchronize(c->lane[1].stream));
   return KML_OK;
 }
+
+// completion of the oldest outstanding kml_receive_submit
+int rx_retire_one(kml_ctx *c) {
+  const int slot = (int)(c->rx_waited % kml_ctx::kRxRing);
+  for (int k = 0; k < 2; k++) KML_CUDA(c, cudaEventSynchronize(c->rx_done[slot][k]));
+  c->rx_waited++;
+  return KML_OK;
+}
 }  // namespace
+
+extern "C" int kml_receive_submit(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
+                                  float *hhat, int32_t *kstar, int32_t *ret, float *metric) {
+  KML_RC(check_batch(c, B));
+  if (!y || !(var > 0) || (c->opts.known_h && !true_h)) return fail_arg(c, "kml_receive_submit: bad argument");
+  KML_CUDA(c, cudaSetDevice(c->device));
+  while (c->rx_submitted - c->rx_waited >= (uint64_t)kml_ctx::kRxRing) KML_RC(rx_retire_one(c));  // ring full: oldest first
+  KML_RC(receive_host(c, B, y, 0, true_h, var, uu_hat_packed, hhat, nullptr, kstar, ret, metric, false));
+  const int slot = (int)(c->rx_submitted % kml_ctx::kRxRing);
+  for (int k = 0; k < 2; k++) {
+    if (!c->rx_done[slot][k]) KML_CUDA(c, cudaEventCreateWithFlags(&c->rx_done[slot][k], cudaEventDisableTiming));
+    KML_CUDA(c, cudaEventRecord(c->rx_done[slot][k], c->lane[k].stream));
+  }
+  c->rx_submitted++;
+  return KML_OK;
+}
+
+extern "C" int kml_receive_wait(kml_ctx *c, int max_outstanding) {
+  if (!c) return KML_ERR_ARG;
+  if (max_outstanding < 0) max_outstanding = 0;
+  KML_CUDA(c, cudaSetDevice(c->device));
+  while (c->rx_submitted - c->rx_waited > (uint64_t)max_outstanding) KML_RC(rx_retire_one(c));
+  return KML_OK;
+}
 
 extern "C" int kml_receive(kml_ctx *c, int B, const float *y, const float *true_h, double var, uint32_t *uu_hat_packed,
                            float *hhat, int32_t *kstar, int32_t *ret, float *metric) {

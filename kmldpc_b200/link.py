@@ -291,6 +291,15 @@ class Link:
                       C.cast(uu_ptr, capi.c_u32p), None, None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None, None),
                     "kml_receive")
 
+    def receive_submit_raw(self, B: int, y_ptr: int, var: float, uu_ptr: int, ret_ptr: int = 0):
+        """kml_receive_submit on host pointers given as integers: enqueue the batch and return (see receive_wait)."""
+        self._check(self._lib.kml_receive_submit(self._h, B, C.cast(y_ptr, capi.c_f32p), None, var, C.cast(uu_ptr, capi.c_u32p), None,
+                                                 None, C.cast(ret_ptr, capi.c_i32p) if ret_ptr else None, None), "kml_receive_submit")
+
+    def receive_wait(self, max_outstanding: int = 0):
+        """Block until at most `max_outstanding` submitted batches are still in flight."""
+        self._check(self._lib.kml_receive_wait(self._h, int(max_outstanding)), "kml_receive_wait")
+
     def receive_f64_raw(self, B: int, y_ptr: int, var: float, uu_ptr: int, ret_ptr: int = 0):
         """kml_receive_f64 on host pointers given as integers (pinned complex128 symbols): no wrapping, no allocation."""
         self._check(self._lib.kml_receive_f64(self._h, B, C.cast(y_ptr, capi.c_f64p), None, var, C.cast(uu_ptr, capi.c_u32p), None,

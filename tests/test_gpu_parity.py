@@ -498,6 +498,30 @@ def test_reference_typed_entry_points(kb):
     link.close()
 
 
+def test_pipelined_receive_equals_blocking_call(kb):
+    """kml_receive_submit / kml_receive_wait: several batches in flight give the answers of the blocking call, batch by batch."""
+    import torch
+    name = "peg2304_4psk_6db"
+    link = util.gpu_link(name, max_batch=512)
+    B, n = 700, 6                                     # 700 frames = two sub-batches per call; 6 calls > the ring of 4
+    ys, ref = [], []
+    for i in range(n):
+        u, c, h, y = link.generate(B, 6.0, seed=50 + i)
+        yt = torch.from_numpy(np.ascontiguousarray(y)).view(torch.float32).reshape(B, -1, 2).pin_memory()
+        ys.append(yt)
+        uu, _, _, ret = link.receive(y, 10 ** -0.6)
+        ref.append((uu.copy(), ret.copy()))
+    outs = [(torch.empty((B, link.k_words), dtype=torch.int32).pin_memory(), torch.empty((B,), dtype=torch.int32).pin_memory())
+            for _ in range(n)]
+    for i in range(n):
+        link.receive_submit_raw(B, ys[i].data_ptr(), 10 ** -0.6, outs[i][0].data_ptr(), outs[i][1].data_ptr())
+    link.receive_wait(2)
+    link.receive_wait(0)
+    for i in range(n):
+        assert np.array_equal(outs[i][0].numpy().view(np.uint32), ref[i][0]) and np.array_equal(outs[i][1].numpy(), ref[i][1]), i
+    link.close()
+
+
 def test_dev_calls_on_two_streams_serialise(kb):
     """Two _dev calls on DIFFERENT streams of one context share its work space: the second waits (on the device) for the
     first, so both give the single-stream answer."""
