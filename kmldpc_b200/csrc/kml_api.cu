@@ -969,6 +969,10 @@ int receive_host(kml_ctx *c, int B, const void *y, int y_is_f64, const void *tru
   int step = c->max_batch;
   if (B > 2 * c->num_sms * 8) step = std::min(step, std::max(c->num_sms * 8, std::min(2048, (B + 1) / 2)));
   int slow = 2;
+  if (!wait) {  // pipelined (kml_receive_submit): the previous batch hides this one's first copy — two halves, one per lane,
+    step = std::min(c->max_batch, std::max(c->num_sms * 8, (B + 1) / 2));  // no slow start (measured on B200, 16384 frames
+    slow = 0;                                                              // per batch: 5.01 ms per step against 5.43 ms)
+  }
 #ifdef KML_TUNING
   if (const char *e = tuning_knob("KML_RX_CHUNK")) step = std::max(1, std::min(c->max_batch, atoi(e)));
   if (const char *e = tuning_knob("KML_RX_SLOW")) slow = std::max(0, std::min(6, atoi(e)));
