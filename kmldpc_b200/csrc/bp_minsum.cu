@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(T, MINB) ms2_regular_kernel(const DecParams p)
     if (tid == 0) {  // a work item = two consecutive entries of the frame queue (the last one may be single: fb = fa)
       const int nB = frame_count(p), fp = (int)atomicAdd(p.work_counter, 1u);
       const int ia = 2 * fp, ib = min(2 * fp + 1, nB - 1);
-      s_pair[0] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ia) : ia) : -1;
-      s_pair[1] = ia < nB ? (p.frame_idx ? __ldg(p.frame_idx + ib) : ib) : -1;
+      s_pair[0] = ia < nB ? frame_at(p, ia) : -1;
+      s_pair[1] = ia < nB ? frame_at(p, ib) : -1;
     }
     __syncthreads();
     const int fa = s_pair[0], fb = s_pair[1];

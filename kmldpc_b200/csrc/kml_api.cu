@@ -155,7 +155,7 @@ int alloc_lane(kml_ctx *c, Lane &l) {
   KML_CUDA(c, l.ret.alloc(B));
   KML_CUDA(c, l.mret.alloc(4 * B));
   KML_CUDA(c, l.dec_queue.alloc(B));
-  KML_CUDA(c, l.dec_queue_n.alloc(1));
+  KML_CUDA(c, l.dec_queue_n.alloc(2));
   if (c->opts.metric_type) {
     KML_CUDA(c, l.soft.alloc(4 * B));
     KML_CUDA(c, l.fsoft.alloc(B));
@@ -488,13 +488,14 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
     d.skip_decode = (d.winner_only && c->opts.early_exit && c->even_rows && c->punct == 0) ? 1 : 0;
     d.words_n = c->words_n; d.out_bits = l.cc_hat_packed.p; d.out_ret = l.ret.p;
     if (d.skip_decode) {
-      d.queue = l.dec_queue.p; d.queue_n = l.dec_queue_n.p;
-      KML_CUDA(c, cudaMemsetAsync(l.dec_queue_n.p, 0, sizeof(int32_t), s));
+      d.queue = l.dec_queue.p; d.queue_n = l.dec_queue_n.p; d.queue_cap = c->max_batch;
+      d.long_metric = c->M / 6;  // (a frame that converges has a handful of wrong bits, three unsatisfied checks each)
+      KML_CUDA(c, cudaMemsetAsync(l.dec_queue_n.p, 0, 2 * sizeof(int32_t), s));
     }
     KML_LAUNCH(c, launch_demap(d, c->num_sms, s));
     if (d.winner_only) {
       DecParams p = dec_params(c, l, B, l.lr.p, nullptr, 1, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
-      if (d.skip_decode) { p.frame_idx = l.dec_queue.p; p.n_frames_dev = l.dec_queue_n.p; }
+      if (d.skip_decode) { p.frame_idx = l.dec_queue.p; p.n_frames_dev = l.dec_queue_n.p; p.queue_cap = c->max_batch; }
       KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
       KML_LAUNCH(c, launch_extract_bits(B, c->K, c->info_offset, c->words_n, l.cc_hat_packed.p, l.uu_hat_packed.p, s));
       return KML_OK;

@@ -43,17 +43,34 @@ struct DecParams {
   // optional frame queue: entry i of the queue decodes frame frame_idx[i]; the queue length is *n_frames_dev (written by
   // an earlier kernel of the stream; B is then only the upper bound the grid is sized for).  Inputs and outputs stay
   // indexed by the frame number, so a queue is just a subset / an order of the batch.
+  // queue_cap > 0: a TWO-ENDED queue in one array of queue_cap entries — n_frames_dev[0] entries filled from the front,
+  // n_frames_dev[1] from the back (entry j of the back part at frame_idx[queue_cap - 1 - j]); the front part is served
+  // first.  The demapper puts the frames that will probably run the full iteration count in front (longest first).
   const int32_t *frame_idx;
   const int32_t *n_frames_dev;
+  int queue_cap;
 };
 
 #ifdef __CUDACC__
-__device__ __forceinline__ int frame_count(const DecParams &p) { return p.n_frames_dev ? min(__ldg(p.n_frames_dev), p.B) : p.B; }
+__device__ __forceinline__ int frame_count(const DecParams &p) {
+  if (!p.n_frames_dev) return p.B;
+  const int n = p.queue_cap ? __ldg(p.n_frames_dev) + __ldg(p.n_frames_dev + 1) : __ldg(p.n_frames_dev);
+  return min(n, p.B);
+}
+// frame behind entry i of the queue (i < frame_count)
+__device__ __forceinline__ int frame_at(const DecParams &p, int i) {
+  if (!p.frame_idx) return i;
+  if (p.queue_cap) {
+    const int nf = __ldg(p.n_frames_dev);
+    return __ldg(p.frame_idx + (i < nf ? i : p.queue_cap - 1 - (i - nf)));
+  }
+  return __ldg(p.frame_idx + i);
+}
 // thread 0 of a CTA: the next frame of the queue, or -1 when it is empty
 __device__ __forceinline__ int next_frame(const DecParams &p) {
   const int i = (int)atomicAdd(p.work_counter, 1u);
   if (i >= frame_count(p)) return -1;
-  return p.frame_idx ? __ldg(p.frame_idx + i) : i;
+  return frame_at(p, i);
 }
 #endif
 
@@ -147,7 +164,8 @@ struct DemapParams {
   int skip_decode, words_n;
   uint32_t *out_bits;
   int32_t *out_ret;
-  int32_t *queue, *queue_n;
+  int32_t *queue, *queue_n;   // two-ended (see DecParams): queue[queue_cap], queue_n[2] = {front, back} lengths
+  int queue_cap, long_metric; // a winner with more than long_metric unsatisfied checks goes to the front (it will hardly converge)
 };
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s);
 

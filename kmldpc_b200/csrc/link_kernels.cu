@@ -976,7 +976,10 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
           const float *w = s_lr + (size_t)best * d.n_tx;
           float *out = d.lr + (size_t)f * d.n_tx;
           for (int i = tid; i < d.n_tx; i += DM_THREADS) out[i] = w[i];
-          if (tid == 0 && d.queue) d.queue[atomicAdd(d.queue_n, 1)] = f;
+          if (tid == 0 && d.queue) {  // longest first: a frame this far from a codeword will run all its iterations
+            if (s_cnt[best] > d.long_metric) d.queue[atomicAdd(d.queue_n, 1)] = f;
+            else d.queue[d.queue_cap - 1 - atomicAdd(d.queue_n + 1, 1)] = f;
+          }
         }
       }
     }
