@@ -89,7 +89,9 @@ typedef struct kml_opts {
                             1 = normalised min-sum, fp32 messages (throughput mode; NOT in the reference, hence not
                                 reference-pinned: checked against oracle/minsum_ref.py and gated by BER/FER against 0);
                             2 = the same with fp16 messages, two frames per shared-memory word ((3,6)-regular codes;
-                                other graphs run algorithm 1) */
+                                other graphs run algorithm 1);
+                            3 = layered (row-serial) min-sum on the block structure of a quasi-cyclic code (the 5G
+                                BG2 code; four frames per CTA); an error for codes without that structure */
 } kml_opts;
 
 typedef struct kml_ctx kml_ctx;
@@ -100,7 +102,7 @@ const char *kml_last_error(const kml_ctx *ctx);  /* ctx may be NULL: message of 
 int kml_set_early_exit(kml_ctx *ctx, int early_exit);
 /* Switches the decoder of every later call (also the 5G metric decodes); alpha = min-sum normalisation in (0, 1]. */
 int kml_set_algorithm(kml_ctx *ctx, int algorithm, double alpha);
-/* Check-node rule of the min-sum decoders (algorithm 1 | 2): |c2v| = max(alpha * min - beta, 0).  alpha = 0.8, beta = 0 is
+/* Check-node rule of the min-sum decoders (algorithm 1 | 2 | 3): |c2v| = max(alpha * min - beta, 0).  alpha = 0.8, beta = 0 is
  * the normalised min-sum kml_set_algorithm selects; alpha = 1, beta = 0.5 the offset min-sum.  Not in the reference. */
 int kml_set_minsum(kml_ctx *ctx, double alpha, double beta);
 /* info[0..7] = n_rows, n_graph, n_tx, k, bits_per_symbol, n_points, n_symbols per frame, max_batch */
@@ -271,7 +273,7 @@ typedef struct kml_sweep_cfg {
   char modem_file[512];                              /* [modem] modem_file */
   /* optional [gpu] table (ignored by the reference binary) */
   uint64_t seed;
-  int32_t n_gpus, max_batch, early_exit, algorithm;  /* [gpu] gpus / batch / early_exit / algorithm (0 SPA, 1 min-sum) */
+  int32_t n_gpus, max_batch, early_exit, algorithm;  /* [gpu] gpus / batch / early_exit / algorithm (0 SPA, 1-3 min-sum, see kml_opts) */
   int32_t debug_frames, reserved2;                   /* [gpu] debug = true: the reference's per-frame log lines ("Generated H",
                                                         "Current Block Number", "Hhat … Metric", "hatIndex") through log_cb, frames
                                                         in index order on GPU 0 — a debugging mode, orders of magnitude slower */

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkmldpc_b200.so")
-SOURCES = ["bp_decode.cu", "bp_minsum.cu", "link_kernels.cu", "kml_api.cu", "host_code.cpp", "layout_opt.cpp", "sweep.cpp"]
+SOURCES = ["bp_decode.cu", "bp_minsum.cu", "bp_layered.cu", "link_kernels.cu", "kml_api.cu", "host_code.cpp", "layout_opt.cpp", "sweep.cpp"]
 HEADERS = ["kml_internal.h", "kml_kernels.cuh", "bp_minsum_nodes.cuh", os.path.join("..", "..", "include", "kmldpc_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function"]

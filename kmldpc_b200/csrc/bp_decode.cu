@@ -818,6 +818,7 @@ __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p
 // KML_DEC_NO_QC, KML_DEC_T8064 choose the fallback layouts / tilings and announce themselves on stderr, kml_internal.h);
 // the A/B and timing-ablation variants exist only in a -DKML_TUNING build.
 dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan, int threads) {
+  if (alg == 3) return layered_kernel();
   if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;  // (fp16 x 2 frames exists for regular codes only)
   if (alg != 0) return minsum_kernel_of(k, alg);
   if (qc_plan == 1 && !soft) {
@@ -958,7 +959,9 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned int), s);
   if (e != cudaSuccess) return e;
   int grid = num_sms * l.ctas_per_sm;
-  const int units = dec_two_frames_per_cta(l.kind, l.alg) ? (p.B + 1) / 2 : p.B;  // work items in the frame queue
+  // work items in the frame queue per CTA: a pair of frames (fp16 x 2), or the layered kernel's concurrent frame groups
+  const int per = l.alg == 3 ? layered_frames_per_cta() : (dec_two_frames_per_cta(l.kind, l.alg) ? 2 : 1);
+  const int units = (p.B + per - 1) / per;
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;
   l.fn<<<grid, l.threads, l.smem_bytes, s>>>(p);

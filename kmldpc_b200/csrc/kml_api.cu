@@ -74,7 +74,11 @@ struct kml_ctx {
   int ell_width = 0;
   DevBuf<uint8_t> vn_deg, cn_deg, cn_deg_rm;
   DecTables dt{}, dt_rm{};  // planar layout (every kernel) / row-major layout (regular sum-product kernels)
-  DecLaunch dl{}, dl_alg[3]{};  // dl = the active algorithm's launch record
+  DecLaunch dl{}, dl_alg[4]{};  // dl = the active algorithm's launch record
+  DevBuf<int32_t> lay_ptr;      // block structure for the layered decoder (algorithm = 3); lay.z == 0: the code is not quasi-cyclic
+  DevBuf<uint32_t> lay_cs;
+  LayeredTables lay{};
+  std::string lay_why;          // why algorithm = 3 is not available for this code
   DecLaunch dl_soft{};          // sum-product kernel that also produces the soft-syndrome sums (metric_type = true)
   float alpha = 0.8f, beta = 0.0f;  // min-sum: normalisation and offset
   Lane lane[2];
@@ -193,6 +197,73 @@ int lane_release(kml_ctx *c, Lane &l, cudaStream_t s) {
   KML_CUDA(c, cudaEventRecord(l.owner_ev, s));
   l.owner = s;
   l.owned = true;
+  return KML_OK;
+}
+
+// Quasi-cyclic structure for the layered decoder (bp_layered.cu): finds the largest Z for which H is a grid of Z x Z
+// blocks that are zero or ONE cyclically shifted identity (row l Z + z meets column c Z + (z + s) mod Z), and uploads the
+// (block column, shift) list of every block row.  Codes without that structure simply have no algorithm 3.
+int build_layered_tables(kml_ctx *c, const kml_code *code) {
+  const int M = c->M, N = c->N;
+  c->lay = LayeredTables{};
+  c->dl_alg[3] = DecLaunch{};
+  c->lay_why = "the parity-check matrix is not a grid of cyclically shifted identity blocks";
+  int g = M, b = N;
+  while (b) { const int t = g % b; g = b; b = t; }  // Z divides gcd(M, N)
+  std::vector<int32_t> ptr;
+  std::vector<uint32_t> cs;
+  int z_found = 0;
+  for (int Z = g; Z >= 8 && !z_found; Z--) {
+    if (g % Z) continue;
+    ptr.assign(1, 0);
+    cs.clear();
+    bool ok = true;
+    std::vector<std::pair<int, int>> first, mine;
+    for (int l = 0; l < M / Z && ok; l++) {
+      for (int z = 0; z < Z && ok; z++) {
+        const int r = l * Z + z;
+        mine.clear();
+        for (int e = code->row_ptr[r]; e < code->row_ptr[r + 1]; e++) {
+          const int col = code->col_idx[e];
+          mine.emplace_back(col / Z, ((col % Z) - z + Z) % Z);
+        }
+        std::sort(mine.begin(), mine.end());
+        for (size_t i = 1; i < mine.size(); i++) ok = ok && mine[i].first != mine[i - 1].first;  // one shift per block
+        if (z == 0) first = mine;
+        else ok = ok && mine == first;
+      }
+      if (ok) {
+        for (auto &bs : first) cs.push_back(((uint32_t)(bs.first * Z) << 16) | (uint32_t)bs.second);
+        ptr.push_back((int32_t)cs.size());
+      }
+    }
+    if (ok) z_found = Z;
+  }
+  if (!z_found) return KML_OK;
+  const int NL = M / z_found;
+  int dmax = 0;
+  for (int l = 0; l < NL; l++) dmax = std::max(dmax, ptr[l + 1] - ptr[l]);
+  if (dmax > layered_max_degree() || (int)cs.size() > layered_max_edges() || NL > layered_max_layers() || N > 0xFFFF) {
+    c->lay_why = "block structure beyond the compiled layered kernel (check degree / block count)";
+    return KML_OK;
+  }
+  DecLaunch dl{};
+  dl.kind = c->dl_alg[0].kind;
+  dl.alg = 3;
+  dl.threads = layered_threads(z_found);
+  dl.smem_bytes = layered_smem_bytes(N, NL, z_found);
+  if (dl.threads > layered_max_threads() || dl.smem_bytes > 227 * 1024) {
+    c->lay_why = "lifting size too large for the layered kernel's frames-per-CTA tiling";
+    return KML_OK;
+  }
+  KML_CUDA(c, c->lay_ptr.alloc(ptr.size()));
+  KML_CUDA(c, cudaMemcpy(c->lay_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  KML_CUDA(c, c->lay_cs.alloc(cs.size()));
+  KML_CUDA(c, cudaMemcpy(c->lay_cs.p, cs.data(), cs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  KML_CUDA(c, dec_prepare(dl));
+  c->dl_alg[3] = dl;
+  c->lay.lay_ptr = c->lay_ptr.p; c->lay.lay_cs = c->lay_cs.p;
+  c->lay.z = z_found; c->lay.n_layers = NL; c->lay.n_edges = (int)cs.size();
   return KML_OK;
 }
 
@@ -379,6 +450,8 @@ int build_decoder_tables(kml_ctx *c, const kml_code *code) {
     KML_CUDA(c, dec_prepare(dl));
     c->dl_alg[alg] = dl;
   }
+  KML_RC(build_layered_tables(c, code));
+  if (c->opts.algorithm == 3 && !c->lay.z) return fail_arg(c, ("algorithm = 3 (layered min-sum): " + c->lay_why).c_str());
   c->dl = c->dl_alg[c->opts.algorithm];
   {  // soft-syndrome twin: regular codes → scalar planar kernel on the planar tables; other graphs → run-time-graph kernel
     DecLaunch ds = c->dl_alg[0];
@@ -403,6 +476,7 @@ DecParams dec_params(kml_ctx *c, Lane &l, int B, const float *in, const int32_t 
   p.B = B; p.iters = iters; p.max_iter = c->opts.max_iter; p.early_exit = c->opts.early_exit;
   p.out_bits = out_bits; p.out_ret = out_ret; p.out_soft = out_soft;
   p.work_counter = l.work_counter.p; p.words_n = c->words_n; p.alpha = c->alpha; p.beta = c->beta;
+  p.lay = c->lay;
   return p;
 }
 
@@ -547,7 +621,7 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
     return fail_arg(nullptr, "kml_create: n_tx is not a multiple of bits_per_symbol");
   if (modem->bits_per_symbol > 6) return fail_arg(nullptr, "kml_create: constellations above 64 points are not built");
   if (opts->max_iter < 1) return fail_arg(nullptr, "kml_create: max_iter < 1");
-  if (opts->algorithm < 0 || opts->algorithm > 2) return fail_arg(nullptr, "kml_create: unknown algorithm");
+  if (opts->algorithm < 0 || opts->algorithm > 3) return fail_arg(nullptr, "kml_create: unknown algorithm");
   if (opts->algorithm != 0 && opts->metric_type)
     return fail_arg(nullptr, "kml_create: the soft-syndrome metric needs the sum-product decoder (algorithm = 0)");
   auto *c = new kml_ctx();
@@ -661,6 +735,7 @@ extern "C" void kml_destroy(kml_ctx *c) {
   free_lane(c->lane[1]);
   c->enc_t.release(); c->points.release(); c->row_ptr.release(); c->col_idx.release();
   c->vn_addr.release(); c->vn_addr_rm.release(); c->vn_addr_g.release(); c->vn_items.release(); c->cn_items.release(); c->cn_deg_rm.release(); c->col_ell.release(); c->vn_deg.release(); c->cn_deg.release(); c->counters.release();
+  c->lay_ptr.release(); c->lay_cs.release();
   if (c->h_counters) cudaFreeHost(c->h_counters);
   if (c->h_chain_counts) cudaFreeHost(c->h_chain_counts);
   for (auto &slot : c->rx_done)
@@ -680,8 +755,10 @@ extern "C" int kml_set_early_exit(kml_ctx *c, int early_exit) {
 
 extern "C" int kml_set_algorithm(kml_ctx *c, int algorithm, double alpha) {
   if (!c) return KML_ERR_ARG;
-  if (algorithm < 0 || algorithm > 2)
-    return fail_arg(c, "kml_set_algorithm: 0 = sum-product, 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames");
+  if (algorithm < 0 || algorithm > 3)
+    return fail_arg(c, "kml_set_algorithm: 0 = sum-product, 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames, "
+                       "3 = layered min-sum (quasi-cyclic codes)");
+  if (algorithm == 3 && !c->lay.z) return fail_arg(c, ("kml_set_algorithm: layered min-sum: " + c->lay_why).c_str());
   if (algorithm != 0 && c->opts.metric_type) return fail_arg(c, "kml_set_algorithm: soft-syndrome metric needs sum-product");
   if (algorithm != 0 && !(alpha > 0.0 && alpha <= 1.0)) return fail_arg(c, "kml_set_algorithm: alpha must be in (0, 1]");
   c->opts.algorithm = algorithm;

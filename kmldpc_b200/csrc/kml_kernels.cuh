@@ -25,8 +25,18 @@ struct DecTables {
   int n_pad, vn_items_n, cn_items_n;
 };
 
+// Block structure of a quasi-cyclic code for the layered decoder (bp_layered.cu): layer l = block row l; its checks'
+// edges e in [lay_ptr[l], lay_ptr[l + 1]) connect check z to variable (lay_cs[e] >> 16) + (z + (lay_cs[e] & 0xFFFF)) mod z
+// (high half = block column * Z, low half = cyclic shift).
+struct LayeredTables {
+  const int32_t *lay_ptr;   // [n_layers + 1]
+  const uint32_t *lay_cs;   // [n_edges]
+  int z, n_layers, n_edges;
+};
+
 struct DecParams {
   DecTables t;
+  LayeredTables lay;        // algorithm = 3 only
   const float *in;          // [B * n_cand][n_tx] natural-log LLR, or likelihood ratio P0/P1 when in_is_lr
   const int32_t *sel;       // optional [B]: candidate picked per frame (row f * n_cand + sel[f] of `in`)
   int n_cand, in_is_lr;
@@ -80,7 +90,8 @@ typedef void (*dec_kernel_t)(const DecParams);
 
 struct DecLaunch {
   DecKernelKind kind;
-  int alg;  // 0 = sum-product (reference semantics, bp_decode.cu), 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames
+  int alg;  // 0 = sum-product (reference semantics, bp_decode.cu), 1 = normalised min-sum fp32, 2 = min-sum fp16 x 2 frames,
+            // 3 = layered min-sum (quasi-cyclic codes, bp_layered.cu)
   int threads;
   int smem_bytes;
   int ctas_per_sm;  // filled by dec_prepare (occupancy query)
@@ -91,6 +102,15 @@ struct DecLaunch {
 };
 
 dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
+// bp_layered.cu (algorithm = 3: layered min-sum for quasi-cyclic codes)
+dec_kernel_t layered_kernel();
+int layered_threads(int z);
+int layered_smem_bytes(int n, int n_layers, int z);
+int layered_max_degree();
+int layered_max_threads();
+int layered_max_edges();
+int layered_max_layers();
+int layered_frames_per_cta();
 inline bool dec_two_frames_per_cta(DecKernelKind k, int alg) { return alg == 2 && (k == DEC_REG_6_3 || k == DEC_REG_12_6); }
 bool dec_wants_rowmajor(DecKernelKind k, int alg);
 int dec_regular_threads(DecKernelKind k);

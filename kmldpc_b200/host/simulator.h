@@ -51,7 +51,7 @@ class Simulator {
       cfg_.n_gpus = (int)toml::find_or<std::int64_t>(gpu, "gpus", 1);
       cfg_.max_batch = (int)toml::find_or<std::int64_t>(gpu, "batch", 0);
       cfg_.early_exit = toml::find_or<bool>(gpu, "early_exit", true) ? 1 : 0;
-      cfg_.algorithm = (int)toml::find_or<std::int64_t>(gpu, "algorithm", 0);  // 1 = normalised min-sum (throughput mode)
+      cfg_.algorithm = (int)toml::find_or<std::int64_t>(gpu, "algorithm", 0);  // 1-3 = min-sum variants (throughput mode)
       cfg_.reduce_on_host = toml::find_or<std::string>(gpu, "reduce", "nccl") == "host" ? 1 : 0;
       cfg_.debug_frames = toml::find_or<bool>(gpu, "debug", false) ? 1 : 0;  // the per-frame lines of the reference's log file
     }
