@@ -258,6 +258,20 @@ def config_leg(kb, torch, dev, stream, smem_peak, spec, steps, with_cpu):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     iters = float(ret.float().clamp(max=MAX_ITER).mean().item())
+    thr = None
+    if is_5g:  # BASELINE names "min-sum decoding" for this config; the reference has none → throughput mode, BER/FER-gated only
+        thr = {"note": "whole receiver, same step; NOT the reference's algorithm (tests/test_gpu_minsum.py gates them)"}
+        for alg, label in ((1, "minsum_flooding_fp32"), (3, "minsum_layered")):
+            link.set_algorithm(alg, 0.8)
+            step(0)
+            torch.cuda.synchronize()
+            a.record()
+            for i in range(steps):
+                step(3 + i)
+            b.record()
+            torch.cuda.synchronize()
+            thr[label + "_receiver_mbps"] = B * K / (a.elapsed_time(b) / steps * 1e-3) / 1e6
+        link.set_algorithm(0)
     hhat = torch.empty((B, 2), dtype=torch.float32, device=dev)
     llr = torch.empty((B, n_tx), dtype=torch.float32, device=dev)
     cc_hat = torch.empty((B, link.words_n), dtype=torch.int32, device=dev)
@@ -282,6 +296,8 @@ def config_leg(kb, torch, dev, stream, smem_peak, spec, steps, with_cpu):
                         "frac": alg_bytes / (dec_ms * 1e-3) / 1e9 / smem_peak if smem_peak else None, "traffic": None,
                         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dec_ms,
                         "decode_only_mbps": B * K / (dec_ms * 1e-3) / 1e6}}
+    if thr:
+        out["throughput_mode"] = thr
     link.close()
     if with_cpu:
         cores = os.cpu_count() or 1
