@@ -4,6 +4,7 @@
 // ncclAllReduce over NVLink (single process, ncclCommInitAll — the path's only collective); lines are
 // formatted exactly like SourceSink::PrintResult (lib/lab/src/sourcesink.cc:50-65) and the tables of simulator.cc:48-66.
 #include <algorithm>
+#include <condition_variable>
 #include <array>
 #include <atomic>
 #include <cctype>
@@ -394,39 +395,82 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
     int32_t info[8];
     kml_info(ctx[0], info);
     // Frames are handed out in chunks of several batches, so that kml_simulate's two lanes overlap inside a call and its
-    // own (lagged, per-batch) stop rule applies.  Guided self-scheduling: a chunk is a quarter of an even share of what is
-    // left (between 1 and 8 batches), so the GPUs finish a point within one batch of each other — with fixed 4-batch chunks
-    // 3.2 M frames over 8 GPUs left some with 7 chunks and some with 6 (C5: 1.46 s instead of 1.2 s).
+    // own (lagged, per-batch) stop rule applies.  The GPUs take chunks from ONE queue that runs through the SNR points in
+    // order: a GPU that finds a point's frames handed out moves on to the next point instead of waiting for the others, so
+    // the only tail is at the end of the sweep.  (With a barrier per point, C5 on 8 GPUs spent a quarter of its time in 31
+    // tails.)  Guided self-scheduling: a chunk is a quarter of an even share of ALL frames left, between 1 and 8 batches.
+    // The caller's thread waits for the points in order, reduces each one's counters and logs its line as it completes.
     const uint64_t batch = (uint64_t)info[7];
     for (int g = 0; g < G; g++) {  // setup ends when every device is idle
       cudaSetDevice(g);
       cudaDeviceSynchronize();
     }
     t_points = now_s();
+    struct Point {
+      uint64_t cursor = 0, err_blk = 0;
+      int inflight = 0;
+      std::vector<uint64_t> mine;  // [G][4]
+    };
+    std::vector<Point> pts((size_t)n_pts);
+    for (auto &pt : pts) pt.mine.assign((size_t)G * 4, 0);
+    std::mutex mu;
+    std::condition_variable cv;
+    int cur = 0, failed = KML_OK;
+    std::string err_msg;  // kml_last_error() of a failing worker (its thread-local copy dies with the thread)
+    // simulator.cc:117 leaves before the first frame when err_blk >= maximum_error_number — with 0 that is at once
+    const bool no_frames = cfg->max_err_blk == 0;
+    const bool debug = cfg->debug_frames && !cfg->histogram_enable && !no_frames;
+    const bool serial_mode = cfg->histogram_enable || debug || no_frames;  // frames in index order on GPU 0 (or none)
+    auto point_seed_of = [&](int i) { return cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull; };  // disjoint Philox streams per point
+    auto point_open = [&](const Point &pt) { return pt.cursor < cfg->max_num_blk && pt.err_blk < cfg->max_err_blk; };  // simulator.cc:117
+    auto worker = [&](int g) {
+      for (;;) {
+        int i;
+        uint64_t begin, count, seen;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          while (cur < n_pts && !point_open(pts[cur])) cur++;
+          if (cur >= n_pts || failed != KML_OK) break;
+          Point &pt = pts[cur];
+          const uint64_t left_here = cfg->max_num_blk - pt.cursor;
+          const uint64_t left_all = left_here + (uint64_t)(n_pts - 1 - cur) * cfg->max_num_blk;
+          uint64_t want = (left_all / (4 * (uint64_t)G) + batch - 1) / batch * batch;
+          want = std::min<uint64_t>(std::max<uint64_t>(want, batch), 8 * batch);
+          i = cur;
+          begin = pt.cursor;
+          count = std::min(want, left_here);
+          seen = pt.err_blk;
+          pt.cursor += count;
+          pt.inflight++;
+        }
+        uint64_t cnt[4] = {0, 0, 0, 0};
+        // what is left of the error budget goes down with the call: kml_simulate stops between its batches
+        const int r = kml_simulate(ctx[g], cfg->min_snr + cfg->step_snr * i, point_seed_of(i), begin, count, cfg->max_err_blk - seen, cnt,
+                                   nullptr);
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          Point &pt = pts[i];
+          if (r != KML_OK && failed == KML_OK) {
+            failed = r;
+            err_msg = kml_last_error(ctx[g]);
+          }
+          pt.err_blk += cnt[1];  // (the stop rule sees this host-side total while other chunks are in flight)
+          for (int k = 0; k < 4; k++) pt.mine[(size_t)g * 4 + k] += cnt[k];
+          pt.inflight--;
+        }
+        cv.notify_all();
+        if (r != KML_OK) break;
+      }
+      cv.notify_all();
+    };
+    std::vector<std::thread> th;
+    if (!serial_mode)
+      for (int g = 0; g < G; g++) th.emplace_back(worker, g);
     for (int i = 0; i < n_pts && rc == KML_OK; i++) {
       const double snr = cfg->min_snr + cfg->step_snr * i;
-      const uint64_t point_seed = cfg->seed + (uint64_t)i * 0x9E3779B97F4A7C15ull;  // disjoint Philox streams per point
-      std::atomic<uint64_t> err_blk{0};
-      std::mutex cursor_mu;
-      uint64_t cursor = 0;
-      auto grab = [&](uint64_t *begin, uint64_t *count) {  // next chunk of this point's frame range, or false
-        std::lock_guard<std::mutex> lk(cursor_mu);
-        if (cursor >= cfg->max_num_blk) return false;
-        const uint64_t left = cfg->max_num_blk - cursor;
-        uint64_t want = (left / (4 * (uint64_t)G) + batch - 1) / batch * batch;
-        want = std::min<uint64_t>(std::max<uint64_t>(want, batch), 8 * batch);
-        *begin = cursor;
-        *count = std::min(want, left);
-        cursor += *count;
-        return true;
-      };
+      const uint64_t point_seed = point_seed_of(i);
       uint64_t tot[4] = {0, 0, 0, 0};
-      std::vector<uint64_t> mine((size_t)G * 4, 0);  // per GPU, this point
-      std::atomic<int> failed{KML_OK};
-      std::mutex err_mu;
-      std::string err_msg;  // kml_last_error() of a failing worker (its thread-local copy dies with the thread)
-      // simulator.cc:117 leaves before the first frame when err_blk >= maximum_error_number — with 0 that is at once
-      const bool no_frames = cfg->max_err_blk == 0;
+      std::vector<uint64_t> &mine = pts[i].mine;  // per GPU, this point
       // histogram mode (simulator.cc:81-84,154-162): "histogram_<snr>.txt" in the working directory, one line per frame
       // with the four metrics rotated to start at the (first) minimum; frames in index order on GPU 0.
       if (cfg->histogram_enable && !no_frames) {
@@ -451,7 +495,6 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
       }
       // [gpu] debug = true: the reference's per-frame log lines, frames in index order on GPU 0 (simulator.cc:124-126,
       // 149-152; kmcodec.cc:64,132-136).  The same frames and counters as the normal path, one batch at a time.
-      const bool debug = cfg->debug_frames && !cfg->histogram_enable && !no_frames;
       if (debug) {
         const int nb_max = info[7];
         std::vector<float> dh(2 * (size_t)nb_max), dhh(2 * (size_t)nb_max), dm(4 * (size_t)nb_max);
@@ -484,31 +527,13 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
           }
         }
       }
-      auto worker = [&](int g) {
-        while (!cfg->histogram_enable && !debug && !no_frames && failed.load() == KML_OK) {
-          const uint64_t seen = err_blk.load();
-          if (seen >= cfg->max_err_blk) break;  // simulator.cc:117
-          uint64_t begin = 0, count = 0;
-          if (!grab(&begin, &count)) break;
-          uint64_t cnt[4] = {0, 0, 0, 0};
-          // what is left of the error budget goes down with the call: kml_simulate stops between its batches
-          const int r = kml_simulate(ctx[g], snr, point_seed, begin, count, cfg->max_err_blk - seen, cnt, nullptr);
-          if (r != KML_OK) {
-            std::lock_guard<std::mutex> lk(err_mu);
-            if (failed.load() == KML_OK) err_msg = kml_last_error(ctx[g]);
-            failed.store(r);
-            break;
-          }
-          err_blk.fetch_add(cnt[1]);  // (the stop rule polls this host-side total while frames are in flight)
-          for (int k = 0; k < 4; k++) mine[(size_t)g * 4 + k] += cnt[k];
+      if (!serial_mode) {  // this point is complete when its frames are handed out (or its budget is spent) and have come back
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return failed != KML_OK || (!point_open(pts[i]) && pts[i].inflight == 0); });
+        if (failed != KML_OK) {
+          rc = failed;
+          set_global_error(err_msg);  // on the CALLER's thread
         }
-      };
-      std::vector<std::thread> th;
-      for (int g = 0; g < G; g++) th.emplace_back(worker, g);
-      for (auto &t : th) t.join();
-      if (rc == KML_OK && failed.load() != KML_OK) {
-        rc = failed.load();
-        set_global_error(err_msg);  // on the CALLER's thread
       }
       if (!cfg->histogram_enable) {
         std::string why;
@@ -532,6 +557,11 @@ extern "C" int kml_sweep_run(const kml_sweep_cfg *cfg, const char *data_dir, dou
         for (int k = 0; k < 4; k++) counters[(size_t)i * 4 + k] = tot[k];
       log(fmt_point_line(snr, tot[0], tot[1], tot[3], b, f));
     }
+    if (rc != KML_OK) {  // (a failure outside the workers: stop them)
+      std::lock_guard<std::mutex> lk(mu);
+      if (failed == KML_OK) failed = rc;
+    }
+    for (auto &t : th) t.join();
     if (rc == KML_OK) {
       log("BER Result");
       for (int i = 0; i < n_pts; i++) log(fmt_table_row(cfg->min_snr + cfg->step_snr * i, ber_v[i]));
