@@ -188,6 +188,25 @@ def test_receiver_chain(name, frames, kb):
     link.close()
 
 
+@pytest.mark.parametrize("snr,frame_errors", [(5.0, 241), (15.0, 53), (30.0, 1)])
+def test_survey_fer_curve_replayed(snr, frame_errors, kb):
+    """SURVEY §8(c) pinned case: PEG2304 + 16QAM Gray blind, 300 frames from LCG state 17 — the frame-error counts measured on
+    the reference itself (FER 0.803 / 0.177 / 0.003; tests/test_oracle_golden.py holds all six points for the oracle).  The CUDA
+    receiver on the same channel outputs must give the SAME frames in error, not just the same count."""
+    olink = ko_link = util.oracle_link("peg2304_16qam_gray_12db")
+    g = util.ko.Lcg(17)
+    rs = [ko_link.frame(g, snr, full=True) for _ in range(300)]
+    link = util.gpu_link("peg2304_16qam_gray_12db", max_batch=128)
+    uu_p, hhat, kstar, ret = link.receive(np.stack([r.y for r in rs]), 10 ** (-0.1 * snr))
+    u = np.stack([r.u for r in rs])
+    fe = (kb.unpack_bits(uu_p, olink.code.K) != u).any(axis=1)
+    ref_fe = np.array([r.nerr > 0 for r in rs])
+    assert ref_fe.sum() == frame_errors
+    assert np.array_equal(fe, ref_fe), np.where(fe != ref_fe)[0]
+    assert np.array_equal(kstar, np.array([r.kstar for r in rs])) and np.array_equal(ret, np.array([r.ret for r in rs]))
+    link.close()
+
+
 def test_golden_fixture_replay(kb):
     """Channel outputs dumped from the UNMODIFIED reference (tests/golden) → same k*, return value, decisions."""
     z, p = util.golden("peg2304_16qam_gray_12db")

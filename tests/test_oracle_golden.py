@@ -161,3 +161,37 @@ def test_bulk_frames_are_thread_invariant_and_equal_single_frames():
     assert np.array_equal(r.y, a["y"][3]) and r.ret == a["ret"][3] and r.kstar == a["kstar"][3]
     assert np.array_equal(r.uu_hat.astype(np.uint8), a["uu_hat"][3]) and r.nerr == a["nerr"][3]
     assert a["converged"][3] == (link.code.parity_check(r.cc_hat) == 0)
+
+
+def test_survey_fer_curve_16qam_gray_blind():
+    """SURVEY §8(c) "pinned behavioural cases": PEG2304 + 16QAM Gray, blind, 300 frames from LCG state 17 (seed -1) per SNR
+    point — the frame-error counts the survey measured on the reference itself (FER 0.803 / 0.430 / 0.177 / 0.050 / 0.010 /
+    0.003 at 5 / 10 / 15 / 20 / 25 / 30 dB)."""
+    link = ko.Link("PEG2304regular0.5.txt", "4bit_16QAM_Gray.txt")
+    for snr, frame_errors in ((5.0, 241), (10.0, 129), (15.0, 53), (20.0, 15), (25.0, 3), (30.0, 1)):
+        g = ko.Lcg(17)
+        assert sum(link.frame(g, snr, full=False).nerr > 0 for _ in range(300)) == frame_errors, snr
+
+
+def test_kmeans_sums_are_never_reset():
+    """the compiled reference keeps ADDING to cnt[] / sum[] over the passes (kmeans.cc:15-84), so
+    its centroids are running means over all passes so far.  A textbook k-means (sums reset every pass) gives a visibly
+    different channel estimate on the same symbols — the oracle must follow the reference, not the textbook."""
+    z, p = load("peg2304_16qam_gray_12db")
+    pts = z["constellation"][:, 0] + 1j * z["constellation"][:, 1]
+    worst = 0.0
+    for i in range(z["f_y"].shape[0]):
+        y = z["f_y"][i, :, 0] + 1j * z["f_y"][i, :, 1]
+        cl, _ = ko.kmeans(y, pts)
+        assert np.allclose(cl, z["f_clusters"][i, :, 0] + 1j * z["f_clusters"][i, :, 1], rtol=0, atol=1e-13)
+        hh = y[np.argmax(np.abs(y))] / pts[0]      # textbook variant from the same start
+        prev = None
+        for _ in range(20):
+            c = pts * hh
+            a = np.argmin(np.abs(y[:, None] - c[None, :]), axis=1)
+            if prev is not None and np.array_equal(c, prev):
+                break
+            prev = c
+            hh = y[a == 0].mean() / pts[0] if np.any(a == 0) else hh
+        worst = max(worst, abs(hh - cl[0] / pts[0]) / abs(cl[0] / pts[0]))
+    assert worst > 1e-3, worst
