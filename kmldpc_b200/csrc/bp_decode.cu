@@ -71,6 +71,7 @@ __device__ __forceinline__ uint32_t v2c_word(float ext, uint32_t pb) {
 
 // sign bit of (x ^ w) as a predicate in ONE instruction (LOP3.LUT with a predicate destination) — the C form
 // `(int)(x ^ w) < 0` compiles to LOP3 + ISETP.  LUT of (a ^ b) & c = (0xF0 ^ 0xCC) & 0xAA = 0x28.
+#pragma nv_diag_suppress 550  // (`d` is the instruction's mandatory 32-bit destination)
 __device__ __forceinline__ bool sign_xor(uint32_t x, uint32_t w) {
   uint32_t d, r;
   asm("{.reg .pred pp; lop3.or.b32 %0|pp, %2, %3, 0x80000000, 0x28, 0; selp.u32 %1, 1, 0, pp;}"
@@ -78,6 +79,7 @@ __device__ __forceinline__ bool sign_xor(uint32_t x, uint32_t w) {
   (void)d;
   return r != 0;
 }
+#pragma nv_diag_default 550
 
 // c2v ratio P0/P1 from the small probability s and the output's hard decision (sign bit of xw).  The clip of c2v0 to
 // [1e-12, 1-1e-12] (binaryldpccodec.cc:259-263) acts on the small side only.  q = (1-s)/s is the ratio for hard = 0;
