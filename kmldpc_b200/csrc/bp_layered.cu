@@ -40,7 +40,7 @@ __device__ __forceinline__ void group_barrier(int id, int threads) {
 // One check of degree D: thread-private compressed state `st`, posteriors L.  Returns 1 if the check saw unsatisfied parity
 // or moved a decision.
 template <int D>
-__device__ __forceinline__ int layer_check(float *L, uint32_t *st, int G, const uint32_t *cs_l, int z, int Z, float alpha, float beta) {
+__device__ __forceinline__ int layer_check(float *L, uint32_t *st, int G, const uint16_t *tab_l, float alpha, float beta) {
   const __half2 mm = *reinterpret_cast<const __half2 *>(st);  // (min1, min2) of the last visit, already scaled
   const uint32_t meta = st[G];                                   // bits 0-15: sign of each old message, 16-19: index of min1
   const float om1 = __low2float(mm), om2 = __high2float(mm);
@@ -52,10 +52,7 @@ __device__ __forceinline__ int layer_check(float *L, uint32_t *st, int G, const 
   uint32_t sgn = 0, par = 0, hard = 0, dec = 0;
 #pragma unroll
   for (int k = 0; k < D; k++) {
-    const uint32_t cs = cs_l[k];  // block column * Z in the high half, shift in the low half
-    int zz = z + (int)(cs & 0xFFFFu);
-    zz = zz >= Z ? zz - Z : zz;
-    col[k] = (int)(cs >> 16) + zz;
+    col[k] = tab_l[k * G];  // this thread's variable in block k of the layer (CTA-wide table, see the kernel)
     const float lv = L[col[k]];
     const uint32_t bit = lv > 0.0f ? 0u : 1u;  // the decision this check sees (tie → 1, like the other decoders)
     hard ^= bit;
@@ -100,11 +97,22 @@ __global__ void __launch_bounds__(LAY_MAX_THREADS, 2) ms_layered_kernel(const De
   for (int i = threadIdx.x; i <= lt.n_layers; i += blockDim.x) s_ptr[i] = __ldg(lt.lay_ptr + i);
   __syncthreads();
   const int Z = lt.z, G = blockDim.x / LAY_FPC;  // G = threads per frame group (Z rounded up to a warp multiple)
+  // tab[e][z] = the variable check z meets in block e: (block column) * Z + (z + shift) mod Z — the same for every frame, so it
+  // is expanded once per CTA (one LDS.U16 per edge instead of seven integer instructions)
+  uint16_t *tab = reinterpret_cast<uint16_t *>(lsm);
+  for (int i = threadIdx.x; i < lt.n_edges * G; i += blockDim.x) {
+    const uint32_t cs = s_cs[i / G];
+    int zz = i % G + (int)(cs & 0xFFFFu);
+    zz = zz >= Z ? zz - Z : zz;
+    tab[i] = (uint16_t)((cs >> 16) + (zz < Z ? zz : 0));
+  }
+  __syncthreads();
+  const int tab_words = (lt.n_edges * G + 1) / 2;
   const int grp = threadIdx.x / G, z = threadIdx.x % G, lane = threadIdx.x & 31;
   const int n = p.t.n, NL = lt.n_layers;
   // per group: posteriors L[n], then the compressed messages [NL][2][G]
   const int grp_words = ((n + 3) & ~3) + NL * G * 2;
-  float *L = reinterpret_cast<float *>(lsm) + (size_t)grp * grp_words;
+  float *L = reinterpret_cast<float *>(lsm) + ((tab_words + 3) & ~3) + (size_t)grp * grp_words;
   uint32_t *cm = reinterpret_cast<uint32_t *>(L + ((n + 3) & ~3));
   __shared__ int s_frame[LAY_FPC];
   const bool active = z < Z;
@@ -129,18 +137,18 @@ __global__ void __launch_bounds__(LAY_MAX_THREADS, 2) ms_layered_kernel(const De
         if (active) {
           const int e0 = s_ptr[l], d = s_ptr[l + 1] - e0;
           uint32_t *st = cm + (l * 2) * G + z;  // two planes per layer: conflict-free for the group's lanes
-          const uint32_t *cs_l = s_cs + e0;
+          const uint16_t *tab_l = tab + e0 * G + z;
           switch (d) {  // (uniform per layer; compiled per degree so that short rows do not issue ten predicated edges)
-            case 3: fail |= layer_check<3>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 4: fail |= layer_check<4>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 5: fail |= layer_check<5>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 6: fail |= layer_check<6>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 7: fail |= layer_check<7>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 8: fail |= layer_check<8>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 9: fail |= layer_check<9>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 10: fail |= layer_check<10>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            case 2: fail |= layer_check<2>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
-            default: fail |= layer_check<1>(L, st, G, cs_l, z, Z, p.alpha, p.beta); break;
+            case 3: fail |= layer_check<3>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 4: fail |= layer_check<4>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 5: fail |= layer_check<5>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 6: fail |= layer_check<6>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 7: fail |= layer_check<7>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 8: fail |= layer_check<8>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 9: fail |= layer_check<9>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 10: fail |= layer_check<10>(L, st, G, tab_l, p.alpha, p.beta); break;
+            case 2: fail |= layer_check<2>(L, st, G, tab_l, p.alpha, p.beta); break;
+            default: fail |= layer_check<1>(L, st, G, tab_l, p.alpha, p.beta); break;
           }
         }
         group_barrier(bar_id, G);  // the next layer's checks read these posteriors
@@ -180,9 +188,10 @@ __global__ void __launch_bounds__(LAY_MAX_THREADS, 2) ms_layered_kernel(const De
 }  // namespace
 
 int layered_threads(int z) { return LAY_FPC * ((z + 31) & ~31); }
-int layered_smem_bytes(int n, int n_layers, int z) {
+int layered_smem_bytes(int n, int n_layers, int n_edges, int z) {
   const int G = (z + 31) & ~31;
-  return LAY_FPC * ((((n + 3) & ~3) + n_layers * G * 2) * 4);
+  const int tab_words = (n_edges * G + 1) / 2;
+  return (((tab_words + 3) & ~3) + LAY_FPC * (((n + 3) & ~3) + n_layers * G * 2)) * 4;
 }
 int layered_max_degree() { return LAY_DC; }
 int layered_max_threads() { return LAY_MAX_THREADS; }

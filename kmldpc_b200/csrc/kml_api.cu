@@ -251,7 +251,7 @@ int build_layered_tables(kml_ctx *c, const kml_code *code) {
   dl.kind = c->dl_alg[0].kind;
   dl.alg = 3;
   dl.threads = layered_threads(z_found);
-  dl.smem_bytes = layered_smem_bytes(N, NL, z_found);
+  dl.smem_bytes = layered_smem_bytes(N, NL, (int)cs.size(), z_found);
   if (dl.threads > layered_max_threads() || dl.smem_bytes > 227 * 1024) {
     c->lay_why = "lifting size too large for the layered kernel's frames-per-CTA tiling";
     return KML_OK;

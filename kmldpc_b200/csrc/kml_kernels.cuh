@@ -105,7 +105,7 @@ dec_kernel_t minsum_kernel_of(DecKernelKind k, int alg);
 // bp_layered.cu (algorithm = 3: layered min-sum for quasi-cyclic codes)
 dec_kernel_t layered_kernel();
 int layered_threads(int z);
-int layered_smem_bytes(int n, int n_layers, int z);
+int layered_smem_bytes(int n, int n_layers, int n_edges, int z);
 int layered_max_degree();
 int layered_max_threads();
 int layered_max_edges();
