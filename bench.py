@@ -555,6 +555,18 @@ def gpu_arm(args):
         b.record()
         torch.cuda.synchronize()
         thr["minsum_fp16x2_I50_receiver_mbps"] = 5 * B * K_INFO / (a.elapsed_time(b) * 1e-3) / 1e6
+        for iters in (10, 5):  # the whole receiver (k-means + resolve + demap + decode) at a smaller fixed iteration count
+            l2 = kb.Link(link.code, link.modem, max_iter=iters, kmeans_iter=KMEANS_ITER, early_exit=False, max_batch=B,
+                         device=dev.index, algorithm=2)
+            for i in range(2):
+                l2.receive_dev(B, ys[i % pool].data_ptr(), var, uu_hat.data_ptr(), ret.data_ptr(), stream=stream)
+            a.record()
+            for i in range(5):
+                l2.receive_dev(B, ys[i % pool].data_ptr(), var, uu_hat.data_ptr(), ret.data_ptr(), stream=stream)
+            b.record()
+            torch.cuda.synchronize()
+            thr[f"minsum_fp16x2_I{iters}_receiver_mbps"] = 5 * B * K_INFO / (a.elapsed_time(b) * 1e-3) / 1e6
+            l2.close()
         thr["note"] = ("decode-only = kml_decode_dev on HBM-resident LLRs, early exit off, CUDA events; min-sum is not in the "
                        "reference (no parity claim): gated by tests/test_gpu_minsum.py against the sum-product decoder")
         link.set_algorithm(0)

@@ -176,3 +176,48 @@ def test_layered_needs_a_quasi_cyclic_code():
     link.close()
     with pytest.raises(kb.KmlError, match="layered"):
         util.gpu_link("peg2304_4psk_6db", algorithm=3)
+
+
+def test_sweep_driver_accepts_the_throughput_algorithms(tmp_path):
+    """`[gpu] algorithm` in config.toml reaches the decoder through kml_sweep_run: the 5G sweep with the layered and the
+    flooding min-sum gives the sum-product's FER within the gate; algorithm 3 on a code without quasi-cyclic structure is an
+    error with a message, not a crash."""
+    import kmldpc_b200 as kb
+
+    def run(matrix, is5g, alg):
+        cfg = tmp_path / f"cfg_{alg}_{int(is5g)}.toml"
+        cfg.write_text(f"""[range]
+minimum_snr = 10.0
+maximum_snr = 12.0
+step_snr = 2.0
+maximum_error_number = 100000000
+maximum_block_number = 8192
+thread_block_number = 32
+[decoder]
+true_h_arg = false
+[xcodec]
+5gldpc = {"true" if is5g else "false"}
+metric_type = false
+metric_iter = 5
+[histogram]
+enable = false
+[ldpc]
+max_iter = 50
+active = true
+matrix_file = "{matrix}"
+[modem]
+modem_file = "4bit_16QAM_Gray.txt"
+[gpu]
+seed = 17
+batch = 2048
+algorithm = {alg}
+""")
+        return kb.Simulator(str(cfg), data_dir=util.ko.CONFIG_DIR).simulate(echo=False)
+
+    _, _, fer0, cnt0 = run("5GLDPCBG2a3_R12_K960.txt", True, 0)
+    for alg in (1, 3):
+        _, _, fer, cnt = run("5GLDPCBG2a3_R12_K960.txt", True, alg)
+        assert (cnt[:, 0] == 8192).all()
+        assert np.all(np.abs(fer - fer0) <= 0.03), (alg, fer, fer0)
+    with pytest.raises(kb.KmlError, match="layered"):
+        run("PEG2304regular0.5.txt", False, 3)
