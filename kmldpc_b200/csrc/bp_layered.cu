@@ -16,7 +16,9 @@
 //     L[col_k] = v_k + c2v_k                           (d stores)
 // The old messages of a check are kept COMPRESSED — (min1, min2) as one half2 word and (index of the minimum, sign bits)
 // as another — two words per check and layer, thread-private in shared memory.  Per edge-iteration: one LDS + one STS of
-// 4 bytes, against four of them for the flooding kernels, and no variable-node phase at all.
+// 4 bytes (plus a 16-bit table read for the variable's index), against four 4-byte accesses for the flooding kernels, and
+// no variable-node phase at all.  What it costs instead is compare / select work on the half-rate ALU pipe (measured:
+// profiles/r2s_layered_5G_full_B8192.txt), which is why it does not beat the flooding plan kernel per iteration.
 //
 // One CTA holds FPC frames (groups of Z threads, each with its own named barrier and its own place in the frame queue).
 #include <cuda_fp16.h>
@@ -87,7 +89,6 @@ __device__ __forceinline__ int layer_check(float *L, uint32_t *st, int G, const 
 }
 
 // (3 CTAs per SM at 56 registers: measured no faster — the kernel is issue-bound)
-template <int DC>
 __global__ void __launch_bounds__(LAY_MAX_THREADS, 2) ms_layered_kernel(const DecParams p) {
   extern __shared__ __align__(16) unsigned char lsm[];
   const LayeredTables &lt = p.lay;
@@ -198,6 +199,6 @@ int layered_max_threads() { return LAY_MAX_THREADS; }
 int layered_max_edges() { return LAY_MAX_EDGES; }
 int layered_max_layers() { return LAY_MAX_LAYERS; }
 int layered_frames_per_cta() { return LAY_FPC; }
-dec_kernel_t layered_kernel() { return ms_layered_kernel<LAY_DC>; }
+dec_kernel_t layered_kernel() { return ms_layered_kernel; }
 
 }  // namespace kml
