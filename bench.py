@@ -261,7 +261,7 @@ def config_leg(kb, torch, dev, stream, smem_peak, spec, steps, with_cpu):
     thr = None
     if is_5g:  # BASELINE names "min-sum decoding" for this config; the reference has none → throughput mode, BER/FER-gated only
         thr = {"note": "whole receiver, same step; NOT the reference's algorithm (tests/test_gpu_minsum.py gates them)"}
-        for alg, label in ((1, "minsum_flooding_fp32"), (3, "minsum_layered")):
+        for alg, label in ((1, "minsum_flooding_fp32"), (2, "minsum_flooding_fp16x2"), (3, "minsum_layered")):
             link.set_algorithm(alg, 0.8)
             step(0)
             torch.cuda.synchronize()

@@ -88,8 +88,8 @@ typedef struct kml_opts {
   int32_t algorithm;     /* 0 = flooding sum-product = the reference's decoder (parity mode);
                             1 = normalised min-sum, fp32 messages (throughput mode; NOT in the reference, hence not
                                 reference-pinned: checked against oracle/minsum_ref.py and gated by BER/FER against 0);
-                            2 = the same with fp16 messages, two frames per shared-memory word ((3,6)-regular codes;
-                                other graphs run algorithm 1);
+                            2 = the same with fp16 messages, two frames per shared-memory word ((3,6)-regular codes and
+                                the quasi-cyclic 5G BG2 plan; other graphs run algorithm 1);
                             3 = layered (row-serial) min-sum on the block structure of a quasi-cyclic code (the 5G
                                 BG2 code; four frames per CTA); an error for codes without that structure */
 } kml_opts;

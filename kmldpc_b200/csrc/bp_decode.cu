@@ -30,6 +30,8 @@
 #include <type_traits>
 #include <utility>
 
+#include <cuda_fp16.h>
+
 #include "kml_internal.h"
 #include "kml_kernels.cuh"
 #include "bp_minsum_nodes.cuh"
@@ -801,17 +803,127 @@ __device__ __forceinline__ void qc_quarter(const DecParams &p, uint32_t *msg, vo
   }
 }
 
+// ALG = 2: the min-sum of ALG = 1 with fp16 messages and TWO frames per 32-bit word (as ms2_regular_kernel in bp_minsum.cu):
+// a work item is a pair of queue entries, each frame latches its own decisions and return value.
+template <class P, int Q>
+__device__ __forceinline__ void qc_quarter_ms2(const DecParams &p, uint32_t *msg, volatile int *s_pair, int z) {
+  constexpr int NE = qc_voff<P, Q>(P::MAXV);
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t va[NE];
+  static_for<P::MAXV>([&](auto ic) {
+    constexpr int i = decltype(ic)::value, D = P::vdeg[Q][i], O = qc_voff<P, Q>(i);
+    if constexpr (D > 0) {
+      const int v = P::vblk[Q][i] * P::Z + z;
+#pragma unroll
+      for (int k = 0; k < D; k++) va[O + k] = __ldg(p.t.vn_addr + (size_t)v * P::DVM + k);
+    }
+  });
+  const int n_words = p.t.m_pad * P::RS;
+  const __half2 alpha2 = __float2half2_rn(p.alpha), nbeta2 = __float2half2_rn(-p.beta);
+  const bool has_offset = p.beta != 0.0f;
+  while (true) {
+    if (tid == 0) {  // two consecutive entries of the frame queue (the last item may be single: fb = fa)
+      const int nB = frame_count(p), fp = (int)atomicAdd(p.work_counter, 1u);
+      const int ia = 2 * fp, ib = min(2 * fp + 1, nB - 1);
+      s_pair[0] = ia < nB ? frame_at(p, ia) : -1;
+      s_pair[1] = ia < nB ? frame_at(p, ib) : -1;
+    }
+    __syncthreads();
+    const int fa = s_pair[0], fb = s_pair[1];
+    if (fa < 0) break;
+    const float *ina = p.in + (size_t)(p.sel ? fa * p.n_cand + __ldg(p.sel + fa) : fa) * p.t.n_tx;
+    const float *inb = p.in + (size_t)(p.sel ? fb * p.n_cand + __ldg(p.sel + fb) : fb) * p.t.n_tx;
+    __half2 ch[P::MAXV];
+    static_for<P::MAXV>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      ch[i] = __float2half2_rn(0.0f);
+      if constexpr (P::vdeg[Q][i] > 0) {
+        const int v = P::vblk[Q][i] * P::Z + z;  // punctured variables: prior (0.5, 0.5) (binary5gldpccodec.cc:126-130)
+        if (v >= p.t.punct)
+          ch[i] = __floats2half2_rn(msn::load_channel_llr(ina, v - p.t.punct, p.in_is_lr),
+                                    msn::load_channel_llr(inb, v - p.t.punct, p.in_is_lr));
+      }
+    });
+    for (int i = tid; i < n_words; i += blockDim.x) msg[i] = 0u;
+    __syncthreads();
+
+    uint32_t bits_a = 0, bits_b = 0, lat_a = 0, lat_b = 0;
+    const int ret_full = p.iters + (p.iters < p.max_iter);
+    int ret_a = ret_full, ret_b = ret_full, nfail_a = 0, nfail_b = 0;
+    bool done_a = false, done_b = false;
+    for (int t = 0; t < p.iters; t++) {
+      bits_a = bits_b = 0;
+      static_for<P::MAXV>([&](auto ic) {
+        constexpr int i = decltype(ic)::value, D = P::vdeg[Q][i], O = qc_voff<P, Q>(i);
+        if constexpr (D > 0) {
+          const uint32_t pb = msn::ms2_vn<D>(msg, va + O, ch[i]);
+          bits_a |= (pb & 1u) << i;
+          bits_b |= (pb >> 16) << i;
+        }
+      });
+      __syncthreads();
+      int fa_cnt = 0, fb_cnt = 0;  // this thread's unsatisfied checks of the decisions just made, per frame
+      static_for<P::MAXC>([&](auto jc) {
+        constexpr int j = decltype(jc)::value, D = P::cdeg[Q][j];
+        const uint32_t x = msn::ms2_cn<D>(msg + (P::cblk[Q][j] * P::Z + z) * P::RS, alpha2, nbeta2, has_offset);
+        fa_cnt += (int)(x & 1u);
+        fb_cnt += (int)((x >> 16) & 1u);
+      });
+      const int any_a = __syncthreads_or(fa_cnt), any_b = __syncthreads_or(fb_cnt);
+      if (!done_a) nfail_a = fa_cnt;  // (a latched frame reports syndrome weight 0 below)
+      if (!done_b) nfail_b = fb_cnt;
+      if (!any_a && !done_a) { done_a = true; lat_a = bits_a; ret_a = t + (t < p.max_iter); }
+      if (!any_b && !done_b) { done_b = true; lat_b = bits_b; ret_b = t + (t < p.max_iter); }
+      if (done_a && done_b && p.early_exit) break;
+    }
+    if (!done_a) lat_a = bits_a;
+    if (!done_b) lat_b = bits_b;
+    static_for<P::MAXV>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      if constexpr (P::vdeg[Q][i] > 0) {
+        const uint32_t wa = __ballot_sync(0xffffffffu, (lat_a >> i) & 1u), wb = __ballot_sync(0xffffffffu, (lat_b >> i) & 1u);
+        if (lane == 0) {
+          p.out_bits[(size_t)fa * p.words_n + ((P::vblk[Q][i] * P::Z + z) >> 5)] = wa;
+          if (fb != fa) p.out_bits[(size_t)fb * p.words_n + ((P::vblk[Q][i] * P::Z + z) >> 5)] = wb;
+        }
+      }
+    });
+    if (tid == 0) {
+      p.out_ret[fa] = ret_a;
+      if (fb != fa) p.out_ret[fb] = ret_b;
+    }
+    if (p.out_synd) {  // ParityCheck(cc_hat) of the final decisions, per frame (see qc_quarter)
+      static_assert(P::MAXC <= 3, "two count bits");
+      const int ta = __syncthreads_count(nfail_a & 1) + 2 * __syncthreads_count(nfail_a & 2);
+      const int tb = __syncthreads_count(nfail_b & 1) + 2 * __syncthreads_count(nfail_b & 2);
+      if (tid == 0) {
+        p.out_synd[fa] = done_a ? 0.0f : (float)ta;
+        if (fb != fa) p.out_synd[fb] = done_b ? 0.0f : (float)tb;
+      }
+    }
+  }
+}
+
 template <class P, int MINB, int ALG>
 __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p) {
   static_assert(P::Z % 32 == 0, "a warp must not straddle two quarters");
   extern __shared__ uint32_t msg[];  // [m_pad][RS]
-  __shared__ int s_frame;
+  __shared__ int s_frame[2];         // the frame (ALG 0 / 1) or the pair of frames (ALG 2) being decoded
   const int q = threadIdx.x / P::Z, z = threadIdx.x % P::Z;
-  switch (q) {  // warp-uniform
-    case 0: qc_quarter<P, 0, ALG>(p, msg, &s_frame, z); break;
-    case 1: qc_quarter<P, 1, ALG>(p, msg, &s_frame, z); break;
-    case 2: qc_quarter<P, 2, ALG>(p, msg, &s_frame, z); break;
-    default: qc_quarter<P, 3, ALG>(p, msg, &s_frame, z); break;
+  if constexpr (ALG == 2) {
+    switch (q) {  // warp-uniform
+      case 0: qc_quarter_ms2<P, 0>(p, msg, s_frame, z); break;
+      case 1: qc_quarter_ms2<P, 1>(p, msg, s_frame, z); break;
+      case 2: qc_quarter_ms2<P, 2>(p, msg, s_frame, z); break;
+      default: qc_quarter_ms2<P, 3>(p, msg, s_frame, z); break;
+    }
+  } else {
+    switch (q) {  // warp-uniform
+      case 0: qc_quarter<P, 0, ALG>(p, msg, s_frame, z); break;
+      case 1: qc_quarter<P, 1, ALG>(p, msg, s_frame, z); break;
+      case 2: qc_quarter<P, 2, ALG>(p, msg, s_frame, z); break;
+      default: qc_quarter<P, 3, ALG>(p, msg, s_frame, z); break;
+    }
   }
 }
 
@@ -821,7 +933,8 @@ __global__ void __launch_bounds__(4 * P::Z, MINB) bp_qc_kernel(const DecParams p
 // the A/B and timing-ablation variants exist only in a -DKML_TUNING build.
 dec_kernel_t kernel_of(DecKernelKind k, int alg, int rowmajor, bool soft, int qc_plan, int threads) {
   if (alg == 3) return layered_kernel();
-  if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;  // (fp16 x 2 frames exists for regular codes only)
+  if (alg == 2 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 2>;  // fp16 x 2 frames per word
+  if (alg != 0 && qc_plan == 1) return bp_qc_kernel<QcPlanBg2R12, 3, 1>;
   if (alg != 0) return minsum_kernel_of(k, alg);
   if (qc_plan == 1 && !soft) {
 #ifdef KML_TUNING
@@ -962,7 +1075,7 @@ cudaError_t dec_launch(const DecLaunch &l, const DecParams &p, int num_sms, cuda
   if (e != cudaSuccess) return e;
   int grid = num_sms * l.ctas_per_sm;
   // work items in the frame queue per CTA: a pair of frames (fp16 x 2), or the layered kernel's concurrent frame groups
-  const int per = l.alg == 3 ? layered_frames_per_cta() : (dec_two_frames_per_cta(l.kind, l.alg) ? 2 : 1);
+  const int per = l.alg == 3 ? layered_frames_per_cta() : ((dec_two_frames_per_cta(l.kind, l.alg) || (l.alg == 2 && l.qc_plan)) ? 2 : 1);
   const int units = (p.B + per - 1) / per;
   if (grid > units) grid = units;
   if (grid < 1) return cudaSuccess;

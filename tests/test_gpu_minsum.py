@@ -87,7 +87,8 @@ def test_minsum_rejects_soft_metric():
 
 
 @pytest.mark.parametrize("name,snr,frames", [("peg2304_4psk_6db", 6.0, 30000), ("peg2304_16qam_gray_12db", 15.0, 30000),
-                                             ("peg8064_64qam_20db", 22.0, 6000)])
+                                             ("peg8064_64qam_20db", 22.0, 6000), ("5g_16qam_gray_10db", 10.0, 20000),
+                                             ("5g_16qam_gray_10db", 14.0, 20000)])
 def test_fp16_two_frame_minsum_gate(name, snr, frames):
     """algorithm = 2 (fp16 messages, two frames per shared-memory word): BER/FER gate against the sum-product decoder on the
     same frames, and pairing must not couple frames: odd batches and shifted pairings give the same per-frame answers."""

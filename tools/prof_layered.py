@@ -11,7 +11,7 @@ from tests import util  # noqa: E402
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
 link = util.gpu_link("5g_16qam_gray_10db", max_batch=16384)
 for snr in (8.0, 10.0, 12.0, 15.0):
-    for alg in (0, 1, 3):
+    for alg in (0, 1, 2, 3):
         link.set_algorithm(alg, 0.8)
         link.simulate(snr, 32768, seed=5)
         t0 = time.perf_counter()
