@@ -207,6 +207,40 @@ def test_survey_fer_curve_replayed(snr, frame_errors, kb):
     link.close()
 
 
+@pytest.mark.parametrize("matrix,modem,is5g,snr,opts", [
+    ("PEG2304regular0.5.txt", "2bits_4PSK.txt", False, 8.0, dict(max_iter=1)),
+    ("PEG2304regular0.5.txt", "2bits_4PSK.txt", False, 8.0, dict(max_iter=2, kmeans_iter=1)),
+    ("PEG2304regular0.5.txt", "4bit_16QAM_Gray.txt", False, 14.0, dict(max_iter=7, kmeans_iter=3)),
+    ("5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, 12.0, dict(max_iter=3, metric_iter=1)),
+    ("5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, 12.0, dict(max_iter=50, metric_iter=8, kmeans_iter=2)),
+    ("PEG2304regular0.5.txt", "2bits_4PSK.txt", False, 8.0, dict(max_iter=4, metric_type=True, metric_iter=2)),
+])
+def test_unusual_iteration_options(matrix, modem, is5g, snr, opts, kb):
+    """The iteration counts the configuration file can set ([ldpc] max_iter, [xcodec] metric_iter) and the k-means pass limit,
+    at their small ends: the CUDA receiver against the oracle on the oracle's own frames — estimate, choice, return value
+    (incl. the `iter + (iter < max_iter)` convention at max_iter = 1), decisions of converged frames, frame errors."""
+    olink = util.ko.Link(matrix, modem, is_5g=is5g, **opts)
+    g = util.ko.Lcg(17)
+    rs = [olink.frame(g, snr, full=True) for _ in range(48)]
+    link = kb.Link(kb.LdpcCode(matrix, is_5g=is5g), kb.Modem(modem), max_batch=32, **opts)
+    uu_p, hhat, kstar, ret = link.receive_f64(np.stack([r.y for r in rs]), 10 ** (-0.1 * snr))
+    ref_h = np.array([r.hhat for r in rs])
+    assert (np.abs(hhat - ref_h) / np.abs(ref_h)).max() <= 1e-10
+    ref_k, ref_ret = np.array([r.kstar for r in rs]), np.array([r.ret for r in rs])
+    if opts.get("metric_type"):  # (soft metric: candidate 0 may inherit a chaotic value, test_parity_statistics_at_scale)
+        assert (kstar == ref_k).mean() >= 0.9
+    else:
+        assert np.array_equal(kstar, ref_k)
+    good = kstar == ref_k
+    assert np.array_equal(ret[good], ref_ret[good])
+    uu = kb.unpack_bits(uu_p, olink.code.K)
+    conv = good & np.array([olink.code.parity_check(r.cc_hat) == 0 for r in rs])
+    assert np.array_equal(uu[conv], np.stack([r.uu_hat for r in rs])[conv])
+    u = np.stack([r.u for r in rs])
+    assert ((uu != u).any(axis=1) == np.array([r.nerr > 0 for r in rs]))[good].mean() >= 0.97
+    link.close()
+
+
 def test_golden_fixture_replay(kb):
     """Channel outputs dumped from the UNMODIFIED reference (tests/golden) → same k*, return value, decisions."""
     z, p = util.golden("peg2304_16qam_gray_12db")
