@@ -241,6 +241,38 @@ def test_unusual_iteration_options(matrix, modem, is5g, snr, opts, kb):
     link.close()
 
 
+@pytest.mark.parametrize("matrix,modem,is5g,active,snr,opts,frames", [
+    ("5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, True, 10.0, dict(known_h=True), 40),
+    ("5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", True, False, 10.0, dict(), 40),
+    ("5GLDPCBG2a3_R12_K960.txt", "2bits_QPSK.txt", True, True, 6.0, dict(), 40),
+    ("5GLDPCBG2a3_R12_K960.txt", "6bits_64QAM_Gray.txt", True, True, 18.0, dict(), 24),
+    ("PEG8064regular0.5.txt", "4bit_16QAM_phi2.txt", False, True, 14.0, dict(known_h=True), 10),
+    ("PEG2304regular0.5.txt", "6bits_64QAM_Gray.txt", False, True, 20.0, dict(), 40),
+])
+def test_option_and_file_combinations_outside_the_fixtures(matrix, modem, is5g, active, snr, opts, frames, kb):
+    """Combinations of code, constellation and switches that no committed fixture holds (5G with known h / encoder off / QPSK /
+    64QAM, PEG8064 with a phi mapping, PEG2304 with 64QAM): CUDA receiver against the oracle on the oracle's frames."""
+    olink = util.ko.Link(matrix, modem, is_5g=is5g, active=active, **opts)
+    g = util.ko.Lcg(17)
+    rs = [olink.frame(g, snr, full=True) for _ in range(frames)]
+    link = kb.Link(kb.LdpcCode(matrix, is_5g=is5g, active=active), kb.Modem(modem), max_batch=16, **opts)
+    th = np.array([r.h for r in rs]) if opts.get("known_h") else None
+    uu_p, hhat, kstar, ret = link.receive_f64(np.stack([r.y for r in rs]), 10 ** (-0.1 * snr), true_h=th)
+    if th is None:
+        ref_h = np.array([r.hhat for r in rs])
+        assert (np.abs(hhat - ref_h) / np.abs(ref_h)).max() <= 1e-10
+        assert np.array_equal(kstar, np.array([r.kstar for r in rs]))
+    assert np.array_equal(ret, np.array([r.ret for r in rs]))
+    uu = kb.unpack_bits(uu_p, olink.code.K)
+    conv = np.array([olink.code.parity_check(r.cc_hat) == 0 for r in rs])
+    assert conv.sum() > 0 and np.array_equal(uu[conv], np.stack([r.uu_hat for r in rs])[conv])
+    u = np.stack([r.u for r in rs])
+    if not active:
+        assert not u.any()
+    assert ((uu != u).any(axis=1) == np.array([r.nerr > 0 for r in rs])).mean() >= 0.97
+    link.close()
+
+
 def test_golden_fixture_replay(kb):
     """Channel outputs dumped from the UNMODIFIED reference (tests/golden) → same k*, return value, decisions."""
     z, p = util.golden("peg2304_16qam_gray_12db")
