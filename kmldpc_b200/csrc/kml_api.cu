@@ -69,6 +69,8 @@ struct kml_ctx {
   DevBuf<int32_t> row_ptr, col_idx;
   KmConst km{};  // fp64 constants of the k-means kernel (n_nb = 0: general kernel)
   int rot_symmetric = 0, rot_perm[3][64];  // s_k e^{j c pi/2} = s_{rot_perm[c-1][k]} for every k (else rot_symmetric = 0)
+  int grid64 = 0;                          // the constellation is the square Gray grid compiled into demap_symbol_grid64
+  float grid_levels[8] = {};
   DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
   DevBuf<uint32_t> vn_items, cn_items;
   int ell_width = 0;
@@ -542,6 +544,8 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   d.symmetric = c->rot_symmetric;
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
+  d.grid64 = c->grid64;
+  std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
   const int32_t *sel = nullptr;
   int n_cand = 1;
   if (c->opts.known_h) {
@@ -679,6 +683,40 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
             if (!used[m] && std::hypot(modem->points[2 * m] - xr, modem->points[2 * m + 1] - xi) < 1e-9) { hit = m; break; }
           if (hit < 0) c->rot_symmetric = 0;
           else { used[hit] = 1; c->rot_perm[cc - 1][k] = hit; }
+        }
+      }
+    }
+    {  // 64 points on a square grid with the Gray labelling demap_symbol_grid64 has compiled in (link_kernels.cu): levels
+       // ascending l_0..l_7 = -l_7..-l_0 on both axes, point k at (level i, level j) with label bits (MSB first)
+       // i >= 4, i in 2..5, i in {1,2,5,6}, j < 4, j in 2..5, j in {1,2,5,6}.  Anything else keeps the general 64-point path.
+      c->grid64 = 0;
+      const char *e = knob("KML_DEMAP_NO_GRID");  // shipped fallback (announced on stderr): the quad-of-lanes demapper
+      if (c->Q == 64 && c->rot_symmetric && !(e && atoi(e))) {
+        std::vector<double> lv;
+        for (int k = 0; k < 64; k++) {
+          bool seen = false;
+          for (double v : lv) seen = seen || std::fabs(v - modem->points[2 * k]) < 1e-9;
+          if (!seen) lv.push_back(modem->points[2 * k]);
+        }
+        std::sort(lv.begin(), lv.end());
+        bool ok = lv.size() == 8;
+        for (int i = 0; ok && i < 8; i++) ok = std::fabs(lv[i] + lv[7 - i]) < 1e-9;
+        auto level_of = [&](double v) {
+          for (int i = 0; i < 8; i++)
+            if (std::fabs(lv[i] - v) < 1e-9) return i;
+          return -1;
+        };
+        for (int k = 0; ok && k < 64; k++) {
+          const int i = level_of(modem->points[2 * k]), j = level_of(modem->points[2 * k + 1]);
+          if (i < 0 || j < 0) { ok = false; break; }
+          const int mid_i = (i >= 2 && i <= 5), low_i = (i == 1 || i == 2 || i == 5 || i == 6);
+          const int mid_j = (j >= 2 && j <= 5), low_j = (j == 1 || j == 2 || j == 5 || j == 6);
+          const int label = ((i >= 4) << 5) | (mid_i << 4) | (low_i << 3) | ((j < 4) << 2) | (mid_j << 1) | low_j;
+          ok = label == k;
+        }
+        if (ok) {
+          c->grid64 = 1;
+          for (int i = 0; i < 8; i++) c->grid_levels[i] = (float)lv[i];
         }
       }
     }
@@ -934,6 +972,8 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   d.symmetric = c->rot_symmetric;
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
+  d.grid64 = c->grid64;
+  std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
   return d;
 }
 

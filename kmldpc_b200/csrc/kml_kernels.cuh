@@ -181,6 +181,9 @@ struct DemapParams {
   // candidate c's point probabilities are candidate 0's, re-labelled
   int symmetric;
   int perm[3][64];
+  // 64 points that form the square Gray-mapped grid compiled into demap_symbol_grid64 (host check): the 8 levels of an axis
+  int grid64;
+  float levels[8];
   int skip_decode, words_n;
   uint32_t *out_bits;
   int32_t *out_ret;

@@ -745,7 +745,8 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
   }
 }
 
-// 64-point constellations: FOUR lanes share a symbol, 16 points each (lane t of the quad owns the points whose two
+// 64-point constellations WITHOUT the separable structure demap_symbol_grid64 needs (or under KML_DEMAP_NO_GRID=1): FOUR
+// lanes share a symbol, 16 points each (lane t of the quad owns the points whose two
 // top label bits are t).  One thread per symbol needs all 64 probabilities live (126 registers → 16 warps per SM, the
 // kernel then runs at half its own instruction bound); a quad keeps 16, exchanges minimum / sum / the bit marginals
 // with 24 shuffles per candidate, and lets 4x more warps be resident.  Same arithmetic as demap_symbol (the sums of a
@@ -831,6 +832,104 @@ __device__ __forceinline__ void demap_symbol_quad64(const float2 yy, const float
   }
 }
 
+// 64QAM on a square grid with a Gray mapping that splits the label into an in-phase and a quadrature half (the shipped
+// 6bits_64QAM_Gray.txt; the host verifies the structure point by point and otherwise keeps demap_symbol_quad64): ONE
+// thread per symbol, ALL candidates from 16 exponentials.
+//   * With z = y / h the exponent -|s h - y|^2 / var = -(|h|^2 / var) ((Re s - Re z)^2 + (Im s - Im z)^2) separates, so the
+//     normalised point probabilities are products  p_(i,j) = a_i b_j  of two 8-point softmaxes (levels against Re z and
+//     against Im z): 16 exponentials instead of 64.
+//   * The reference clips every p_k to >= 1e-12 BEFORE the bit marginals (modemlinearsystem.cc:78, modem.cc:26-27), which
+//     does not separate — so the 8 x 8 grid of max(a_i b_j, 1e-12) is formed (one FMUL + FMNMX per point) and reduced to its
+//     row sums R_i and column sums C_j; a bit of the in-phase half is a ratio of sums of R, of the quadrature half of C.
+//   * Candidate c divides by h e^{j c pi/2}: z turns by -c quarter turns, which on a symmetric grid only swaps / reverses the
+//     roles of the two axes: (I, Q) marginals = (R, C), (C, rev R), (rev R, rev C), (rev C, R) for c = 0..3.  Reversal
+//     leaves the label sets {0,1,6,7}|{2..5} and {0,3,4,7}|{1,2,5,6} of the two lower Gray bits in place and swaps the
+//     halves of the top bit: eight ratios serve all 24 (candidate, bit) outputs.
+// Label layout compiled in (levels ascending, MSB first): bit 0 = level >= 4, bit 1 = level in 2..5, bit 2 = level in
+// {1,2,5,6} of the in-phase axis; bit 3 = level < 4, bits 4, 5 like 1, 2 of the quadrature axis.
+struct GridSums {
+  float t0, t1, m0, m1, l0, l1;  // levels 0-3 | 4-7, {0,1,6,7} | {2..5}, {0,3,4,7} | {1,2,5,6}
+};
+__device__ __forceinline__ GridSums grid_sums(const float (&x)[8]) {
+  const float p01 = x[0] + x[1], p23 = x[2] + x[3], p45 = x[4] + x[5], p67 = x[6] + x[7];
+  GridSums g;
+  g.t0 = p01 + p23; g.t1 = p45 + p67;
+  g.m0 = p01 + p67; g.m1 = p23 + p45;
+  g.l0 = (x[0] + x[3]) + (x[4] + x[7]); g.l1 = (x[1] + x[2]) + (x[5] + x[6]);
+  return g;
+}
+__device__ __forceinline__ float grid_ratio(float z0, float z1) { return fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax); }
+
+template <int NC>
+__device__ __forceinline__ void demap_symbol_grid64(const float2 yy, const float2 hb, float inv_var, const float (&lv)[8],
+                                                    float *lr_base, size_t lr_stride, unsigned int (&rr)[6]) {
+  const float h2 = fmaf(hb.x, hb.x, hb.y * hb.y);
+  const bool live = h2 > 1.0e-30f;  // (h = 0: every point coincides, the softmax is uniform)
+  const float ih2 = live ? dm_rcp(h2) : 0.0f;
+  const float zr = (yy.x * hb.x + yy.y * hb.y) * ih2, zi = (yy.y * hb.x - yy.x * hb.y) * ih2;
+  const float g = live ? h2 * inv_var * 1.4426950408889634f : 0.0f;  // exponents in bits: ex2 below
+  float a[8], b[8], ma = -3.0e38f, mb = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float dr = lv[i] - zr, di = lv[i] - zi;
+    a[i] = -g * dr * dr;
+    b[i] = -g * di * di;
+    ma = fmaxf(ma, a[i]);
+    mb = fmaxf(mb, b[i]);
+  }
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] = dm_ex2(a[i] - ma);
+    b[i] = dm_ex2(b[i] - mb);
+    sa += a[i];
+    sb += b[i];
+  }
+  const float ia = dm_rcp(sa), ib = dm_rcp(sb);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    a[i] *= ia;
+    b[i] *= ib;
+  }
+  float R[8], C[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) R[i] = C[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float t = fmaxf(a[i] * b[j], kSmallProbF);  // the reference's per-point clip (the upper one is 1.0f in fp32)
+      R[i] += t;
+      C[j] += t;
+    }
+  const GridSums sr = grid_sums(R), sc = grid_sums(C);
+  const float rt_r = grid_ratio(sr.t0, sr.t1), rti_r = grid_ratio(sr.t1, sr.t0), rm_r = grid_ratio(sr.m0, sr.m1),
+              rl_r = grid_ratio(sr.l0, sr.l1);
+  float ratio[NC][6];
+  ratio[0][0] = rt_r; ratio[0][1] = rm_r; ratio[0][2] = rl_r;
+  {
+    const float rti_c = grid_ratio(sc.t1, sc.t0), rm_c = grid_ratio(sc.m0, sc.m1), rl_c = grid_ratio(sc.l0, sc.l1);
+    ratio[0][3] = rti_c; ratio[0][4] = rm_c; ratio[0][5] = rl_c;
+    if constexpr (NC == 4) {
+      const float rt_c = grid_ratio(sc.t0, sc.t1);
+      ratio[1][0] = rt_c;  ratio[1][1] = rm_c; ratio[1][2] = rl_c; ratio[1][3] = rt_r;  ratio[1][4] = rm_r; ratio[1][5] = rl_r;
+      ratio[2][0] = rti_r; ratio[2][1] = rm_r; ratio[2][2] = rl_r; ratio[2][3] = rt_c;  ratio[2][4] = rm_c; ratio[2][5] = rl_c;
+      ratio[3][0] = rti_c; ratio[3][1] = rm_c; ratio[3][2] = rl_c; ratio[3][3] = rti_r; ratio[3][4] = rm_r; ratio[3][5] = rl_r;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 6; j++) rr[j] = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    float2 *dst = reinterpret_cast<float2 *>(lr_base + c * lr_stride);  // 24 bytes per symbol: 8-byte aligned
+    dst[0] = make_float2(ratio[c][0], ratio[c][1]);
+    dst[1] = make_float2(ratio[c][2], ratio[c][3]);
+    dst[2] = make_float2(ratio[c][4], ratio[c][5]);
+#pragma unroll
+    for (int j = 0; j < 6; j++) rr[j] |= (ratio[c][j] > 1.0f ? 1u : 0u) << c;  // inverted on purpose, see demap_symbol
+  }
+}
+
 template <int BITS, int NC, bool SYM>
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) {
   constexpr int Q = 1 << BITS;
@@ -875,7 +974,18 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
     }
     __syncthreads();
     float *lr0 = d.winner_only ? s_lr : d.lr + (size_t)f * NC * d.n_tx;
-    if constexpr (BITS == 6) {  // a quad of lanes per symbol
+    if (BITS == 6 && d.grid64) {  // separable grid: a thread per symbol, all candidates at once
+      if constexpr (BITS == 6) {
+        for (int i = tid; i < d.n_sym; i += DM_THREADS) {
+          unsigned int rr[6];
+          demap_symbol_grid64<NC>(yf[i], hb, d.inv_var, d.levels, lr0 + i * BITS, lr_stride, rr);
+          if (d.hard_metric) {
+#pragma unroll
+            for (int j = 0; j < 6; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
+          }
+        }
+      }
+    } else if constexpr (BITS == 6) {  // a quad of lanes per symbol
       const int t = tid & 3;
       for (int i0 = 0; i0 < d.n_sym; i0 += DM_THREADS / 4) {
         const int i = i0 + (tid >> 2);
