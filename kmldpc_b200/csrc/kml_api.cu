@@ -586,6 +586,20 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
     }
     sel = l.kstar.p;
     n_cand = 4;
+    // A chosen candidate whose metric decode already reached a zero syndrome needs no final decode: Decoder(max_iter) on the
+    // same input repeats those iterations and returns the same word and value (reuse_metric_kernel).  Off in the
+    // fixed-iteration timing mode, like skip_decode above.
+    if (decode_metric && c->opts.early_exit && c->opts.metric_iter <= c->opts.max_iter) {
+      KML_CUDA(c, cudaMemsetAsync(l.dec_queue_n.p, 0, 2 * sizeof(int32_t), s));
+      KML_LAUNCH(c, launch_reuse_metric(B, c->K, c->info_offset, c->words_n, l.kstar.p, l.metric.p, l.mret.p, l.cc_hat_packed.p,
+                                        l.uu_hat_packed.p, l.ret.p, l.dec_queue.p, l.dec_queue_n.p, s));
+      DecParams p = dec_params(c, l, B, l.lr.p, sel, n_cand, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
+      p.frame_idx = l.dec_queue.p; p.n_frames_dev = l.dec_queue_n.p; p.queue_cap = 0;
+      KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));
+      KML_LAUNCH(c, launch_extract_bits_queue(B, l.dec_queue.p, l.dec_queue_n.p, c->K, c->info_offset, c->words_n,
+                                              l.cc_hat_packed.p, l.uu_hat_packed.p, s));
+      return KML_OK;
+    }
   }
   DecParams p = dec_params(c, l, B, l.lr.p, sel, n_cand, 1, c->opts.max_iter, l.cc_hat_packed.p, l.ret.p, nullptr);
   KML_LAUNCH(c, dec_launch(c->dl, p, c->num_sms, s));

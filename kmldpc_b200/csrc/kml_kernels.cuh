@@ -193,6 +193,12 @@ struct DemapParams {
 cudaError_t launch_demap(const DemapParams &d, int num_sms, cudaStream_t s);
 
 // syndrome weight of packed decisions: bits [F][words_n] → metric[F] (float)
+// frames whose chosen candidate's metric decode converged take its result; the others are appended to queue (*queue_n zeroed by the caller)
+cudaError_t launch_reuse_metric(int B, int nbits, int bit_offset, int words_n, const int32_t *kstar, const float *metric,
+                                const int32_t *mret, const uint32_t *cand_bits, uint32_t *uu_hat, int32_t *ret, int32_t *queue,
+                                int32_t *queue_n, cudaStream_t s);
+cudaError_t launch_extract_bits_queue(int max_frames, const int32_t *queue, const int32_t *queue_n, int nbits, int bit_offset,
+                                      int src_words, const uint32_t *src, uint32_t *dst, cudaStream_t s);
 cudaError_t launch_syndrome_weight(int F, const uint32_t *bits, int words_n, int m_rows, const int32_t *row_ptr,
                                    const int32_t *col_idx, float *metric, cudaStream_t s);
 cudaError_t launch_abs_inplace(int n, float *v, cudaStream_t s);

@@ -1211,6 +1211,51 @@ __global__ void argmin4_kernel(int B, const float *metric, int32_t *kstar) {
   kstar[f] = best;
 }
 
+// Metric decodes that already hold the answer (5G-style metric: Decoder(metric_iter) on every candidate, kmcodec.cc:157-160).
+// If the CHOSEN candidate's metric decode reached a zero syndrome, the final Decoder(max_iter) call on the same input
+// (kmcodec.cc:70-71) repeats exactly those iterations and stops at the same one with the same decisions and the same
+// return value (metric_iter <= max_iter): its result is taken from the metric decode, and only the other frames are
+// queued for the final decoder.  One warp per frame.
+__global__ void reuse_metric_kernel(int B, int nbits, int bit_offset, int words_n, const int32_t *kstar, const float *metric,
+                                    const int32_t *mret, const uint32_t *cand_bits, uint32_t *uu_hat, int32_t *ret,
+                                    int32_t *queue, int32_t *queue_n) {
+  const int lane = threadIdx.x & 31, words = (nbits + 31) / 32;
+  for (int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < B; f += gridDim.x * (blockDim.x >> 5)) {
+    const int k = kstar[f];
+    if (metric[(size_t)f * 4 + k] != 0.0f) {  // not converged: the final decoder starts from scratch, like the reference
+      if (lane == 0) queue[atomicAdd(queue_n, 1)] = f;
+      continue;
+    }
+    const uint32_t *src = cand_bits + ((size_t)f * 4 + k) * words_n;
+    for (int w = lane; w < words; w += 32) {
+      const int q = bit_offset + 32 * w, wi = q >> 5, sh = q & 31;
+      uint32_t v = src[wi] >> sh;
+      if (sh && wi + 1 < words_n) v |= src[wi + 1] << (32 - sh);
+      const int valid = nbits - 32 * w;
+      if (valid < 32) v &= (1u << valid) - 1u;
+      uu_hat[(size_t)f * words + w] = v;
+    }
+    if (lane == 0) ret[f] = mret[(size_t)f * 4 + k];
+  }
+}
+
+// extract_bits_kernel for the frames of a device-side list
+__global__ void extract_bits_queue_kernel(const int32_t *queue, const int32_t *queue_n, int nbits, int bit_offset, int src_words,
+                                          const uint32_t *src, uint32_t *dst) {
+  const int words = (nbits + 31) / 32;
+  const long long total = (long long)(*queue_n) * words;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = queue[i / words], w = (int)(i % words);
+    const uint32_t *s = src + (size_t)f * src_words;
+    const int q = bit_offset + 32 * w, wi = q >> 5, sh = q & 31;
+    uint32_t v = s[wi] >> sh;
+    if (sh && wi + 1 < src_words) v |= s[wi + 1] << (32 - sh);
+    const int valid = nbits - 32 * w;
+    if (valid < 32) v &= (1u << valid) - 1u;
+    dst[(size_t)f * words + w] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ utilities
 __global__ void pack_bits_kernel(int F, int nbits, const int32_t *bits, uint32_t *packed) {
   const int words = (nbits + 31) / 32;
@@ -1457,6 +1502,23 @@ cudaError_t launch_abs_inplace(int n, float *v, cudaStream_t s) {
 cudaError_t launch_argmin4(int B, const float *metric, int32_t *kstar, cudaStream_t s) {
   if (B < 1) return cudaSuccess;
   argmin4_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, metric, kstar);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reuse_metric(int B, int nbits, int bit_offset, int words_n, const int32_t *kstar, const float *metric,
+                                const int32_t *mret, const uint32_t *cand_bits, uint32_t *uu_hat, int32_t *ret, int32_t *queue,
+                                int32_t *queue_n, cudaStream_t s) {
+  if (B < 1) return cudaSuccess;
+  reuse_metric_kernel<<<std::min((B + 7) / 8, 148 * 8), 256, 0, s>>>(B, nbits, bit_offset, words_n, kstar, metric, mret, cand_bits,
+                                                                  uu_hat, ret, queue, queue_n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract_bits_queue(int max_frames, const int32_t *queue, const int32_t *queue_n, int nbits, int bit_offset,
+                                      int src_words, const uint32_t *src, uint32_t *dst, cudaStream_t s) {
+  const long long total = (long long)max_frames * ((nbits + 31) / 32);
+  if (total < 1) return cudaSuccess;
+  extract_bits_queue_kernel<<<grid_for(total, 256), 256, 0, s>>>(queue, queue_n, nbits, bit_offset, src_words, src, dst);
   return cudaGetLastError();
 }
 
