@@ -69,6 +69,7 @@ struct kml_ctx {
   DevBuf<int32_t> row_ptr, col_idx;
   KmConst km{};  // fp64 constants of the k-means kernel (n_nb = 0: general kernel)
   int rot_symmetric = 0, rot_perm[3][64];  // s_k e^{j c pi/2} = s_{rot_perm[c-1][k]} for every k (else rot_symmetric = 0)
+  uint32_t q4_code = 0xFFFFFFFFu;          // 4 points: partition code of demap_symbol_q4 (all ones: general demapper)
   int grid64 = 0;                          // the constellation is the square Gray grid compiled into demap_symbol_grid64
   float grid_levels[8] = {};
   DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
@@ -547,6 +548,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
   d.grid64 = c->grid64;
   std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
+  d.q4_code = c->q4_code;
   const int32_t *sel = nullptr;
   int n_cand = 1;
   if (c->opts.known_h) {
@@ -699,6 +701,26 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
           if (hit < 0) c->rot_symmetric = 0;
           else { used[hit] = 1; c->rot_perm[cc - 1][k] = hit; }
         }
+      }
+    }
+    {  // 4 points: for every (candidate c, bit j) the pair of point indices whose probabilities add up to P(bit = 0)
+       // (demap_symbol_q4's partition code); candidate c reads point perm_c[k] under label k
+      c->q4_code = 0xFFFFFFFFu;
+      const char *e4 = knob("KML_DEMAP_NO_Q4");  // shipped fallback (announced on stderr): the general demapper
+      if (c->Q == 4 && !(e4 && atoi(e4))) {
+        uint32_t code = 0;
+        for (int cc = 0; cc < 4; cc++)
+          for (int j = 0; j < 2; j++) {
+            int z0[2], n0 = 0;
+            for (int k = 0; k < 4; k++)
+              if (((k >> (1 - j)) & 1) == 0) z0[n0++] = (cc == 0 || !c->rot_symmetric) ? k : c->rot_perm[cc - 1][k];
+            const int a = std::min(z0[0], z0[1]), b = std::max(z0[0], z0[1]);
+            int idx = 0;
+            if (a == 0 && b == 1) idx = 0; else if (a == 2 && b == 3) idx = 1; else if (a == 0 && b == 2) idx = 2;
+            else if (a == 1 && b == 3) idx = 3; else if (a == 0 && b == 3) idx = 4; else idx = 5;
+            code |= (uint32_t)idx << (3 * (2 * cc + j));
+          }
+        c->q4_code = code;
       }
     }
     {  // 64 points on a square grid with the Gray labelling demap_symbol_grid64 has compiled in (link_kernels.cu): levels
@@ -987,6 +1009,7 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
   d.grid64 = c->grid64;
   std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
+  d.q4_code = c->q4_code;
   return d;
 }
 

@@ -184,6 +184,8 @@ struct DemapParams {
   // 64 points that form the square Gray-mapped grid compiled into demap_symbol_grid64 (host check): the 8 levels of an axis
   int grid64;
   float levels[8];
+  // 4 points: which 2 | 2 partition each (candidate, bit) reads (demap_symbol_q4); 0xFFFFFFFF: general path
+  uint32_t q4_code;
   int skip_decode, words_n;
   uint32_t *out_bits;
   int32_t *out_ret;

@@ -745,6 +745,66 @@ __device__ __forceinline__ void demap_symbol(const float2 yy, const float2 *s_pt
   }
 }
 
+// 4 points with quarter-turn symmetry (QPSK, 4PSK): candidate c's probabilities are candidate 0's in another order, and a
+// bit splits the four points 2 | 2 — one of the three partitions {01|23}, {02|13}, {03|12}, in one of two orientations.
+// Which one each (candidate, bit) reads is a property of the constellation file; CODE holds it (3 bits per entry 2c + j:
+// 0 = 01|23, 1 = 23|01, 2 = 02|13, 3 = 13|02, 4 = 03|12, 5 = 12|03), found on the host from the label permutations
+// (kml_api.cu) and compiled in for the two shipped files.  Four exponentials, at most six ratios, everything in registers —
+// no staging through shared memory, no permutation look-ups.  Same arithmetic as demap_symbol otherwise.
+constexpr uint32_t kQ4CodeQpsk = 0u | (2u << 3) | (3u << 6) | (0u << 9) | (1u << 12) | (3u << 15) | (2u << 18) | (1u << 21);
+constexpr uint32_t kQ4Code4psk = 0u | (2u << 3) | (5u << 6) | (3u << 9) | (1u << 12) | (2u << 15) | (4u << 18) | (3u << 21);
+template <uint32_t CODE, int NC>
+__host__ __device__ constexpr bool q4_uses(int idx) {
+  for (int e = 0; e < 2 * NC; e++)
+    if (((CODE >> (3 * e)) & 7u) == (uint32_t)idx) return true;
+  return false;
+}
+template <int NC, uint32_t CODE>
+__device__ __forceinline__ void demap_symbol_q4(const float2 yy, const float2 *s_pts, float rscale, float *lr_base, size_t lr_stride,
+                                                unsigned int (&rr)[2]) {
+  const float2 ny = make_float2(-yy.x * rscale, -yy.y * rscale);
+  float p[4], mx = -3.0e38f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    p[k] = -dm_dist2(s_pts[k], ny);
+    mx = fmaxf(mx, p[k]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    p[k] = dm_ex2(p[k] - mx);
+    sum += p[k];
+  }
+  const float inv = dm_rcp(sum);
+#pragma unroll
+  for (int k = 0; k < 4; k++) p[k] = fmaxf(p[k] * inv, kSmallProbF);
+  float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto ratio = [](float z0, float z1) { return fminf(fmaxf(z0 * dm_rcp(z1), kLrMin), kLrMax); };
+  if constexpr (q4_uses<CODE, NC>(0) || q4_uses<CODE, NC>(1)) {
+    const float a = p[0] + p[1], b = p[2] + p[3];
+    if constexpr (q4_uses<CODE, NC>(0)) r[0] = ratio(a, b);
+    if constexpr (q4_uses<CODE, NC>(1)) r[1] = ratio(b, a);
+  }
+  if constexpr (q4_uses<CODE, NC>(2) || q4_uses<CODE, NC>(3)) {
+    const float a = p[0] + p[2], b = p[1] + p[3];
+    if constexpr (q4_uses<CODE, NC>(2)) r[2] = ratio(a, b);
+    if constexpr (q4_uses<CODE, NC>(3)) r[3] = ratio(b, a);
+  }
+  if constexpr (q4_uses<CODE, NC>(4) || q4_uses<CODE, NC>(5)) {
+    const float a = p[0] + p[3], b = p[1] + p[2];
+    if constexpr (q4_uses<CODE, NC>(4)) r[4] = ratio(a, b);
+    if constexpr (q4_uses<CODE, NC>(5)) r[5] = ratio(b, a);
+  }
+  rr[0] = rr[1] = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    const float r0 = r[(CODE >> (3 * (2 * c))) & 7u], r1 = r[(CODE >> (3 * (2 * c + 1))) & 7u];
+    *reinterpret_cast<float2 *>(lr_base + c * lr_stride) = make_float2(r0, r1);
+    rr[0] |= (r0 > 1.0f ? 1u : 0u) << c;  // inverted on purpose, see demap_symbol
+    rr[1] |= (r1 > 1.0f ? 1u : 0u) << c;
+  }
+}
+
 // 64-point constellations WITHOUT the separable structure demap_symbol_grid64 needs (or under KML_DEMAP_NO_GRID=1): FOUR
 // lanes share a symbol, 16 points each (lane t of the quad owns the points whose two
 // top label bits are t).  One thread per symbol needs all 64 probabilities live (126 registers → 16 warps per SM, the
@@ -930,7 +990,7 @@ __device__ __forceinline__ void demap_symbol_grid64(const float2 yy, const float
   }
 }
 
-template <int BITS, int NC, bool SYM>
+template <int BITS, int NC, bool SYM, uint32_t Q4 = 0xFFFFFFFFu>  // Q4 != all-ones: BITS == 2, the partition code of demap_symbol_q4
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) {
   constexpr int Q = 1 << BITS;
   constexpr int MAXS = 6;  // symbols a thread keeps in flight (n_sym <= MAXS * DM_THREADS on the fast path)
@@ -1004,7 +1064,8 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
       const int i = u * DM_THREADS + tid;
       if (i < d.n_sym) {
         unsigned int rr[BITS];
-        demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+        if constexpr (Q4 != 0xFFFFFFFFu) demap_symbol_q4<NC, Q4>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
+        else demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
         if (d.hard_metric) {
 #pragma unroll
           for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -1013,7 +1074,8 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
     }
     for (int i = MAXS * DM_THREADS + tid; BITS != 6 && i < d.n_sym; i += DM_THREADS) {  // very long frames
       unsigned int rr[BITS];
-      demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+      if constexpr (Q4 != 0xFFFFFFFFu) demap_symbol_q4<NC, Q4>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
+      else demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
       if (d.hard_metric) {
 #pragma unroll
         for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -1448,6 +1510,20 @@ cudaError_t launch_kmeans(int B, const void *y, int y_is_f64, int n_sym, const f
 
 template <int BITS>
 static cudaError_t launch_demap_bits(const DemapParams &d, int grid, int smem, cudaStream_t s) {
+  if constexpr (BITS == 2) {  // 4 points: the compiled partition codes (demap_symbol_q4); anything else takes the general path
+    if (d.n_cand == 4 && d.symmetric && d.q4_code == kQ4CodeQpsk) {
+      demap_kernel<2, 4, false, kQ4CodeQpsk><<<grid, DM_THREADS, smem, s>>>(d);
+      return cudaGetLastError();
+    }
+    if (d.n_cand == 4 && d.symmetric && d.q4_code == kQ4Code4psk) {
+      demap_kernel<2, 4, false, kQ4Code4psk><<<grid, DM_THREADS, smem, s>>>(d);
+      return cudaGetLastError();
+    }
+    if (d.n_cand == 1 && d.q4_code != 0xFFFFFFFFu) {  // (candidate 0 reads 01|23 and 02|13 whatever the file)
+      demap_kernel<2, 1, false, kQ4CodeQpsk><<<grid, DM_THREADS, smem, s>>>(d);
+      return cudaGetLastError();
+    }
+  }
   if (d.n_cand == 4) {
     constexpr bool kCanSym = BITS <= 5;  // (64 points: the quad-of-lanes path keeps one softmax per candidate, see there)
     const bool sym = kCanSym && d.symmetric;
