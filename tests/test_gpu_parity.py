@@ -824,10 +824,13 @@ def test_decoder_kernel_selection():
 
 
 @pytest.mark.parametrize("knob,name,frames", [("KML_DEC_PLANAR", "peg2304_4psk_6db", 80), ("KML_DEC_NO_QC", "5g_16qam_gray_10db", 60),
-                                              ("KML_DEC_T8064=672", "peg8064_64qam_20db", 12)])
+                                              ("KML_DEC_T8064=672", "peg8064_64qam_20db", 12),
+                                              ("KML_DEMAP_NO_GRID", "peg8064_64qam_20db", 12),
+                                              ("KML_DEMAP_NO_Q4", "peg2304_qpsk_10db", 60), ("KML_DEMAP_NO_Q4", "peg2304_4psk_6db", 60)])
 def test_decoder_fallback_paths_stay_correct(monkeypatch, knob, name, frames):
     """The run-time knobs select kernels that are still shipped (planar layout, run-time-graph kernel on the 5G matrix, the
-    exact 672-thread PEG8064 tiling): each must reproduce the reference as well.  (A/B and timing-ablation variants exist
+    exact 672-thread PEG8064 tiling, the general demappers behind the 64QAM grid and the 4-point paths): each must reproduce
+    the reference as well.  (A/B and timing-ablation variants exist
     only in a -DKML_TUNING build.)"""
     key, _, val = knob.partition("=")
     monkeypatch.setenv(key, val or "1")
