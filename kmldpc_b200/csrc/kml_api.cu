@@ -70,7 +70,7 @@ struct kml_ctx {
   KmConst km{};  // fp64 constants of the k-means kernel (n_nb = 0: general kernel)
   int rot_symmetric = 0, rot_perm[3][64];  // s_k e^{j c pi/2} = s_{rot_perm[c-1][k]} for every k (else rot_symmetric = 0)
   uint32_t q4_code = 0xFFFFFFFFu;          // 4 points: partition code of demap_symbol_q4 (all ones: general demapper)
-  int grid64 = 0;                          // the constellation is the square Gray grid compiled into demap_symbol_grid64
+  int grid64 = 0, grid16 = 0;              // the constellation is the square Gray grid compiled into demap_symbol_grid64 / grid16
   float grid_levels[8] = {};
   DevBuf<uint16_t> vn_addr, vn_addr_rm, vn_addr_g, col_ell;
   DevBuf<uint32_t> vn_items, cn_items;
@@ -546,7 +546,7 @@ int receive_on_lane(kml_ctx *c, Lane &l, cudaStream_t s, int B, const void *y, i
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   d.symmetric = c->rot_symmetric;
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
-  d.grid64 = c->grid64;
+  d.grid64 = c->grid64; d.grid16 = c->grid16;
   std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
   d.q4_code = c->q4_code;
   const int32_t *sel = nullptr;
@@ -754,6 +754,37 @@ extern "C" int kml_create(kml_ctx **out, int device, const kml_code *code, const
         if (ok) {
           c->grid64 = 1;
           for (int i = 0; i < 8; i++) c->grid_levels[i] = (float)lv[i];
+        }
+      }
+    }
+    {  // 16 points on the 4 x 4 Gray grid demap_symbol_grid16 has compiled in: label bits (MSB first) j < 2, j in {1,2}, i < 2,
+       // i in {1,2} for the point at (in-phase level i, quadrature level j)
+      c->grid16 = 0;
+      const char *e = knob("KML_DEMAP_NO_GRID");
+      if (c->Q == 16 && c->rot_symmetric && !(e && atoi(e))) {
+        std::vector<double> lv;
+        for (int k = 0; k < 16; k++) {
+          bool seen = false;
+          for (double v : lv) seen = seen || std::fabs(v - modem->points[2 * k]) < 1e-9;
+          if (!seen) lv.push_back(modem->points[2 * k]);
+        }
+        std::sort(lv.begin(), lv.end());
+        bool ok = lv.size() == 4;
+        for (int i = 0; ok && i < 4; i++) ok = std::fabs(lv[i] + lv[3 - i]) < 1e-9;
+        auto level_of = [&](double v) {
+          for (int i = 0; i < (int)lv.size(); i++)
+            if (std::fabs(lv[i] - v) < 1e-9) return i;
+          return -1;
+        };
+        for (int k = 0; ok && k < 16; k++) {
+          const int i = level_of(modem->points[2 * k]), j = level_of(modem->points[2 * k + 1]);
+          if (i < 0 || j < 0) { ok = false; break; }
+          const int label = ((j < 2) << 3) | ((j == 1 || j == 2) << 2) | ((i < 2) << 1) | (i == 1 || i == 2);
+          ok = label == k;
+        }
+        if (ok) {
+          c->grid16 = 1;
+          for (int i = 0; i < 4; i++) c->grid_levels[i] = (float)lv[i];
         }
       }
     }
@@ -1007,7 +1038,7 @@ DemapParams demap_params(kml_ctx *c, Lane &l, int B, double var, int n_cand, int
   d.lr = l.lr.p; d.metric = l.metric.p; d.kstar = l.kstar.p;
   d.symmetric = c->rot_symmetric;
   std::memcpy(d.perm, c->rot_perm, sizeof d.perm);
-  d.grid64 = c->grid64;
+  d.grid64 = c->grid64; d.grid16 = c->grid16;
   std::memcpy(d.levels, c->grid_levels, sizeof d.levels);
   d.q4_code = c->q4_code;
   return d;

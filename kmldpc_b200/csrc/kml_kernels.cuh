@@ -182,7 +182,7 @@ struct DemapParams {
   int symmetric;
   int perm[3][64];
   // 64 points that form the square Gray-mapped grid compiled into demap_symbol_grid64 (host check): the 8 levels of an axis
-  int grid64;
+  int grid64, grid16;  // (grid16: the 4 x 4 Gray grid of demap_symbol_grid16, levels[0..3])
   float levels[8];
   // 4 points: which 2 | 2 partition each (candidate, bit) reads (demap_symbol_q4); 0xFFFFFFFF: general path
   uint32_t q4_code;

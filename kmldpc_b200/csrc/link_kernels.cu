@@ -990,6 +990,70 @@ __device__ __forceinline__ void demap_symbol_grid64(const float2 yy, const float
   }
 }
 
+// The same separation for 16 points (4 x 4 grid, the shipped 4bit_16QAM_Gray.txt): 8 exponentials for all candidates.  Label layout
+// compiled in (levels ascending, MSB first): bit 0 = quadrature level < 2, bit 1 = quadrature level in {1, 2}, bits 2, 3 the
+// same of the in-phase level.  (phi1 / phi2 do not split into an in-phase and a quadrature half: general path.)
+template <int NC>
+__device__ __forceinline__ void demap_symbol_grid16(const float2 yy, const float2 hb, float inv_var, const float (&lv)[8],
+                                                    float *lr_base, size_t lr_stride, unsigned int (&rr)[4]) {
+  const float h2 = fmaf(hb.x, hb.x, hb.y * hb.y);
+  const bool live = h2 > 1.0e-30f;
+  const float ih2 = live ? dm_rcp(h2) : 0.0f;
+  const float zr = (yy.x * hb.x + yy.y * hb.y) * ih2, zi = (yy.y * hb.x - yy.x * hb.y) * ih2;
+  const float g = live ? h2 * inv_var * 1.4426950408889634f : 0.0f;
+  float a[4], b[4], ma = -3.0e38f, mb = -3.0e38f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float dr = lv[i] - zr, di = lv[i] - zi;
+    a[i] = -g * dr * dr;
+    b[i] = -g * di * di;
+    ma = fmaxf(ma, a[i]);
+    mb = fmaxf(mb, b[i]);
+  }
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    a[i] = dm_ex2(a[i] - ma);
+    b[i] = dm_ex2(b[i] - mb);
+    sa += a[i];
+    sb += b[i];
+  }
+  const float ia = dm_rcp(sa), ib = dm_rcp(sb);
+  float R[4] = {0.f, 0.f, 0.f, 0.f}, C[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    a[i] *= ia;
+    b[i] *= ib;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float t = fmaxf(a[i] * b[j], kSmallProbF);  // the reference's per-point clip
+      R[i] += t;
+      C[j] += t;
+    }
+  const float rlo = R[0] + R[1], rhi = R[2] + R[3], rout = R[0] + R[3], rin = R[1] + R[2];
+  const float clo = C[0] + C[1], chi = C[2] + C[3], cout = C[0] + C[3], cin = C[1] + C[2];
+  const float rti_r = grid_ratio(rhi, rlo), rm_r = grid_ratio(rout, rin), rti_c = grid_ratio(chi, clo), rm_c = grid_ratio(cout, cin);
+  float ratio[NC][4];
+  ratio[0][0] = rti_c; ratio[0][1] = rm_c; ratio[0][2] = rti_r; ratio[0][3] = rm_r;
+  if constexpr (NC == 4) {
+    const float rt_r = grid_ratio(rlo, rhi), rt_c = grid_ratio(clo, chi);
+    ratio[1][0] = rt_r;  ratio[1][1] = rm_r; ratio[1][2] = rti_c; ratio[1][3] = rm_c;
+    ratio[2][0] = rt_c;  ratio[2][1] = rm_c; ratio[2][2] = rt_r;  ratio[2][3] = rm_r;
+    ratio[3][0] = rti_r; ratio[3][1] = rm_r; ratio[3][2] = rt_c;  ratio[3][3] = rm_c;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) rr[j] = 0;
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    *reinterpret_cast<float4 *>(lr_base + c * lr_stride) = make_float4(ratio[c][0], ratio[c][1], ratio[c][2], ratio[c][3]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) rr[j] |= (ratio[c][j] > 1.0f ? 1u : 0u) << c;  // inverted on purpose, see demap_symbol
+  }
+}
+
 template <int BITS, int NC, bool SYM, uint32_t Q4 = 0xFFFFFFFFu>  // Q4 != all-ones: BITS == 2, the partition code of demap_symbol_q4
 __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) {
   constexpr int Q = 1 << BITS;
@@ -1065,7 +1129,10 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
       if (i < d.n_sym) {
         unsigned int rr[BITS];
         if constexpr (Q4 != 0xFFFFFFFFu) demap_symbol_q4<NC, Q4>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
-        else demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+        else if constexpr (BITS == 4) {
+          if (d.grid16) demap_symbol_grid16<NC>(yreg[u], hb, d.inv_var, d.levels, lr0 + i * BITS, lr_stride, rr);
+          else demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+        } else demap_symbol<BITS, NC, SYM>(yreg[u], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
         if (d.hard_metric) {
 #pragma unroll
           for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
@@ -1075,7 +1142,10 @@ __global__ void __launch_bounds__(DM_THREADS) demap_kernel(const DemapParams d) 
     for (int i = MAXS * DM_THREADS + tid; BITS != 6 && i < d.n_sym; i += DM_THREADS) {  // very long frames
       unsigned int rr[BITS];
       if constexpr (Q4 != 0xFFFFFFFFu) demap_symbol_q4<NC, Q4>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr);
-      else demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+      else if constexpr (BITS == 4) {
+        if (d.grid16) demap_symbol_grid16<NC>(yf[i], hb, d.inv_var, d.levels, lr0 + i * BITS, lr_stride, rr);
+        else demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
+      } else demap_symbol<BITS, NC, SYM>(yf[i], s_pts, rscale, lr0 + i * BITS, lr_stride, rr, stage, d);
       if (d.hard_metric) {
 #pragma unroll
         for (int j = 0; j < BITS; j++) s_rr[d.punct + i * BITS + j] = (unsigned char)rr[j];
