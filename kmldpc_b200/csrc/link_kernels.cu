@@ -450,6 +450,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
                    int32_t *passes_out, float2 *y32_out) {
   static_assert(MAXNB % 2 == 0 && SPL <= 64, "neighbours are tested in pairs; one mask bit per sample");
   constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ float2 km_copy[];  // [KMW_WARPS][SPL][32], fp32 input only
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * KMW_WARPS + (threadIdx.x >> 5), wstride = gridDim.x * KMW_WARPS;
   const float2 s0f = make_float2((float)kc.s0r, (float)kc.s0i);
@@ -464,6 +465,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
       return F64IN ? km_exact_load(yd + j * 32 + lane) : km_widen(v);
     };
     float2 ys[SPL];
+    float2 *ysm = km_copy + (size_t)(threadIdx.x >> 5) * SPL * 32 + lane;  // fp32 input: a copy that CAN be indexed at run time
     unsigned long long best = 0ull;
     KmMask<SPL> valid;
 #pragma unroll
@@ -476,6 +478,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
           if (y32_out) y32_out[(size_t)f * n + i] = ys[j];  // the fp32 copy the demapper reads
         } else {
           ys[j] = yf[i];
+          ysm[j * 32] = ys[j];
         }
         valid.set(j, true);
         // |y|^2 is monotone in |y|; ties → smallest index (max_element returns the first maximum)
@@ -597,27 +600,22 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
       if (__any_sync(FULL, chg.any())) {  // samples that entered / left cluster 0 since the last pass
         double dr = 0.0, di = 0.0;
         int dc = 0;
-        constexpr int G = 6;  // samples per group: their (fp64-input: global) reads are in flight together
-#pragma unroll
-        for (int j0 = 0; j0 < SPL; j0 += G) {
-          bool any = false;
-#pragma unroll
-          for (int t = 0; t < G; t++)
-            if (j0 + t < SPL) any = any || chg.get(j0 + t);
-          if (!__any_sync(FULL, any)) continue;
-          double2 v[G];
-#pragma unroll
-          for (int t = 0; t < G; t++)
-            if (j0 + t < SPL) v[t] = valid.get(j0 + t) ? exact(j0 + t, ys[j0 + t]) : make_double2(0.0, 0.0);
-#pragma unroll
-          for (int t = 0; t < G; t++)
-            if (j0 + t < SPL && chg.get(j0 + t)) {
-              const bool in = now.get(j0 + t);
-              dr += in ? v[t].x : -v[t].x;
-              di += in ? v[t].y : -v[t].y;
-              dc += in ? 1 : -1;
-            }
-        }
+        // A lane has a handful of changed samples at most: it walks the set bits of its mask (ascending, the order the sums
+        // have always been taken in) and fetches each sample by its run-time index — from the shared-memory copy for fp32
+        // input (the registers cannot be indexed), from global memory for fp64 input.
+        auto walk = [&](uint32_t bits, uint32_t in_bits, int base) {
+          while (bits) {
+            const int j = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const double2 v = F64IN ? km_exact_load(yd + (base + j) * 32 + lane) : km_widen(ysm[(base + j) * 32]);
+            const bool in = (in_bits >> j) & 1u;
+            dr += in ? v.x : -v.x;
+            di += in ? v.y : -v.y;
+            dc += in ? 1 : -1;
+          }
+        };
+        walk(chg.lo, now.lo, 0);
+        if (SPL > 32) walk(chg.hi, now.hi, 32);
         set_re += km_warp_sum(dr);
         set_im += km_warp_sum(di);
 #pragma unroll
@@ -1538,7 +1536,12 @@ static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmC
                                       double2 *hhat64, int32_t *passes, float2 *y32_out, int num_sms, cudaStream_t s) {
   const int spl = (n_sym + 31) / 32;
   const int grid = std::min((B + KMW_WARPS - 1) / KMW_WARPS, num_sms * 16);
-#define KMW(SPL, NB) kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, 0, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out)
+#define KMW(SPL, NB)                                                                                                          \
+  do {                                                                                                                        \
+    const int smem = F64IN ? 0 : KMW_WARPS * SPL * 32 * (int)sizeof(float2);                                                  \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kmeans_warp_kernel<SPL, NB, F64IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, smem, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out);      \
+  } while (0)
   if (kc.n_nb <= 2) {
     if (spl <= 16) KMW(16, 2); else if (spl <= 24) KMW(24, 2); else if (spl <= 36) KMW(36, 2); else if (spl <= 48) KMW(48, 2); else KMW(64, 2);
   } else if (kc.n_nb <= 4) {
