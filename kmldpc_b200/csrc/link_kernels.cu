@@ -1539,7 +1539,7 @@ static cudaError_t launch_kmeans_warp(int B, const void *y, int n_sym, const KmC
 #define KMW(SPL, NB)                                                                                                          \
   do {                                                                                                                        \
     const int smem = F64IN ? 0 : KMW_WARPS * SPL * 32 * (int)sizeof(float2);                                                  \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kmeans_warp_kernel<SPL, NB, F64IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    if (smem > 40 * 1024) cudaFuncSetAttribute(kmeans_warp_kernel<SPL, NB, F64IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     kmeans_warp_kernel<SPL, NB, F64IN><<<grid, KMW_WARPS * 32, smem, s>>>(B, y, n_sym, kc, iters, hhat, hhat64, passes, y32_out);      \
   } while (0)
   if (kc.n_nb <= 2) {
