@@ -195,3 +195,26 @@ def test_kmeans_sums_are_never_reset():
             hh = y[a == 0].mean() / pts[0] if np.any(a == 0) else hh
         worst = max(worst, abs(hh - cl[0] / pts[0]) / abs(cl[0] / pts[0]))
     assert worst > 1e-3, worst
+
+
+def test_minsum_statements_agree_on_converged_frames():
+    """The two numpy statements behind the throughput-mode decoders (oracle/minsum_ref.py: flooding and layered min-sum) are
+    independent of each other and of the CUDA kernels; on the reference's own 5G frames they must reach the same codeword
+    wherever both converge — the one the reference's sum-product decoder reaches, when it converges too — and the layered
+    schedule must not need more iterations.  Also pins the quasi-cyclic structure the layered decoder is built on."""
+    from oracle import minsum_ref
+    link = ko.Link("5GLDPCBG2a3_R12_K960.txt", "4bit_16QAM_Gray.txt", is_5g=True)
+    g = ko.Lcg(17)
+    rs = [link.frame(g, 12.0, full=True) for _ in range(16)]
+    ex = link.code.export(with_enc=False)
+    Z, layers = minsum_ref.qc_structure(ex["row_ptr"], ex["col_idx"], len(ex["row_ptr"]) - 1, link.code.N)
+    assert Z == 96 and [len(l) for l in layers] == [8, 10, 8, 10, 4, 6, 6, 6, 4, 5, 5, 5]
+    llr = np.stack([np.log(np.clip(r.p0, 1e-12, 1 - 1e-12) / (1 - np.clip(r.p0, 1e-12, 1 - 1e-12))) for r in rs]).astype(np.float32)
+    ret_f, cc_f = minsum_ref.decode(ex["row_ptr"], ex["col_idx"], link.code.N, link.code.two_z, llr, 50, 50, alpha=0.8)
+    ret_l, cc_l = minsum_ref.decode_layered(layers, Z, link.code.N, link.code.two_z, llr, 50, 50, alpha=0.8)
+    both = (ret_f < 50) & (ret_l < 50)
+    assert both.sum() >= 8 and np.array_equal(cc_f[both], cc_l[both])
+    spa = np.array([link.code.parity_check(r.cc_hat) == 0 for r in rs])
+    ref_cc = np.stack([r.cc_hat for r in rs])
+    assert np.array_equal(cc_l[both & spa], ref_cc[both & spa])
+    assert (ret_l[both] - 1).sum() <= ret_f[both].sum()
