@@ -486,7 +486,7 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
         const unsigned long long key = ((unsigned long long)__float_as_uint(a2) << 32) | (uint32_t)(0x7fffffff - i);
         best = key > best ? key : best;
       } else {
-        ys[j] = make_float2(0.f, 0.f);  // masked out of the membership below
+        ys[j] = make_float2(3.0e15f, 1.0e15f);  // masked out of the membership below; far from every boundary (never "unsure")
       }
     }
 #pragma unroll
@@ -558,19 +558,28 @@ kmeans_warp_kernel(int B, const void *y_in, int n, const KmConst kc, int iters, 
       // band is >= 5x that bound
       const float cmax = sqrtf(cmax2);
       const float tau = 4.0e-6f * cmax * (ymax_l1 + cmax);
+      // Membership = "every d_t <= 0" (first minimum wins ties → cluster 0 keeps them).  Per sample the filter keeps just the
+      // SIGN BIT of max_t d_t (shifted into a word) and the smallest |max_t d_t| of the lane: a zero or a value inside the
+      // band makes the pass "unsure" and the membership is then decided in fp64 below, so the sign bit is all fp32 has to say.
       KmMask<SPL> now;
-      bool unsure = false;
+      uint32_t sgn_a = 0, sgn_b = 0;
+      float closest = 3.0e38f;
 #pragma unroll
       for (int j = 0; j < SPL; j++) {
-        float dmax = -3.0e38f;
+        float dmax;
 #pragma unroll
         for (int t = 0; t < MAXNB / 2; t++) {
           const float2 v = km_fma2(ax[t], make_float2(ys[j].x, ys[j].x), km_fma2(ay[t], make_float2(ys[j].y, ys[j].y), nth[t]));
-          dmax = fmaxf(dmax, fmaxf(v.x, v.y));
+          dmax = t == 0 ? fmaxf(v.x, v.y) : fmaxf(dmax, fmaxf(v.x, v.y));
         }
-        now.set(j, dmax <= 0.0f);  // first minimum wins ties → cluster 0 keeps them
-        unsure = unsure || (fabsf(dmax) <= tau);
+        if (j < 32) sgn_a = __funnelshift_l(__float_as_uint(dmax), sgn_a, 1);
+        else sgn_b = __funnelshift_l(__float_as_uint(dmax), sgn_b, 1);
+        closest = fminf(closest, fabsf(dmax));
       }
+      now.lo = __brev(sgn_a) >> (SPL >= 32 ? 0 : 32 - SPL);  // sample j of the lane at bit j
+      (void)sgn_b;
+      if constexpr (SPL > 32) now.hi = __brev(sgn_b) >> (SPL >= 64 ? 0 : 64 - SPL);
+      const bool unsure = closest <= tau;
       if (__any_sync(FULL, unsure)) {  // rare: this pass's membership in fp64 from the fp64 estimate
         double ar[MAXNB], ai[MAXNB], th[MAXNB];
         const double h2 = hr * hr + hi * hi;
